@@ -1,0 +1,165 @@
+/*
+ * sis_b200.h — C-ABI of the B200-native Synthesis-in-Style hot path (libsis_b200.so).
+ *
+ * Plain pointers and sizes only; no torch types.  Every pointer named `d_*` / documented as "device" is a
+ * CUDA device pointer on the current device; `stream` is a `cudaStream_t` passed as `void*` (0 = legacy
+ * default stream).  All launches are asynchronous on `stream`; nothing synchronises unless stated.
+ * Every function returns 0 on success and a non-zero `sis_status` otherwise; `sis_last_error()` gives the
+ * message of the last failure on the calling thread.  Paths are relative to /root/reference
+ * (`scf/` = `stylegan_code_finder/`).
+ *
+ * The library is sm_100a only and has no CPU fallback.
+ */
+#ifndef SIS_B200_H
+#define SIS_B200_H
+
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define SIS_API __attribute__((visibility("default")))
+#else
+#define SIS_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    SIS_OK = 0,
+    SIS_ERR_INVALID = 1,   /* bad argument (the reference would TORCH_CHECK / produce garbage) */
+    SIS_ERR_CUDA = 2,      /* a CUDA runtime / driver call failed */
+    SIS_ERR_UNSUPPORTED = 3,
+    SIS_ERR_STATE = 4      /* object used before it was prepared, missing weights, ... */
+} sis_status;
+
+typedef enum { SIS_F32 = 0, SIS_F16 = 1, SIS_F64 = 2 } sis_dtype;
+
+SIS_API const char* sis_last_error(void);
+SIS_API int sis_version(void);
+/* Number of kernel launches issued by this library on the calling process since load (all threads). */
+SIS_API uint64_t sis_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Op 1 — replaces pybind `fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)`
+ *   scf/networks/stylegan2/op/fused_bias_act.cpp:11-20 -> fused_bias_act_kernel.cu:18-98.
+ * y[i] = act(x[i] + b[(i / step_b) % size_b]) * scale;  act*10+grad: 30 lrelu, 31 lrelu gated by ref,
+ * 12/32 zero, everything else linear.  size_b == 0 => no bias; d_ref == NULL => no ref.
+ * x/out/ref: `size_x` elements of `dtype`; bias: `size_b` elements of `dtype`.
+ * ------------------------------------------------------------------------------------------------------- */
+SIS_API int sis_fused_bias_act(void* d_out, const void* d_x, const void* d_bias, const void* d_ref, int dtype,
+                       int64_t size_x, int64_t step_b, int64_t size_b, int act, int grad, float alpha,
+                       float scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Op 2 — replaces pybind `upfirdn2d.upfirdn2d(input[major,H,W,minor], kernel[kh,kw], up_x, up_y, down_x,
+ * down_y, pad_x0, pad_x1, pad_y0, pad_y1)`  scf/networks/stylegan2/op/upfirdn2d.cpp:12-23 ->
+ * upfirdn2d_kernel.cu:52-272.  Output is [major, out_h, out_w, minor] with
+ * out = (in*up + pad0 + pad1 - k + down) / down  (upfirdn2d_kernel.cu:168-169); compute it with
+ * sis_upfirdn2d_out_size.  Unlike the reference (which silently returns uninitialised memory when no
+ * mode matches, upfirdn2d_kernel.cu:172-226) every (up, down, kernel<=32x32) combination is computed.
+ * The reference dispatches on the input dtype and reads the taps as that dtype; `d_kernel` is `dtype` too.
+ * ------------------------------------------------------------------------------------------------------- */
+SIS_API int sis_upfirdn2d_out_size(int in_size, int up, int down, int pad0, int pad1, int ksize);
+SIS_API int sis_upfirdn2d(void* d_out, const void* d_x, const void* d_kernel, int dtype, int64_t major, int in_h,
+                  int in_w, int minor, int kernel_h, int kernel_w, int up_x, int up_y, int down_x, int down_y,
+                  int pad_x0, int pad_x1, int pad_y0, int pad_y1, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Generator — replaces `Generator.forward` scf/networks/stylegan2/model.py:479-561 and everything it calls
+ * (PixelNorm :15-20, EqualLinear :133-162, ModulatedConv2d :237-278, Blur :76-92, NoiseInjection :287-292,
+ * StyledConv :336-342, ToRGB :355-364, ConstantInput :295-305), `mean_latent` :468-474.
+ *
+ * Lifecycle: create -> set_param for every state-dict tensor (keys of SURVEY.md §8b, fp32 device
+ * pointers; the library COPIES / repacks them at prepare time, so the caller's tensors may change
+ * afterwards — call prepare again to pick the changes up) -> prepare -> forward*.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct sis_generator sis_generator;
+
+typedef enum {
+    SIS_PRECISION_FP32 = 0,    /* fp32 FMA implicit GEMM on CUDA cores (bit-closest to the reference) */
+    SIS_PRECISION_BF16X3 = 1   /* tcgen05 bf16 split precision: hi*hi + hi*lo + lo*hi, fp32 TMEM accumulate */
+} sis_precision;
+
+SIS_API int sis_generator_create(int size, int style_dim, int n_mlp, int channel_multiplier, sis_generator** out);
+SIS_API int sis_generator_destroy(sis_generator* g);
+/* `key` is the reference state-dict key, e.g. "convs.3.conv.modulation.weight". */
+SIS_API int sis_generator_set_param(sis_generator* g, const char* key, const float* d_ptr, int64_t numel);
+SIS_API int sis_generator_prepare(sis_generator* g, void* stream);
+SIS_API int sis_generator_n_latent(const sis_generator* g);
+SIS_API int sis_generator_num_layers(const sis_generator* g);
+/* channels of captured activation `idx` (0..n_latent-1) and its resolution */
+SIS_API int sis_generator_activation_shape(const sis_generator* g, int idx, int* channels, int* res);
+
+/* style MLP: `Generator.style` / `get_latent`, model.py:383-392,476-477.  z,w: [n, style_dim] fp32 device. */
+SIS_API int sis_generator_style(sis_generator* g, const float* d_z, float* d_w, int64_t n, void* stream);
+
+typedef struct {
+    int batch;
+    /* --- styles (model.py:491-528) ---
+     * d_styles[j]: [batch, style_dim] (z if !input_is_latent, else w), or [batch, n_latent, style_dim]
+     * when styles_are_wplus (single style only, model.py:515-519). n_styles is 1 or 2. */
+    int n_styles;
+    const float* d_styles[2];
+    int input_is_latent;
+    int styles_are_wplus;
+    int inject_index;            /* used when n_styles == 2; the caller resolves the random default */
+    float truncation;            /* < 1 => w = t_latent + truncation*(w - t_latent), model.py:502-510 */
+    const float* d_truncation_latent; /* [1 or batch, style_dim] */
+    int truncation_latent_rows;  /* 1 or batch */
+    /* --- noise (model.py:494-500, 287-292) ---
+     * d_noise[l]: noise map of layer l (num_layers entries), [1,1,H,W] (noise_batch_stride[l] = 0) or
+     * [batch,1,H,W] (stride = H*W).  All must be non-NULL: the caller draws `randomize_noise` maps. */
+    const float* const* d_noise;
+    const int64_t* noise_batch_stride;
+    /* --- outputs --- */
+    float* d_image;              /* [batch, 3, size, size] fp32 */
+    float* d_latent_out;         /* optional [batch, n_latent, style_dim] (return_latents) or NULL */
+    float* const* d_activations; /* optional: n_latent pointers, entry idx = [batch, C_idx, H_idx, H_idx] fp32
+                                    NCHW or NULL to skip that capture (model.py:530-549) */
+    int precision;               /* sis_precision */
+} sis_forward_args;
+
+SIS_API int sis_generator_forward(sis_generator* g, const sis_forward_args* args, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Labelling — replaces, on the device and in one pass per layer,
+ *   FactorCatalog.predict / pairwise_distance  scf/segmentation/gan_local_edit/factor_catalog.py:47-75
+ *   predict_clusters                           scf/segmentation/base_cluster_based_dataset_segmenter.py:119-138
+ *   resize_to_image_size                       scf/segmentation/base_dataset_segmenter.py:32-42
+ * d_act: [batch, C, H, W] fp32 NCHW.  d_centroids: [k, C] fp32.  ids = argmin_k sum_c (x_c - m_kc)^2, ties ->
+ * lowest k.  d_cluster_class_bits[k]: bit j set <=> cluster belongs to class j (n_class <= 32).
+ * Outputs (each optional / NULL):
+ *   d_ids_u8  [batch,H,W] uint8, d_ids_i64 [batch,H,W] int64 (the reference's dtype),
+ *   d_masks   [n_class, batch, S, S] uint8 0/1, nearest-resized to S (src = floor(dst*H/S)); S >= H,
+ *   d_margin  [batch,H,W] fp32 second-best minus best distance,
+ *   d_hist    [k] uint64, cluster pixel counts ACCUMULATED (atomicAdd) at native resolution.
+ * mode 0: assign at native resolution then nearest-resize (reference cluster path).
+ * mode 1: bilinear-upsample features to SxS (align_corners=False) then assign; ids/margin are [batch,S,S].
+ * ------------------------------------------------------------------------------------------------------- */
+SIS_API int sis_label_assign(const float* d_act, int batch, int channels, int h, int w, const float* d_centroids, int k,
+                     const uint32_t* d_cluster_class_bits, int n_class, int image_size, int mode,
+                     uint8_t* d_ids_u8, int64_t* d_ids_i64, uint8_t* d_masks, float* d_margin,
+                     unsigned long long* d_hist, void* stream);
+
+/* predict_clusters' mask step alone: ids(int64)[n] -> masks [n_class, n] uint8
+ * (base_cluster_based_dataset_segmenter.py:131-135). */
+SIS_API int sis_class_masks_from_ids(const int64_t* d_ids, int64_t n, const uint32_t* d_cluster_class_bits, int k,
+                             int n_class, uint8_t* d_masks, void* stream);
+
+/* resize_to_image_size alone: nearest resize of uint8/bool planes [planes, h, w] -> [planes, S, S]
+ * (base_dataset_segmenter.py:38, F.interpolate default mode). */
+SIS_API int sis_nearest_resize_u8(const uint8_t* d_in, int64_t planes, int h, int w, int out_h, int out_w, uint8_t* d_out,
+                          void* stream);
+
+/* merge_sub_images: dst |= src over n bytes (black_white_handwritten_printed_text_segmenter.py:31-40). */
+SIS_API int sis_or_u8(uint8_t* d_dst, const uint8_t* d_src, int64_t n, void* stream);
+
+/* make_image (pytorch_training.images.make_image, call site scf/create_dataset_for_segmentation.py:135):
+ * [batch,3,S,S] fp32 -> [batch,S,S,3] uint8, clamp(-1,1), (x+1)/2*255 truncated. */
+SIS_API int sis_make_image_u8(const float* d_image, int batch, int size, uint8_t* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SIS_B200_H */

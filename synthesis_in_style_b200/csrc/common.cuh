@@ -1,0 +1,75 @@
+// Shared helpers for libsis_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+#include "../../include/sis_b200.h"
+
+namespace sis {
+
+void set_error(const char* fmt, ...);
+extern std::atomic<unsigned long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+#define SIS_CHECK_CUDA(expr)                                                                      \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            sis::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return SIS_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+#define SIS_CHECK_LAUNCH()                                                                        \
+    do {                                                                                          \
+        cudaError_t _e = cudaGetLastError();                                                      \
+        if (_e != cudaSuccess) {                                                                  \
+            sis::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return SIS_ERR_CUDA;                                                                  \
+        }                                                                                         \
+        sis::count_launch();                                                                      \
+    } while (0)
+
+#define SIS_REQUIRE(cond, ...)                                                                    \
+    do {                                                                                          \
+        if (!(cond)) {                                                                            \
+            sis::set_error(__VA_ARGS__);                                                          \
+            return SIS_ERR_INVALID;                                                               \
+        }                                                                                         \
+    } while (0)
+
+#define SIS_PROPAGATE(expr)                                                                       \
+    do {                                                                                          \
+        int _s = (expr);                                                                          \
+        if (_s != SIS_OK) return _s;                                                              \
+    } while (0)
+
+constexpr int kNumSMs = 148;
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float lrelu_scale(float x, float alpha, float scale) {
+    // (x > 0 ? x : x*alpha) * scale with the reference's rounding sequence
+    // (fused_bias_act_kernel.cu:39,47): two separately rounded multiplies, never an FMA.
+    float y = (x > 0.0f) ? x : __fmul_rn(x, alpha);
+    return __fmul_rn(y, scale);
+}
+
+// 128-bit streaming accesses: data touched once goes around L1.
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream_f4(float4* p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+}  // namespace sis

@@ -1,0 +1,384 @@
+// Activation -> semantic-class labelling, fully on the device, one pass over the activation map per layer.
+//   FactorCatalog.predict / pairwise_distance   scf/segmentation/gan_local_edit/factor_catalog.py:47-75
+//   partial_flat                                scf/segmentation/gan_local_edit/ptutils.py:25-28
+//   predict_clusters (class OR masks)           scf/segmentation/base_cluster_based_dataset_segmenter.py:119-138
+//   resize_to_image_size (nearest)              scf/segmentation/base_dataset_segmenter.py:32-42
+//   bilinear feature upsample (DatasetGAN path) scf/create_dataset_for_segmentation.py:39-44
+// The reference ships every labelled map to the CPU, builds an [N,k,C] temporary, and ships ids back.
+//
+// HBM-bound (AI ~ k/2 FLOP/B): algorithmic bytes per layer = B*H*W*C*4 (activations, read once, 128-bit
+// coalesced along W) + B*H*W (ids) + n_class*B*S*S (masks) + k*C*4.
+// Thread = 4 consecutive pixels x one channel slice; the k partial distances of the SLICES slices are
+// reduced through shared memory in fixed order (deterministic), then argmin (ties -> lowest k, as
+// torch.argmin), class-bit LUT, nearest replication of the masks to SxS, and a warp-aggregated histogram.
+#include "common.cuh"
+
+namespace sis {
+
+constexpr int LBL_SLICES = 8;
+
+struct LabelArgs {
+    const float* act; int batch, C, H, W;
+    const float* centroids; int k;
+    const uint32_t* class_bits; int n_class; int S;
+    uint8_t* ids_u8; int64_t* ids_i64; uint8_t* masks; float* margin; unsigned long long* hist;
+};
+
+template <int KMAX, int PPT>
+struct LabelSmem {
+    // centroids transposed [C][KMAX] + reduction scratch [SLICES][KMAX][PPT][32]
+    static size_t bytes(int C) { return ((size_t)C * KMAX + (size_t)LBL_SLICES * KMAX * PPT * 32) * sizeof(float) + 64 * sizeof(unsigned); }
+};
+
+__device__ __forceinline__ void write_label_outputs(const LabelArgs& a, int b, int y, int x, int id, float best,
+                                                    float second) {
+    const int64_t n = ((int64_t)b * a.H + y) * a.W + x;
+    if (a.ids_u8) a.ids_u8[n] = (uint8_t)id;
+    if (a.ids_i64) a.ids_i64[n] = id;
+    if (a.margin) a.margin[n] = second - best;
+}
+
+// nearest source index as ATen's legacy `nearest`: min(floor(dst * (in/out)), in-1), scale in float.
+__device__ __forceinline__ int nearest_src(int dst, float scale, int in_size) {
+    int s = (int)floorf((float)dst * scale);
+    return s < in_size - 1 ? s : in_size - 1;
+}
+
+template <int KMAX, int PPT>
+__global__ void __launch_bounds__(32 * LBL_SLICES) label_native_kernel(LabelArgs a) {
+    extern __shared__ float smem[];
+    float* sc = smem;                                   // [C][KMAX]
+    float* red = smem + (size_t)a.C * KMAX;             // [SLICES][KMAX][PPT][32]
+    unsigned* shist = reinterpret_cast<unsigned*>(red + LBL_SLICES * KMAX * PPT * 32);  // [KMAX<=64]
+    const int lane = threadIdx.x, slice = threadIdx.y;
+    const int tid = slice * 32 + lane;
+    for (int i = tid; i < a.C * KMAX; i += 32 * LBL_SLICES) {
+        int c = i / KMAX, kk = i - c * KMAX;
+        sc[i] = kk < a.k ? a.centroids[(int64_t)kk * a.C + c] : 0.0f;
+    }
+    if (tid < 64) shist[tid] = 0;
+    __syncthreads();
+
+    const int64_t hw = (int64_t)a.H * a.W;
+    const int64_t groups_per_sample = hw / PPT;
+    const int64_t total_groups = groups_per_sample * a.batch;
+    const int cps = (a.C + LBL_SLICES - 1) / LBL_SLICES;
+    const int c_begin = slice * cps, c_end = min(a.C, c_begin + cps);
+    const int rep = a.S / a.H;   // integer replication factor when S % H == 0, else generic path below
+    const bool int_ratio = (a.S % a.H == 0) && (a.S % a.W == 0) && (a.H == a.W);
+
+    for (int64_t g0 = (int64_t)blockIdx.x * 32; g0 < total_groups; g0 += (int64_t)gridDim.x * 32) {
+        const int64_t g = g0 + lane;
+        const bool valid = g < total_groups;
+        const int b = valid ? (int)(g / groups_per_sample) : 0;
+        const int64_t pix = valid ? (g - (int64_t)b * groups_per_sample) * PPT : 0;
+        float acc[KMAX][PPT];
+#pragma unroll
+        for (int kk = 0; kk < KMAX; ++kk)
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) acc[kk][p] = 0.0f;
+        if (valid) {
+            const float* xb = a.act + ((int64_t)b * a.C) * hw + pix;
+#pragma unroll 2
+            for (int c = c_begin; c < c_end; ++c) {
+                float xv[PPT];
+                if (PPT == 4) {
+                    const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(xb + (int64_t)c * hw));
+                    xv[0] = v.x; xv[1] = v.y; xv[2 % PPT] = v.z; xv[3 % PPT] = v.w;
+                } else {
+#pragma unroll
+                    for (int p = 0; p < PPT; ++p) xv[p] = __ldg(xb + (int64_t)c * hw + p);
+                }
+                const float* cc = sc + (size_t)c * KMAX;
+#pragma unroll
+                for (int kk = 0; kk < KMAX; ++kk) {
+                    const float m = cc[kk];
+#pragma unroll
+                    for (int p = 0; p < PPT; ++p) {
+                        const float df = __fsub_rn(xv[p], m);      // (A - B) ** 2 summed over channels
+                        acc[kk][p] = __fmaf_rn(df, df, acc[kk][p]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < KMAX; ++kk)
+#pragma unroll
+            for (int p = 0; p < PPT; ++p) red[((slice * KMAX + kk) * PPT + p) * 32 + lane] = acc[kk][p];
+        __syncthreads();
+        // finalisation: PPT*32 pixels, one thread each (threads 0 .. PPT*32-1)
+        if (tid < PPT * 32) {
+            const int ln = tid % 32, p = tid / 32;
+            const int64_t gg = g0 + ln;
+            int id = -1;
+            if (gg < total_groups) {
+                float best = INFINITY, second = INFINITY;
+                id = 0;
+                for (int kk = 0; kk < a.k; ++kk) {
+                    float d = 0.0f;
+#pragma unroll
+                    for (int s = 0; s < LBL_SLICES; ++s) d += red[((s * KMAX + kk) * PPT + p) * 32 + ln];
+                    if (d < best) { second = best; best = d; id = kk; }
+                    else if (d < second) { second = d; }
+                }
+                const int bb = (int)(gg / groups_per_sample);
+                const int64_t px = (gg - (int64_t)bb * groups_per_sample) * PPT + p;
+                const int y = (int)(px / a.W), x = (int)(px % a.W);
+                write_label_outputs(a, bb, y, x, id, best, second);
+                if (a.masks) {
+                    const uint32_t bits = __ldg(a.class_bits + id);
+                    const int64_t plane = (int64_t)a.S * a.S;
+                    if (int_ratio) {
+                        for (int j = 0; j < a.n_class; ++j) {
+                            const uint8_t m = (bits >> j) & 1u;
+                            uint8_t* dst = a.masks + ((int64_t)j * a.batch + bb) * plane + (int64_t)y * rep * a.S + (int64_t)x * rep;
+                            if ((rep & 3) == 0 && ((((uintptr_t)a.masks) & 3) == 0)) {
+                                const uint32_t word = m * 0x01010101u;   // 4 replicated pixels per store
+                                for (int ry = 0; ry < rep; ++ry)
+                                    for (int rx = 0; rx < rep / 4; ++rx)
+                                        reinterpret_cast<uint32_t*>(dst + (int64_t)ry * a.S)[rx] = word;
+                            } else {
+                                for (int ry = 0; ry < rep; ++ry)
+                                    for (int rx = 0; rx < rep; ++rx) dst[(int64_t)ry * a.S + rx] = m;
+                            }
+                        }
+                    }
+                }
+            }
+            if (a.hist) {
+                // warp-aggregated histogram: one shared atomic per (warp, cluster present)
+                for (int kk = 0; kk < a.k; ++kk) {
+                    const unsigned m = __ballot_sync(0xffffffffu, id == kk);
+                    if (ln == 0 && m) atomicAdd(&shist[kk], __popc(m));
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (a.hist && tid < a.k && shist[tid]) atomicAdd(a.hist + tid, (unsigned long long)shist[tid]);
+}
+
+// masks for a non-integer resize ratio: gather from the ids (rare; power-of-two sizes never take it)
+__global__ void __launch_bounds__(256) masks_gather_kernel(uint8_t* __restrict__ masks, const uint8_t* __restrict__ ids,
+                                                           const uint32_t* __restrict__ class_bits, int n_class,
+                                                           int batch, int H, int W, int S) {
+    const int64_t total = (int64_t)batch * S * S;
+    const float sy = (float)H / (float)S, sx = (float)W / (float)S;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % S);
+        const int y = (int)((i / S) % S);
+        const int b = (int)(i / ((int64_t)S * S));
+        const int id = ids[((int64_t)b * H + nearest_src(y, sy, H)) * W + nearest_src(x, sx, W)];
+        const uint32_t bits = class_bits[id];
+        for (int j = 0; j < n_class; ++j) masks[((int64_t)j * batch + b) * S * S + (int64_t)y * S + x] = (bits >> j) & 1u;
+    }
+}
+
+// mode 1: bilinear upsample (align_corners=False, ATen's area_pixel_compute_source_index) of the features to
+// SxS, then assign.  One thread per output pixel, centroids in shared memory; the 4 taps are gathered per
+// channel (each source element is re-read ~ (S/H)^2 times but from L1/L2: DRAM traffic stays ~ one pass).
+template <int KMAX>
+__global__ void __launch_bounds__(256) label_bilinear_kernel(LabelArgs a) {
+    extern __shared__ float smem[];
+    float* sc = smem;  // [C][KMAX]
+    for (int i = threadIdx.x; i < a.C * KMAX; i += blockDim.x) {
+        int c = i / KMAX, kk = i - c * KMAX;
+        sc[i] = kk < a.k ? a.centroids[(int64_t)kk * a.C + c] : 0.0f;
+    }
+    __syncthreads();
+    const int S = a.S;
+    const int64_t total = (int64_t)a.batch * S * S;
+    const float scale_h = (float)a.H / (float)S, scale_w = (float)a.W / (float)S;  // 1/scale_factor
+    const int64_t hw = (int64_t)a.H * a.W;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % S), y = (int)((i / S) % S), b = (int)(i / ((int64_t)S * S));
+        float fy = fmaxf(scale_h * ((float)y + 0.5f) - 0.5f, 0.0f);
+        float fx = fmaxf(scale_w * ((float)x + 0.5f) - 0.5f, 0.0f);
+        const int y0 = (int)fy, x0 = (int)fx;
+        const int y1 = y0 + (y0 < a.H - 1 ? 1 : 0), x1 = x0 + (x0 < a.W - 1 ? 1 : 0);
+        const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.0f - ly, hx = 1.0f - lx;
+        const float* xb = a.act + (int64_t)b * a.C * hw;
+        float acc[KMAX];
+#pragma unroll
+        for (int kk = 0; kk < KMAX; ++kk) acc[kk] = 0.0f;
+        for (int c = 0; c < a.C; ++c) {
+            const float* pc = xb + (int64_t)c * hw;
+            const float v00 = __ldg(pc + (int64_t)y0 * a.W + x0), v01 = __ldg(pc + (int64_t)y0 * a.W + x1);
+            const float v10 = __ldg(pc + (int64_t)y1 * a.W + x0), v11 = __ldg(pc + (int64_t)y1 * a.W + x1);
+            // ATen upsample_bilinear2d: h0lambda*(w0lambda*v00 + w1lambda*v01) + h1lambda*(w0lambda*v10 + w1lambda*v11)
+            const float v = __fadd_rn(__fmul_rn(hy, __fadd_rn(__fmul_rn(hx, v00), __fmul_rn(lx, v01))),
+                                      __fmul_rn(ly, __fadd_rn(__fmul_rn(hx, v10), __fmul_rn(lx, v11))));
+            const float* cc = sc + (size_t)c * KMAX;
+#pragma unroll
+            for (int kk = 0; kk < KMAX; ++kk) {
+                const float df = __fsub_rn(v, cc[kk]);
+                acc[kk] = __fmaf_rn(df, df, acc[kk]);
+            }
+        }
+        float best = INFINITY, second = INFINITY;
+        int id = 0;
+        for (int kk = 0; kk < a.k; ++kk) {
+            const float d = acc[kk];
+            if (d < best) { second = best; best = d; id = kk; }
+            else if (d < second) { second = d; }
+        }
+        if (a.ids_u8) a.ids_u8[i] = (uint8_t)id;
+        if (a.ids_i64) a.ids_i64[i] = id;
+        if (a.margin) a.margin[i] = second - best;
+        if (a.masks) {
+            const uint32_t bits = __ldg(a.class_bits + id);
+            for (int j = 0; j < a.n_class; ++j)
+                a.masks[((int64_t)j * a.batch + b) * S * S + (int64_t)y * S + x] = (bits >> j) & 1u;
+        }
+        if (a.hist) atomicAdd(a.hist + id, 1ull);
+    }
+}
+
+__global__ void __launch_bounds__(256) class_masks_from_ids_kernel(uint8_t* __restrict__ masks, const int64_t* __restrict__ ids,
+                                                                   const uint32_t* __restrict__ class_bits, int k,
+                                                                   int n_class, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t id = ids[i];
+        const uint32_t bits = (id >= 0 && id < k) ? class_bits[id] : 0u;
+        for (int j = 0; j < n_class; ++j) masks[(int64_t)j * n + i] = (bits >> j) & 1u;
+    }
+}
+
+__global__ void __launch_bounds__(256) nearest_resize_u8_kernel(uint8_t* __restrict__ out, const uint8_t* __restrict__ in,
+                                                                int64_t planes, int h, int w, int oh, int ow) {
+    const float sy = (float)h / (float)oh, sx = (float)w / (float)ow;
+    const int64_t total = planes * oh * ow;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % ow), y = (int)((i / ow) % oh);
+        const int64_t p = i / ((int64_t)ow * oh);
+        out[i] = in[(p * h + nearest_src(y, sy, h)) * w + nearest_src(x, sx, w)];
+    }
+}
+
+__global__ void __launch_bounds__(256) or_u8_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = dst[i] | src[i];
+}
+
+static int flat_grid(int64_t n, int per_block = 256) {
+    int64_t b = ceil_div64(n, per_block);
+    int64_t cap = (int64_t)kNumSMs * 8;
+    return (int)(b < 1 ? 1 : (b < cap ? b : cap));
+}
+
+template <int KMAX, int PPT>
+static int launch_native(const LabelArgs& a, cudaStream_t stream) {
+    size_t smem = LabelSmem<KMAX, PPT>::bytes(a.C);
+    auto kern = label_native_kernel<KMAX, PPT>;
+    if (smem > 48 * 1024) SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t groups = (int64_t)a.H * a.W / PPT * a.batch;
+    int64_t blocks = ceil_div64(groups, 32);
+    int64_t cap = (int64_t)kNumSMs * 4;
+    int grid = (int)(blocks < cap ? blocks : cap);
+    kern<<<grid, dim3(32, LBL_SLICES), smem, stream>>>(a);
+    SIS_CHECK_LAUNCH();
+    return SIS_OK;
+}
+
+template <int KMAX>
+static int launch_bilinear(const LabelArgs& a, cudaStream_t stream) {
+    size_t smem = (size_t)a.C * KMAX * sizeof(float);
+    auto kern = label_bilinear_kernel<KMAX>;
+    if (smem > 48 * 1024) SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<flat_grid((int64_t)a.batch * a.S * a.S), 256, smem, stream>>>(a);
+    SIS_CHECK_LAUNCH();
+    return SIS_OK;
+}
+
+}  // namespace sis
+
+using namespace sis;
+
+extern "C" int sis_label_assign(const float* d_act, int batch, int channels, int h, int w, const float* d_centroids,
+                                int k, const uint32_t* d_cluster_class_bits, int n_class, int image_size, int mode,
+                                uint8_t* d_ids_u8, int64_t* d_ids_i64, uint8_t* d_masks, float* d_margin,
+                                unsigned long long* d_hist, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIS_REQUIRE(batch >= 0 && channels >= 1 && h >= 0 && w >= 0, "label_assign: bad shape");
+    SIS_REQUIRE(k >= 1 && k <= 64, "label_assign: k must be in [1, 64] (got %d)", k);
+    SIS_REQUIRE(n_class >= 0 && n_class <= 32, "label_assign: n_class must be <= 32");
+    SIS_REQUIRE(mode == 0 || mode == 1, "label_assign: mode must be 0 or 1");
+    SIS_REQUIRE(!d_masks || (d_cluster_class_bits && image_size >= h && image_size >= w),
+                "label_assign: masks need class bits and image_size >= map size");
+    SIS_REQUIRE((size_t)channels * 64 * 4 <= 200 * 1024 || k <= 32, "label_assign: centroid table does not fit shared memory");
+    if ((int64_t)batch * h * w == 0) return SIS_OK;
+    SIS_REQUIRE(d_act && d_centroids, "label_assign: activations / centroids must be CUDA tensors (null pointer)");
+    LabelArgs a;
+    a.act = d_act; a.batch = batch; a.C = channels; a.H = h; a.W = w; a.centroids = d_centroids; a.k = k;
+    a.class_bits = d_cluster_class_bits; a.n_class = n_class; a.S = image_size;
+    a.ids_u8 = d_ids_u8; a.ids_i64 = d_ids_i64; a.masks = d_masks; a.margin = d_margin; a.hist = d_hist;
+    if (mode == 1) {
+        SIS_REQUIRE(image_size >= 1, "label_assign: image_size required for mode 1");
+        if (k <= 4) return launch_bilinear<4>(a, stream);
+        if (k <= 8) return launch_bilinear<8>(a, stream);
+        if (k <= 16) return launch_bilinear<16>(a, stream);
+        if (k <= 32) return launch_bilinear<32>(a, stream);
+        return launch_bilinear<64>(a, stream);
+    }
+    const bool vec4 = ((h * w) % 4 == 0) && ((((uintptr_t)d_act) & 15) == 0);
+    const bool int_ratio = d_masks && (image_size % h == 0) && (image_size % w == 0) && (h == w);
+    uint8_t* tmp_ids = nullptr;
+    bool gather = d_masks && !int_ratio;
+    if (gather) {
+        // non-integer ratio: masks are gathered from the ids afterwards
+        SIS_REQUIRE(d_ids_u8 != nullptr, "label_assign: non-integer resize ratio needs d_ids_u8");
+        tmp_ids = d_ids_u8;
+        a.masks = nullptr;
+    }
+    int st;
+    if (vec4) {
+        if (k <= 4) st = launch_native<4, 4>(a, stream);
+        else if (k <= 8) st = launch_native<8, 4>(a, stream);
+        else if (k <= 16) st = launch_native<16, 4>(a, stream);
+        else if (k <= 32) st = launch_native<32, 2>(a, stream);
+        else st = launch_native<64, 1>(a, stream);
+    } else {
+        if (k <= 8) st = launch_native<8, 1>(a, stream);
+        else if (k <= 32) st = launch_native<32, 1>(a, stream);
+        else st = launch_native<64, 1>(a, stream);
+    }
+    SIS_PROPAGATE(st);
+    if (gather) {
+        masks_gather_kernel<<<flat_grid((int64_t)batch * image_size * image_size), 256, 0, stream>>>(
+            d_masks, tmp_ids, d_cluster_class_bits, n_class, batch, h, w, image_size);
+        SIS_CHECK_LAUNCH();
+    }
+    return SIS_OK;
+}
+
+extern "C" int sis_class_masks_from_ids(const int64_t* d_ids, int64_t n, const uint32_t* d_cluster_class_bits, int k,
+                                        int n_class, uint8_t* d_masks, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIS_REQUIRE(n >= 0 && k >= 0 && n_class >= 0 && n_class <= 32, "class_masks_from_ids: bad arguments");
+    if (n == 0 || n_class == 0) return SIS_OK;
+    SIS_REQUIRE(d_ids && d_cluster_class_bits && d_masks, "class_masks_from_ids: null pointer");
+    class_masks_from_ids_kernel<<<flat_grid(n), 256, 0, stream>>>(d_masks, d_ids, d_cluster_class_bits, k, n_class, n);
+    SIS_CHECK_LAUNCH();
+    return SIS_OK;
+}
+
+extern "C" int sis_nearest_resize_u8(const uint8_t* d_in, int64_t planes, int h, int w, int out_h, int out_w,
+                                     uint8_t* d_out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIS_REQUIRE(planes >= 0 && h >= 1 && w >= 1 && out_h >= 0 && out_w >= 0, "nearest_resize_u8: bad shape");
+    if (planes * out_h * out_w == 0) return SIS_OK;
+    SIS_REQUIRE(d_in && d_out, "nearest_resize_u8: null pointer");
+    nearest_resize_u8_kernel<<<flat_grid(planes * out_h * out_w), 256, 0, stream>>>(d_out, d_in, planes, h, w, out_h, out_w);
+    SIS_CHECK_LAUNCH();
+    return SIS_OK;
+}
+
+extern "C" int sis_or_u8(uint8_t* d_dst, const uint8_t* d_src, int64_t n, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIS_REQUIRE(n >= 0, "or_u8: negative size");
+    if (n == 0) return SIS_OK;
+    SIS_REQUIRE(d_dst && d_src, "or_u8: null pointer");
+    or_u8_kernel<<<flat_grid(n), 256, 0, stream>>>(d_dst, d_src, n);
+    SIS_CHECK_LAUNCH();
+    return SIS_OK;
+}

@@ -1,0 +1,676 @@
+// Modulated 3x3 convolution as a shared-weight implicit GEMM on the 5th-gen tensor cores (sm_100a).
+//   ModulatedConv2d.forward   scf/networks/stylegan2/model.py:237-278
+//   StyledConv.forward        model.py:336-342   (noise + bias + leaky ReLU fused into the epilogue)
+//
+//   y[b,o,p] = d[b,o] * sum_{t,i} Ws[t,o,i] * xs[b,p+t,i],   xs = s[b,i]*x[b,i,p]  (pre-scaled by the producer)
+//
+// GEMM view: M = pixels (128 per tile = a TBxTHxTW box), N = Cout (BN per tile), K = taps*Cin in 64-wide chunks.
+//   A tile  : one TMA 4-D box {64 ch, TW, TH, TB} of the NHWC bf16 plane at the tap-shifted coordinate; the
+//             conv's zero padding is TMA out-of-bounds fill, so there is no im2col buffer and no halo code.
+//   B tile  : one TMA 3-D box {64 ch, BN, 1 tap} of the [tap][Cout][Cin] weight pack (shared by all samples).
+//   MMA     : tcgen05.mma cta_group::1 kind::f16, M=128, N=BN, K=16, operands straight from 128B-swizzled
+//             shared memory, fp32 accumulator in TMEM (double-buffered: 2 x BN columns).
+//   Precision: 3-term bf16 split (hi*hi + hi*lo + lo*hi) into the same accumulator (single-pass
+//             bf16/tf32 operands cannot meet the label criterion; the 3-term split gives ~1e-4 max abs error).
+//   Epilogue: tcgen05.ld 32x32b -> x demod -> + noise -> + bias -> lrelu*sqrt2 -> fp32 NCHW capture + the next
+//             conv's pre-scaled bf16 hi/lo NHWC planes (plain conv); or x demod -> fp32 NHWC scratch at the
+//             phase position (transposed conv; blur + activation follow in blur_act_split_kernel).
+//   The stride-2 transposed conv (model.py:251-259) is 4 output-phase sub-GEMMs with 4/2/2/1 taps (no wasted
+//   FLOPs): out[2y'+py, 2x'+px] = sum_{ky = py (mod 2)...} W[ky,kx] x[y' - ky/2, x' - kx/2].
+// Warp roles (192 threads, persistent, static round-robin tile schedule): warp 0 = TMA producer, warp 1 = MMA
+// issuer + TMEM allocator, warps 2-5 = epilogue (TMEM lane quarter = warp_id % 4).
+#include <cuda.h>
+#include <cstring>
+#include "common.cuh"
+#include "kernels.h"
+#include "modconv_tc.h"
+
+namespace sis {
+
+using bf16 = __nv_bfloat16;
+
+// ------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must never hang the GPU.  ~4e9 cycles (about 2 s) then record + trap.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned int* error, unsigned int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) {
+            if (error) atomicExch(error, code);
+            __threadfence_system();
+            asm volatile("trap;");
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_load_4d(const void* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const void* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: 8-row atoms of 1024 B (SBO), LBO unused (=1), descriptor version 1.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;                 // leading byte offset (16 B units), ignored for swizzled K-major
+    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                 // version = 1 (Blackwell)
+    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    return d;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+struct TcSubProblem {
+    int ntaps;
+    signed char dy[9], dx[9], widx[9];
+    int oh, ow;                 // extent of this sub-problem's output grid
+    int ostride, ooff_y, ooff_x;
+    int tiles_y, tiles_x;
+    int tile_begin;
+};
+
+struct TcKernelArgs {
+    TcSubProblem sub[4];
+    int nsub, total_tiles;
+    int batch, cin, cout, b_tiles, n_tiles, kchunks;
+    int mode;                   // 0 plain (fused activation), 1 transposed-conv phase (demod only)
+    const float* demod; const float* noise; int64_t noise_bstride; float noise_w; const float* bias;
+    float* out_f32; int out_h, out_w;
+    const float* s_next; bf16* next_hi; bf16* next_lo;
+    unsigned int* error;
+};
+
+constexpr int BM = 128, BK = 64, UMMA_K = 16;
+constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
+constexpr int TC_THREADS = 192;
+
+template <int BN> struct TcCfg {
+    static constexpr int B_TILE_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+    static constexpr int STAGES = (220 * 1024) / STAGE_BYTES > 6 ? 6 : (220 * 1024) / STAGE_BYTES;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+};
+
+struct TileCoord { int sub, b0, y0, x0, n0; };
+
+template <int BN, int TH, int TW, int TB>
+__device__ __forceinline__ TileCoord decode_tile(const TcKernelArgs& a, int t) {
+    int p = 0;
+#pragma unroll
+    for (int i = 1; i < 4; ++i)
+        if (i < a.nsub && t >= a.sub[i].tile_begin) p = i;
+    const TcSubProblem& s = a.sub[p];
+    const int local = t - s.tile_begin;
+    const int m_tiles = a.b_tiles * s.tiles_y * s.tiles_x;
+    const int m = local % m_tiles, n = local / m_tiles;
+    TileCoord c;
+    c.sub = p;
+    c.x0 = (m % s.tiles_x) * TW;
+    c.y0 = ((m / s.tiles_x) % s.tiles_y) * TH;
+    c.b0 = (m / (s.tiles_x * s.tiles_y)) * TB;
+    c.n0 = n * BN;
+    return c;
+}
+
+template <int BN, int TH, int TW, int TB>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+modconv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                  const __grid_constant__ TcKernelArgs a) {
+    static_assert(TH * TW * TB == BM, "tile box must hold 128 pixels");
+    using Cfg = TcCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* full_bar = bars;                 // [STAGES]
+    uint64_t* empty_bar = bars + STAGES;       // [STAGES]
+    uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+    uint32_t* tmem_ptr_smem = (uint32_t*)(bars + 2 * STAGES + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
+        tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo);
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+                const TileCoord c = decode_tile<BN, TH, TW, TB>(a, t);
+                const TcSubProblem& s = a.sub[c.sub];
+                for (int tap = 0; tap < s.ntaps; ++tap) {
+                    const int ax = c.x0 + s.dx[tap], ay = c.y0 + s.dy[tap], wi = s.widx[tap];
+                    for (int kc = 0; kc < a.kchunks; ++kc) {
+                        mbar_wait(&empty_bar[stage], phase ^ 1, a.error, 0x100 + stage);
+                        uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+                        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                        tma_load_4d(&map_a_hi, &full_bar[stage], st, kc * BK, ax, ay, c.b0);
+                        tma_load_4d(&map_a_lo, &full_bar[stage], st + A_TILE_BYTES, kc * BK, ax, ay, c.b0);
+                        tma_load_3d(&map_w_hi, &full_bar[stage], st + 2 * A_TILE_BYTES, kc * BK, c.n0, wi);
+                        tma_load_3d(&map_w_lo, &full_bar[stage], st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES, kc * BK, c.n0, wi);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        if (lane == 0) {
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int stage = 0; uint32_t phase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+                const TileCoord c = decode_tile<BN, TH, TW, TB>(a, t);
+                const int kblocks = a.sub[c.sub].ntaps * a.kchunks;
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1, a.error, 0x200 + acc);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase, a.error, 0x300 + stage);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
+                    const uint64_t d_ah = make_smem_desc(sa), d_al = make_smem_desc(sa + A_TILE_BYTES);
+                    const uint64_t d_bh = make_smem_desc(sa + 2 * A_TILE_BYTES);
+                    const uint64_t d_bl = make_smem_desc(sa + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B per K step inside the swizzle row
+                        umma_bf16(d_tmem, d_ah + koff, d_bh + koff, idesc, (kb | k) ? 1u : 0u);
+                        umma_bf16(d_tmem, d_ah + koff, d_bl + koff, idesc, 1u);
+                        umma_bf16(d_tmem, d_al + koff, d_bh + koff, idesc, 1u);
+                    }
+                    umma_commit(&empty_bar[stage]);     // frees this smem stage when the MMAs above retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);           // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ============================== epilogue (warps 2..5) ==============================
+        const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+        const int row = quarter * 32 + lane;            // GEMM row = pixel of the tile box
+        const int tw = row % TW, th = (row / TW) % TH, tb = row / (TW * TH);
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+            const TileCoord c = decode_tile<BN, TH, TW, TB>(a, t);
+            const TcSubProblem& s = a.sub[c.sub];
+            const int b = c.b0 + tb, yy = c.y0 + th, xx = c.x0 + tw;
+            const bool valid = b < a.batch && yy < s.oh && xx < s.ow;
+            const int oy = yy * s.ostride + s.ooff_y, ox = xx * s.ostride + s.ooff_x;
+            mbar_wait(&tfull_bar[acc], acc_phase, a.error, 0x400 + acc);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+            const float* dm = a.demod + (int64_t)(valid ? b : 0) * a.cout + c.n0;
+            float nz = 0.0f;
+            if (a.mode == 0 && valid) nz = __fmul_rn(a.noise_w, a.noise[(int64_t)b * a.noise_bstride + (int64_t)oy * a.out_w + ox]);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + (uint32_t)c0, r);
+                tmem_ld_wait();
+                if (valid) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __fmul_rn(__uint_as_float(r[j]), __ldg(dm + c0 + j));
+                    if (a.mode == 0) {
+                        // NoiseInjection + FusedLeakyReLU (model.py:292, fused_bias_act_kernel.cu:26-47)
+                        const int64_t plane = (int64_t)a.out_h * a.out_w;
+                        float* dst = a.out_f32 + ((int64_t)b * a.cout + c.n0 + c0) * plane + (int64_t)oy * a.out_w + ox;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float x = __fadd_rn(v[j], nz);
+                            x = __fadd_rn(x, __ldg(a.bias + c.n0 + c0 + j));
+                            x = lrelu_scale(x, 0.2f, 1.41421356237309504880f);
+                            v[j] = x;
+                            dst[(int64_t)j * plane] = x;       // lanes = consecutive x: coalesced per channel
+                        }
+                        if (a.s_next) {
+                            const float* sn = a.s_next + (int64_t)b * a.cout + c.n0 + c0;
+                            const int64_t off = (((int64_t)b * a.out_h + oy) * a.out_w + ox) * a.cout + c.n0 + c0;
+                            uint4* ph = reinterpret_cast<uint4*>(a.next_hi + off);
+                            uint4* pl = reinterpret_cast<uint4*>(a.next_lo + off);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint32_t wh[4], wl[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int j = q * 8 + e * 2;
+                                    const float x0 = __fmul_rn(v[j], __ldg(sn + j)), x1 = __fmul_rn(v[j + 1], __ldg(sn + j + 1));
+                                    const bf16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                                    const bf16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+                                    const bf16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                                    wh[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                                    wl[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                                }
+                                ph[q] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                                pl[q] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+                            }
+                        }
+                    } else {
+                        // transposed-conv phase: demodulated fp32, NHWC scratch [B][out_h][out_w][cout]
+                        float4* dst = reinterpret_cast<float4*>(
+                            a.out_f32 + (((int64_t)b * a.out_h + oy) * a.out_w + ox) * a.cout + c.n0 + c0);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------- blur + activation + split
+// Second half of the up-sampling StyledConv: Blur(4x4, pad (1,1)) + noise + bias + lrelu*sqrt2 over the NHWC fp32
+// scratch, writing the fp32 NCHW capture and the next conv's pre-scaled bf16 hi/lo NHWC planes in one pass.
+// Block = 8x16 output pixels x 32 channels; lane = channel (conflict-free smem, 128 B coalesced NHWC rows).
+struct BlurSplitArgs {
+    const float* in; int IH, IW;          // [B][IH][IW][C]
+    float* out_f32; int OH, OW, C, batch; // [B][C][OH][OW]
+    const float* blur_k; const float* noise; int64_t noise_bstride; float noise_w; const float* bias;
+    const float* s_next; bf16* next_hi; bf16* next_lo;   // [B][OH][OW][C]
+};
+constexpr int BS_TH = 8, BS_TW = 16, BS_C = 32;
+constexpr int BS_IH = BS_TH + 3, BS_IW = BS_TW + 3;
+
+__global__ void __launch_bounds__(256) blur_act_split_kernel(BlurSplitArgs a) {
+    __shared__ float sin_[BS_IH * BS_IW][BS_C];          // 26.1 KB
+    __shared__ float sout[BS_C][BS_TH * BS_TW + 1];      // 16.1 KB
+    __shared__ float sk[16];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 16) sk[tid] = a.blur_k[(3 - tid / 4) * 4 + (3 - tid % 4)];   // flipped taps
+    const int tiles_x = (a.OW + BS_TW - 1) / BS_TW, tiles_y = (a.OH + BS_TH - 1) / BS_TH;
+    const int cgroups = a.C / BS_C;
+    const int64_t total = (int64_t)a.batch * tiles_y * tiles_x * cgroups;
+    for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int cg = (int)(tile % cgroups);
+        int64_t r = tile / cgroups;
+        const int tx = (int)(r % tiles_x); r /= tiles_x;
+        const int ty = (int)(r % tiles_y);
+        const int b = (int)(r / tiles_y);
+        const int y0 = ty * BS_TH, x0 = tx * BS_TW, c0 = cg * BS_C;
+        __syncthreads();
+        for (int i = warp; i < BS_IH * BS_IW; i += 8) {
+            const int iy = y0 + i / BS_IW - 1, ix = x0 + i % BS_IW - 1;
+            float v = 0.0f;
+            if (iy >= 0 && ix >= 0 && iy < a.IH && ix < a.IW)
+                v = __ldg(a.in + (((int64_t)b * a.IH + iy) * a.IW + ix) * a.C + c0 + lane);
+            sin_[i][lane] = v;
+        }
+        __syncthreads();
+        const float bias = a.bias[c0 + lane];
+        const float sn = a.s_next ? a.s_next[(int64_t)b * a.C + c0 + lane] : 0.0f;
+#pragma unroll 2
+        for (int p = warp; p < BS_TH * BS_TW; p += 8) {
+            const int py = p / BS_TW, px = p % BS_TW;
+            float v = 0.0f;
+#pragma unroll
+            for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 4; ++kx) v = __fmaf_rn(sin_[(py + ky) * BS_IW + px + kx][lane], sk[ky * 4 + kx], v);
+            const int oy = y0 + py, ox = x0 + px;
+            if (oy < a.OH && ox < a.OW) {
+                v = __fadd_rn(v, __fmul_rn(a.noise_w, __ldg(a.noise + (int64_t)b * a.noise_bstride + (int64_t)oy * a.OW + ox)));
+                v = __fadd_rn(v, bias);
+                v = lrelu_scale(v, 0.2f, 1.41421356237309504880f);
+                if (a.s_next) {
+                    const float xs = __fmul_rn(v, sn);
+                    const bf16 h = __float2bfloat16_rn(xs);
+                    const bf16 l = __float2bfloat16_rn(xs - __bfloat162float(h));
+                    const int64_t off = (((int64_t)b * a.OH + oy) * a.OW + ox) * a.C + c0 + lane;
+                    a.next_hi[off] = h; a.next_lo[off] = l;
+                }
+            }
+            sout[lane][p] = v;
+        }
+        __syncthreads();
+        // NCHW capture: each warp writes 4 channels; lanes = 32 consecutive tile pixels (2 rows of 16)
+        for (int ci = warp; ci < BS_C; ci += 8) {
+            float* dst = a.out_f32 + ((int64_t)b * a.C + c0 + ci) * a.OH * a.OW;
+#pragma unroll
+            for (int p = lane; p < BS_TH * BS_TW; p += 32) {
+                const int oy = y0 + p / BS_TW, ox = x0 + p % BS_TW;
+                if (oy < a.OH && ox < a.OW) dst[(int64_t)oy * a.OW + ox] = sout[ci][p];
+            }
+        }
+    }
+}
+
+// NCHW fp32 * s -> NHWC bf16 hi/lo (only used for the 4x4 constant input; tiny)
+__global__ void __launch_bounds__(256) prescale_split_kernel(bf16* __restrict__ hi, bf16* __restrict__ lo, const float* __restrict__ x,
+                                                             const float* __restrict__ s, int batch, int C, int64_t hw) {
+    const int64_t total = (int64_t)batch * hw * C;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % C);
+        const int64_t p = (i / C) % hw;
+        const int b = (int)(i / (C * hw));
+        const float v = __fmul_rn(x[((int64_t)b * C + c) * hw + p], s[(int64_t)b * C + c]);
+        const bf16 h = __float2bfloat16_rn(v);
+        hi[i] = h;
+        lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+// scale*W [Cout][Cin][9] fp32 -> hi/lo [9][Cout][Cin] bf16
+__global__ void __launch_bounds__(256) pack_weights_kernel(bf16* __restrict__ hi, bf16* __restrict__ lo, const float* __restrict__ w,
+                                                           float scale, int cout, int cin) {
+    const int64_t total = (int64_t)9 * cout * cin;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % cin);
+        const int o = (int)((i / cin) % cout);
+        const int t = (int)(i / ((int64_t)cin * cout));
+        const float v = __fmul_rn(w[((int64_t)o * cin + ci) * 9 + t], scale);
+        const bf16 h = __float2bfloat16_rn(v);
+        hi[i] = h;
+        lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------- host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    fn = (PFN_encodeTiled)p;
+    return fn;
+}
+
+static int make_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint32_t* box) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return SIS_ERR_CUDA; }
+    cuuint64_t gdim[5]; cuuint64_t gstride[4]; cuuint32_t bdim[5]; cuuint32_t estr[5];
+    uint64_t stride = 2;
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1;
+        stride *= dims[i];
+        if (i < rank - 1) gstride[i] = stride;    // byte stride of dimension i+1
+    }
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, gdim, gstride, bdim, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank); return SIS_ERR_CUDA; }
+    return SIS_OK;
+}
+
+struct TcTensorMapCacheEntry { CUtensorMap m; };
+
+int tc_pack_weights(TcConvWeights& w, const float* d_weight, int cin, int cout, bool up, float scale, cudaStream_t stream) {
+    (void)up;
+    const size_t bytes = (size_t)9 * cin * cout * sizeof(bf16);
+    if (w.cin != cin || w.cout != cout || !w.hi) {
+        tc_free_weights(w);
+        SIS_CHECK_CUDA(cudaMalloc(&w.hi, bytes));
+        SIS_CHECK_CUDA(cudaMalloc(&w.lo, bytes));
+        w.cin = cin; w.cout = cout;
+    }
+    int64_t total = (int64_t)9 * cin * cout;
+    int grid = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)kNumSMs * 8);
+    pack_weights_kernel<<<grid, 256, 0, stream>>>((bf16*)w.hi, (bf16*)w.lo, d_weight, scale, cout, cin);
+    SIS_CHECK_LAUNCH();
+    return SIS_OK;
+}
+
+void tc_free_weights(TcConvWeights& w) {
+    if (w.hi) cudaFree(w.hi);
+    if (w.lo) cudaFree(w.lo);
+    w.hi = w.lo = nullptr; w.cin = w.cout = 0;
+}
+
+int tc_ensure_workspace(TcWorkspace& ws, int batch, int size, int c4, const std::map<int, int>& channels) {
+    if (ws.batch == batch) return SIS_OK;
+    size_t max_elems = (size_t)batch * c4 * 16;
+    for (int res = 8; res <= size; res *= 2) max_elems = std::max(max_elems, (size_t)batch * channels.at(res) * res * res);
+    const size_t bytes = max_elems * sizeof(bf16);
+    if (bytes > ws.a_bytes) {
+        for (int i = 0; i < 2; ++i) {
+            if (ws.a_hi[i]) cudaFree(ws.a_hi[i]);
+            if (ws.a_lo[i]) cudaFree(ws.a_lo[i]);
+            ws.a_hi[i] = ws.a_lo[i] = nullptr;
+        }
+        ws.a_bytes = 0;
+        for (int i = 0; i < 2; ++i) {
+            SIS_CHECK_CUDA(cudaMalloc(&ws.a_hi[i], bytes));
+            SIS_CHECK_CUDA(cudaMalloc(&ws.a_lo[i], bytes));
+        }
+        ws.a_bytes = bytes;
+    }
+    if (!ws.d_error) {
+        SIS_CHECK_CUDA(cudaMalloc((void**)&ws.d_error, sizeof(unsigned int)));
+        SIS_CHECK_CUDA(cudaMemset(ws.d_error, 0, sizeof(unsigned int)));
+    }
+    ws.batch = batch;
+    return SIS_OK;
+}
+
+void tc_free_workspace(TcWorkspace& ws) {
+    for (int i = 0; i < 2; ++i) {
+        if (ws.a_hi[i]) cudaFree(ws.a_hi[i]);
+        if (ws.a_lo[i]) cudaFree(ws.a_lo[i]);
+        ws.a_hi[i] = ws.a_lo[i] = nullptr;
+    }
+    if (ws.d_error) cudaFree(ws.d_error);
+    ws.d_error = nullptr; ws.a_bytes = 0; ws.batch = -1;
+    for (auto* e : ws.maps) delete e;
+    ws.maps.clear();
+}
+
+int tc_check_error(TcWorkspace& ws, cudaStream_t stream) {
+    if (!ws.d_error) return SIS_OK;
+    unsigned int h = 0;
+    SIS_CHECK_CUDA(cudaMemcpyAsync(&h, ws.d_error, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    SIS_CHECK_CUDA(cudaStreamSynchronize(stream));
+    if (h) { set_error("tcgen05 conv watchdog fired: code 0x%x", h); return SIS_ERR_CUDA; }
+    return SIS_OK;
+}
+
+int tc_prescale_split(TcWorkspace& ws, int slot, const float* x, const float* s, int batch, int c, int h, int w, cudaStream_t stream) {
+    const int64_t total = (int64_t)batch * c * h * w;
+    SIS_REQUIRE((size_t)total * sizeof(bf16) <= ws.a_bytes, "tc_prescale_split: workspace too small");
+    int grid = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)kNumSMs * 8);
+    prescale_split_kernel<<<grid, 256, 0, stream>>>((bf16*)ws.a_hi[slot], (bf16*)ws.a_lo[slot], x, s, batch, c, (int64_t)h * w);
+    SIS_CHECK_LAUNCH();
+    return SIS_OK;
+}
+
+template <int BN, int TH, int TW, int TB>
+static int launch_tc(const CUtensorMap maps[4], const TcKernelArgs& a, cudaStream_t stream) {
+    using Cfg = TcCfg<BN>;
+    auto kern = modconv_tc_kernel<BN, TH, TW, TB>;
+    static bool configured = false;
+    if (!configured) {
+        SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
+    kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], a);
+    SIS_CHECK_LAUNCH();
+    return SIS_OK;
+}
+
+template <int BN>
+static int launch_tc_bn(int th, int tw, int tb, const CUtensorMap maps[4], const TcKernelArgs& a, cudaStream_t stream) {
+    if (th == 4 && tw == 4 && tb == 8) return launch_tc<BN, 4, 4, 8>(maps, a, stream);
+    if (th == 8 && tw == 8 && tb == 2) return launch_tc<BN, 8, 8, 2>(maps, a, stream);
+    if (th == 8 && tw == 16 && tb == 1) return launch_tc<BN, 8, 16, 1>(maps, a, stream);
+    set_error("tc_modconv: unsupported tile box %dx%dx%d", th, tw, tb);
+    return SIS_ERR_UNSUPPORTED;
+}
+
+int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, cudaStream_t stream) {
+    SIS_REQUIRE(call.cin % BK == 0, "tc_modconv: Cin must be a multiple of 64 (got %d)", call.cin);
+    SIS_REQUIRE(call.cout % 32 == 0, "tc_modconv: Cout must be a multiple of 32 (got %d)", call.cout);
+    SIS_REQUIRE(w.hi && w.cin == call.cin && w.cout == call.cout, "tc_modconv: weights not packed for this layer");
+    const int B = call.batch, H = call.res_in;
+    const int BN = call.cout >= 256 ? 256 : call.cout;
+    SIS_REQUIRE(BN == 256 || BN == 128 || BN == 64 || BN == 32, "tc_modconv: unsupported Cout %d", call.cout);
+    // tile box by the GEMM grid extent (plain: H; transposed phases: up to H+1)
+    const int ext = call.up ? H + 1 : H;
+    int th, tw, tb;
+    if (ext <= 4) { th = 4; tw = 4; tb = 8; }
+    else if (ext <= 8) { th = 8; tw = 8; tb = 2; }
+    else { th = 8; tw = 16; tb = 1; }
+
+    TcKernelArgs a;
+    memset(&a, 0, sizeof(a));
+    a.batch = B; a.cin = call.cin; a.cout = call.cout; a.kchunks = call.cin / BK;
+    a.b_tiles = ceil_div(B, tb); a.n_tiles = call.cout / BN;
+    a.demod = call.demod; a.noise = call.noise; a.noise_bstride = call.noise_bstride; a.noise_w = call.noise_w; a.bias = call.bias;
+    a.error = ws.d_error;
+    int tiles = 0;
+    if (!call.up) {
+        a.mode = 0; a.nsub = 1;
+        TcSubProblem& s = a.sub[0];
+        s.ntaps = 9;
+        for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx) { int t = ky * 3 + kx; s.dy[t] = (signed char)(ky - 1); s.dx[t] = (signed char)(kx - 1); s.widx[t] = (signed char)t; }
+        s.oh = H; s.ow = H; s.ostride = 1; s.ooff_y = 0; s.ooff_x = 0;
+        s.tiles_y = ceil_div(H, th); s.tiles_x = ceil_div(H, tw); s.tile_begin = 0;
+        tiles = a.b_tiles * s.tiles_y * s.tiles_x * a.n_tiles;
+        a.out_f32 = call.out_f32; a.out_h = H; a.out_w = H;
+        a.s_next = call.s_next; a.next_hi = (bf16*)ws.a_hi[call.out_slot]; a.next_lo = (bf16*)ws.a_lo[call.out_slot];
+    } else {
+        // F.conv_transpose2d(stride 2, pad 0), model.py:259: out[2i+k] += x[i]*W[k]; phase p = o mod 2.
+        a.mode = 1; a.nsub = 4;
+        int si = 0;
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+                TcSubProblem& s = a.sub[si++];
+                s.ntaps = 0;
+                for (int ky = py; ky < 3; ky += 2)
+                    for (int kx = px; kx < 3; kx += 2) {
+                        s.dy[s.ntaps] = (signed char)(-(ky / 2)); s.dx[s.ntaps] = (signed char)(-(kx / 2));
+                        s.widx[s.ntaps] = (signed char)(ky * 3 + kx); s.ntaps++;
+                    }
+                s.oh = H + (py == 0 ? 1 : 0); s.ow = H + (px == 0 ? 1 : 0);
+                s.ostride = 2; s.ooff_y = py; s.ooff_x = px;
+                s.tiles_y = ceil_div(s.oh, th); s.tiles_x = ceil_div(s.ow, tw);
+                s.tile_begin = tiles;
+                tiles += a.b_tiles * s.tiles_y * s.tiles_x * a.n_tiles;
+            }
+        a.out_f32 = call.upconv_tmp; a.out_h = 2 * H + 1; a.out_w = 2 * H + 1;
+    }
+    a.total_tiles = tiles;
+
+    CUtensorMap maps[4];
+    {
+        const uint64_t adims[4] = {(uint64_t)call.cin, (uint64_t)H, (uint64_t)H, (uint64_t)B};
+        const uint32_t abox[4] = {(uint32_t)BK, (uint32_t)tw, (uint32_t)th, (uint32_t)tb};
+        SIS_PROPAGATE(make_map(&maps[0], ws.a_hi[call.in_slot], 4, adims, abox));
+        SIS_PROPAGATE(make_map(&maps[1], ws.a_lo[call.in_slot], 4, adims, abox));
+        const uint64_t wdims[3] = {(uint64_t)call.cin, (uint64_t)call.cout, 9};
+        const uint32_t wbox[3] = {(uint32_t)BK, (uint32_t)BN, 1};
+        SIS_PROPAGATE(make_map(&maps[2], w.hi, 3, wdims, wbox));
+        SIS_PROPAGATE(make_map(&maps[3], w.lo, 3, wdims, wbox));
+    }
+    int st;
+    if (BN == 256) st = launch_tc_bn<256>(th, tw, tb, maps, a, stream);
+    else if (BN == 128) st = launch_tc_bn<128>(th, tw, tb, maps, a, stream);
+    else if (BN == 64) st = launch_tc_bn<64>(th, tw, tb, maps, a, stream);
+    else st = launch_tc_bn<32>(th, tw, tb, maps, a, stream);
+    SIS_PROPAGATE(st);
+
+    if (call.up) {
+        BlurSplitArgs bs;
+        bs.in = call.upconv_tmp; bs.IH = 2 * H + 1; bs.IW = 2 * H + 1;
+        bs.out_f32 = call.out_f32; bs.OH = call.res_out; bs.OW = call.res_out; bs.C = call.cout; bs.batch = B;
+        bs.blur_k = call.blur_k; bs.noise = call.noise; bs.noise_bstride = call.noise_bstride; bs.noise_w = call.noise_w; bs.bias = call.bias;
+        bs.s_next = call.s_next; bs.next_hi = (bf16*)ws.a_hi[call.out_slot]; bs.next_lo = (bf16*)ws.a_lo[call.out_slot];
+        const int64_t total = (int64_t)B * ceil_div(bs.OH, BS_TH) * ceil_div(bs.OW, BS_TW) * (bs.C / BS_C);
+        const int grid = (int)std::min<int64_t>(total, (int64_t)kNumSMs * 4);
+        blur_act_split_kernel<<<grid, 256, 0, stream>>>(bs);
+        SIS_CHECK_LAUNCH();
+    }
+    return SIS_OK;
+}
+
+}  // namespace sis

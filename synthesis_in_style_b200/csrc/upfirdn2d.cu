@@ -1,0 +1,238 @@
+// upfirdn2d: zero-insert upsample -> pad -> 2-D FIR (true convolution, flipped taps) -> decimate.
+// Replaces upfirdn2d_kernel / upfirdn2d_op (scf/networks/stylegan2/op/upfirdn2d_kernel.cu:52-272).
+//
+// Index math per output (same as the reference kernel, :112-121):
+//   mid = o*down + up - 1 - pad0 ; in0 = floor(mid / up) ; k0 = (in0+1)*up - mid - 1
+//   v = sum_{y} sum_{x} in[in0y + y][in0x + x] * kflip[k0y + y*up][k0x + x*up]      (y outer, x inner,
+//   accumulated as an FMA chain from 0, which is what nvcc makes of the reference's `v += a*b`).
+//
+// Two paths, both sm_100a CUDA:
+//   * tiled fp32 path for minor == 1 and the reference's six (up, down, K) modes: per-plane output tile
+//     32x64, input tile + halo staged in shared memory with coalesced row loads, 4 consecutive outputs per
+//     thread with 128-bit stores.  HBM-bound: (N_in + N_out)*4 algorithmic bytes.
+//   * generic path for every other (dtype, minor, up, down, kernel <= 32x32): one thread per output.
+#include "common.cuh"
+
+namespace sis {
+
+__host__ __device__ __forceinline__ int floor_div(int a, int b) {
+    int c = a / b;
+    if (c * b > a) c--;
+    return c;
+}
+
+struct UpfirdnParams {
+    int up_x, up_y, down_x, down_y, pad_x0, pad_y0;
+    int in_h, in_w, minor, kernel_h, kernel_w, out_h, out_w;
+    int64_t major;
+};
+
+constexpr int kMaxTaps = 32;
+
+// ---------------------------------------------------------------------------------------------- generic
+template <typename T> struct Acc;
+template <> struct Acc<float> {
+    using type = float;
+    static __device__ __forceinline__ float mac(float v, float a, float k) { return __fmaf_rn(a, k, v); }
+};
+template <> struct Acc<double> {
+    // the reference stages input and taps in `volatile float` shared memory (upfirdn2d_kernel.cu:56-57):
+    // products are float, the running sum is double.
+    using type = double;
+    static __device__ __forceinline__ double mac(double v, float a, float k) { return v + (double)__fmul_rn(a, k); }
+};
+template <> struct Acc<__half> {
+    using type = __half;
+    static __device__ __forceinline__ __half mac(__half v, float a, float k) {
+        __half p = __float2half_rn(__fmul_rn(a, k));
+        return __float2half_rn(__fadd_rn(__half2float(v), __half2float(p)));
+    }
+};
+template <typename T> __device__ __forceinline__ float to_f(T v) { return (float)v; }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T zero_of() { return (T)0; }
+template <> __device__ __forceinline__ __half zero_of<__half>() { return __float2half(0.0f); }
+
+template <typename T>
+__global__ void __launch_bounds__(256) upfirdn2d_generic_kernel(T* __restrict__ out, const T* __restrict__ in,
+                                                                const T* __restrict__ kernel, UpfirdnParams p) {
+    __shared__ float sk[kMaxTaps * kMaxTaps];
+    for (int t = threadIdx.x; t < p.kernel_h * p.kernel_w; t += blockDim.x) {
+        int ky = t / p.kernel_w, kx = t - ky * p.kernel_w;
+        sk[t] = to_f<T>(kernel[(p.kernel_h - 1 - ky) * p.kernel_w + (p.kernel_w - 1 - kx)]);  // flipped
+    }
+    __syncthreads();
+    const int64_t total = p.major * p.out_h * p.out_w * p.minor;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) {
+        int m = (int)(idx % p.minor);
+        int64_t r = idx / p.minor;
+        int ox = (int)(r % p.out_w); r /= p.out_w;
+        int oy = (int)(r % p.out_h);
+        int64_t mj = r / p.out_h;
+        int mid_x = ox * p.down_x + p.up_x - 1 - p.pad_x0;
+        int mid_y = oy * p.down_y + p.up_y - 1 - p.pad_y0;
+        int in_x0 = floor_div(mid_x, p.up_x), in_y0 = floor_div(mid_y, p.up_y);
+        int kx0 = (in_x0 + 1) * p.up_x - mid_x - 1, ky0 = (in_y0 + 1) * p.up_y - mid_y - 1;
+        typename Acc<T>::type v = zero_of<T>();
+        for (int y = 0, ky = ky0; ky < p.kernel_h; ++y, ky += p.up_y) {
+            int iy = in_y0 + y;
+            for (int x = 0, kx = kx0; kx < p.kernel_w; ++x, kx += p.up_x) {
+                int ix = in_x0 + x;
+                float a = 0.0f;
+                if (ix >= 0 && iy >= 0 && ix < p.in_w && iy < p.in_h)
+                    a = to_f<T>(in[((mj * p.in_h + iy) * p.in_w + ix) * p.minor + m]);
+                v = Acc<T>::mac(v, a, sk[ky * p.kernel_w + kx]);
+            }
+        }
+        out[idx] = v;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ tiled
+// One block = one TH x TW output tile of one plane (minor == 1).  K = padded (template) tap count as in the
+// reference's mode table; taps beyond the real kernel are zero, so the FMA chain has the reference's order.
+template <int UP, int DOWN, int K, int TH, int TW>
+__global__ void __launch_bounds__(TH * TW / 4) upfirdn2d_tiled_kernel(float* __restrict__ out,
+                                                                     const float* __restrict__ in,
+                                                                     const float* __restrict__ kernel,
+                                                                     UpfirdnParams p, int tiles_x, int tiles_y) {
+    constexpr int TIN_H = ((TH - 1) * DOWN + K - 1) / UP + 1;
+    constexpr int TIN_W = ((TW - 1) * DOWN + K - 1) / UP + 1;
+    constexpr int TIN_WP = TIN_W + 1;
+    constexpr int NT = TH * TW / 4;
+    __shared__ float sk[K][K];
+    __shared__ float sx[TIN_H][TIN_WP];
+
+    for (int t = threadIdx.x; t < K * K; t += NT) {
+        int ky = t / K, kx = t - ky * K;
+        float v = 0.0f;
+        if (kx < p.kernel_w && ky < p.kernel_h) v = kernel[(p.kernel_h - 1 - ky) * p.kernel_w + (p.kernel_w - 1 - kx)];
+        sk[ky][kx] = v;
+    }
+    const int64_t tiles_per_plane = (int64_t)tiles_x * tiles_y;
+    const int64_t total_tiles = tiles_per_plane * p.major;
+    const int tx = threadIdx.x % (TW / 4), ty = threadIdx.x / (TW / 4);
+
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int64_t plane = tile / tiles_per_plane;
+        const int trem = (int)(tile - plane * tiles_per_plane);
+        const int tile_out_y = (trem / tiles_x) * TH, tile_out_x = (trem % tiles_x) * TW;
+        const int tile_mid_x = tile_out_x * DOWN + UP - 1 - p.pad_x0;
+        const int tile_mid_y = tile_out_y * DOWN + UP - 1 - p.pad_y0;
+        const int tile_in_x = floor_div(tile_mid_x, UP), tile_in_y = floor_div(tile_mid_y, UP);
+        const float* src = in + plane * (int64_t)p.in_h * p.in_w;
+        __syncthreads();
+        for (int i = threadIdx.x; i < TIN_H * TIN_W; i += NT) {
+            int ry = i / TIN_W, rx = i - ry * TIN_W;
+            int ix = rx + tile_in_x, iy = ry + tile_in_y;
+            float v = 0.0f;
+            if (ix >= 0 && iy >= 0 && ix < p.in_w && iy < p.in_h) v = __ldg(src + (int64_t)iy * p.in_w + ix);
+            sx[ry][rx] = v;
+        }
+        __syncthreads();
+        const int oy = tile_out_y + ty;
+        const int mid_y = tile_mid_y + ty * DOWN;
+        const int in_y = floor_div(mid_y, UP);
+        const int rel_y = in_y - tile_in_y;
+        const int ky0 = (in_y + 1) * UP - mid_y - 1;
+        float res[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int rel_ox = tx * 4 + j;
+            const int mid_x = tile_mid_x + rel_ox * DOWN;
+            const int in_x = floor_div(mid_x, UP);
+            const int rel_x = in_x - tile_in_x;
+            const int kx0 = (in_x + 1) * UP - mid_x - 1;
+            float v = 0.0f;
+#pragma unroll
+            for (int y = 0; y < K / UP; ++y)
+#pragma unroll
+                for (int x = 0; x < K / UP; ++x)
+                    v = __fmaf_rn(sx[rel_y + y][rel_x + x], sk[ky0 + y * UP][kx0 + x * UP], v);
+            res[j] = v;
+        }
+        if (oy < p.out_h) {
+            float* dst = out + (plane * p.out_h + oy) * (int64_t)p.out_w + tile_out_x + tx * 4;
+            const int ox = tile_out_x + tx * 4;
+            if (ox + 3 < p.out_w && ((((uintptr_t)dst) & 15) == 0)) {
+                st_stream_f4((float4*)dst, make_float4(res[0], res[1], res[2], res[3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if (ox + j < p.out_w) dst[j] = res[j];
+            }
+        }
+    }
+}
+
+template <int UP, int DOWN, int K>
+static void launch_tiled(float* out, const float* in, const float* kernel, const UpfirdnParams& p,
+                         cudaStream_t stream) {
+    constexpr int TH = 16, TW = 64;
+    int tiles_x = ceil_div(p.out_w, TW), tiles_y = ceil_div(p.out_h, TH);
+    int64_t total = (int64_t)tiles_x * tiles_y * p.major;
+    int64_t cap = (int64_t)kNumSMs * 8;
+    int grid = (int)(total < cap ? total : cap);
+    upfirdn2d_tiled_kernel<UP, DOWN, K, TH, TW><<<grid, TH * TW / 4, 0, stream>>>(out, in, kernel, p, tiles_x, tiles_y);
+}
+
+}  // namespace sis
+
+using namespace sis;
+
+extern "C" int sis_upfirdn2d_out_size(int in_size, int up, int down, int pad0, int pad1, int ksize) {
+    // upfirdn2d_kernel.cu:168-169
+    return (in_size * up + pad0 + pad1 - ksize + down) / down;
+}
+
+extern "C" int sis_upfirdn2d(void* d_out, const void* d_x, const void* d_kernel, int dtype, int64_t major, int in_h,
+                             int in_w, int minor, int kernel_h, int kernel_w, int up_x, int up_y, int down_x,
+                             int down_y, int pad_x0, int pad_x1, int pad_y0, int pad_y1, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIS_REQUIRE(up_x >= 1 && up_y >= 1 && down_x >= 1 && down_y >= 1, "upfirdn2d: up/down must be >= 1");
+    SIS_REQUIRE(kernel_h >= 1 && kernel_w >= 1 && kernel_h <= kMaxTaps && kernel_w <= kMaxTaps,
+                "upfirdn2d: kernel must be between 1x1 and %dx%d (got %dx%d)", kMaxTaps, kMaxTaps, kernel_h, kernel_w);
+    SIS_REQUIRE(major >= 0 && in_h >= 0 && in_w >= 0 && minor >= 0, "upfirdn2d: negative size");
+    UpfirdnParams p;
+    p.up_x = up_x; p.up_y = up_y; p.down_x = down_x; p.down_y = down_y; p.pad_x0 = pad_x0; p.pad_y0 = pad_y0;
+    p.in_h = in_h; p.in_w = in_w; p.minor = minor; p.kernel_h = kernel_h; p.kernel_w = kernel_w; p.major = major;
+    p.out_h = sis_upfirdn2d_out_size(in_h, up_y, down_y, pad_y0, pad_y1, kernel_h);
+    p.out_w = sis_upfirdn2d_out_size(in_w, up_x, down_x, pad_x0, pad_x1, kernel_w);
+    SIS_REQUIRE(p.out_h >= 0 && p.out_w >= 0, "upfirdn2d: negative output size %dx%d", p.out_h, p.out_w);
+    const int64_t total = major * p.out_h * p.out_w * minor;
+    if (total == 0) return SIS_OK;
+    SIS_REQUIRE(d_out && d_kernel, "upfirdn2d: kernel must be a CUDA tensor (null pointer)");
+    SIS_REQUIRE(d_x || (int64_t)in_h * in_w * minor * major == 0, "upfirdn2d: input must be a CUDA tensor (null pointer)");
+
+    bool done = false;
+    if (dtype == SIS_F32 && minor == 1 && up_x == up_y && down_x == down_y && in_h > 0 && in_w > 0) {
+        float* o = (float*)d_out; const float* x = (const float*)d_x; const float* k = (const float*)d_kernel;
+        const int kmax = kernel_h > kernel_w ? kernel_h : kernel_w;
+        done = true;
+        // the reference's mode table (upfirdn2d_kernel.cu:177-211); later matches override earlier ones there.
+        if (up_x == 1 && down_x == 1 && kmax <= 3) launch_tiled<1, 1, 3>(o, x, k, p, stream);
+        else if (up_x == 1 && down_x == 1 && kmax <= 4) launch_tiled<1, 1, 4>(o, x, k, p, stream);
+        else if (up_x == 2 && down_x == 1 && kmax <= 2) launch_tiled<2, 1, 2>(o, x, k, p, stream);
+        else if (up_x == 2 && down_x == 1 && kmax <= 4) launch_tiled<2, 1, 4>(o, x, k, p, stream);
+        else if (up_x == 1 && down_x == 2 && kmax <= 4) launch_tiled<1, 2, 4>(o, x, k, p, stream);  // modes 5 and 6
+        else done = false;
+    }
+    if (!done) {
+        int64_t blocks = ceil_div64(total, 256);
+        int64_t cap = (int64_t)kNumSMs * 8;
+        int grid = (int)(blocks < cap ? blocks : cap);
+        if (dtype == SIS_F32)
+            upfirdn2d_generic_kernel<float><<<grid, 256, 0, stream>>>((float*)d_out, (const float*)d_x, (const float*)d_kernel, p);
+        else if (dtype == SIS_F64)
+            upfirdn2d_generic_kernel<double><<<grid, 256, 0, stream>>>((double*)d_out, (const double*)d_x, (const double*)d_kernel, p);
+        else if (dtype == SIS_F16)
+            upfirdn2d_generic_kernel<__half><<<grid, 256, 0, stream>>>((__half*)d_out, (const __half*)d_x, (const __half*)d_kernel, p);
+        else {
+            set_error("upfirdn2d: unsupported dtype %d", dtype);
+            return SIS_ERR_UNSUPPORTED;
+        }
+    }
+    SIS_CHECK_LAUNCH();
+    return SIS_OK;
+}

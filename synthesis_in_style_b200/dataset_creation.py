@@ -1,0 +1,152 @@
+"""Latent / noise stream, batched generation and the seed-sharded labelled-pair pipeline.
+
+Mirrors
+  scf/latent_projecting/__init__.py:15-28      Latents
+  scf/utils/dataset_creation.py:32-58          build_latent_and_noise_generator, generate_images
+  scf/create_dataset_for_segmentation.py:109-148  the per-batch hot loop (GPU part)
+and adds the multi-GPU partitioning of SURVEY.md §8e: one process per GPU, batch index b is owned by rank
+b mod world_size, every rank replays the single reference RNG stream (CPU latents, device noise) and keeps only
+its own batches, so the union over ranks equals the reference's single-process run on the same seed.  The only
+collective is one all-reduce of an int64 statistics vector (NCCL on GPUs, gloo in the CPU tests).
+"""
+from dataclasses import dataclass
+from typing import Dict, Iterable, Iterator, List, Optional, Tuple
+
+import torch
+
+from .labelling import ClusterSegmenter, make_image
+from .model import Generator
+
+
+@dataclass
+class Latents:
+    latent: torch.Tensor
+    noise: List[torch.Tensor]
+
+    def to(self, device) -> 'Latents':
+        self.latent = self.latent.to(device)
+        self.noise = [n.to(device) for n in self.noise]
+        return self
+
+    def __getitem__(self, key: int) -> 'Latents':
+        return Latents(self.latent[key].unsqueeze(0), [n[key].unsqueeze(0) for n in self.noise])
+
+    def detach(self):
+        self.latent = self.latent.detach()
+        self.noise = [n.detach() for n in self.noise]
+
+    def numpy(self) -> 'Latents':
+        return Latents(self.latent.cpu().numpy(), [n.cpu().numpy() for n in self.noise])
+
+
+def _decoder_of(model):
+    """The reference passes a StyleganAutoencoder whose `.decoder` is the Generator (networks/encoder/autoencoder.py);
+    a bare Generator is accepted as well."""
+    return getattr(model, 'decoder', model)
+
+
+def build_latent_and_noise_generator(autoencoder, config: Dict, seed=1) -> Iterable[Latents]:
+    """Seeded, infinite (latent, noise) stream: z = randn(B, latent_size) on the CPU generator, noise maps from
+    `decoder.make_noise()` on the decoder's device; the seed is applied lazily at the first `next()`
+    (utils/dataset_creation.py:32-37)."""
+    decoder = _decoder_of(autoencoder)
+    torch.random.manual_seed(seed)
+    while True:
+        latent_code = torch.randn(config['batch_size'], config['latent_size'])
+        noise = decoder.make_noise()
+        yield Latents(latent_code, noise)
+
+
+def generate_images(batch: Latents, autoencoder, device: str = 'cuda', mean_latent: Optional[torch.Tensor] = None,
+                    capture_layers=None) -> Tuple[Dict[int, torch.Tensor], torch.Tensor]:
+    """(activations, image) exactly as utils/dataset_creation.py:40-58: truncation 0.7 iff mean_latent is given."""
+    if not isinstance(batch, Latents):
+        raise NotImplementedError('the encoder path (dict batches) is outside the hot path (SURVEY.md §2 row 16)')
+    latents = batch.to(device)
+    decoder = _decoder_of(autoencoder)
+    kwargs = {}
+    if capture_layers is not None:
+        kwargs['capture_layers'] = capture_layers
+    with torch.no_grad():
+        image, activations = decoder(
+            [latents.latent], input_is_latent=False, noise=latents.noise, return_intermediate_activations=True,
+            truncation=0.7 if mean_latent is not None else 1, truncation_latent=mean_latent, **kwargs)
+    return activations, image
+
+
+# ------------------------------------------------------------------------------------------- sharding
+def owned_batches(rank: int, world_size: int, num_batches: int) -> List[int]:
+    """Batch indices owned by `rank` (round-robin; the unit is a batch because noise is drawn per batch)."""
+    return list(range(rank, num_batches, world_size))
+
+
+def sharded_latent_stream(generator: Generator, config: Dict, seed: int, rank: int, world_size: int) -> Iterator[Tuple[int, Latents]]:
+    """Replay of the reference's single stream: every rank draws every batch (CPU latents are positional; the
+    device Philox stream advances identically on every GPU) and yields only its own."""
+    stream = iter(build_latent_and_noise_generator(generator, config, seed=seed))
+    idx = 0
+    while True:
+        batch = next(stream)
+        if idx % world_size == rank:
+            yield idx, batch
+        idx += 1
+
+
+@dataclass
+class LabelledBatch:
+    batch_index: int
+    image: torch.Tensor                      # [B, 3, S, S] fp32, unclamped (what the reference hands to make_image)
+    masks: Dict[str, Dict[str, torch.Tensor]]  # PredictedClusters at S x S (bool)
+    activations: Dict[int, torch.Tensor]
+
+
+class LabelledPairGenerator:
+    """GPU part of `build_dataset`'s loop: generate -> label, per batch, for this rank's shard."""
+
+    def __init__(self, generator: Generator, segmenter: ClusterSegmenter, config: Dict, seed: int = 1,
+                 mean_latent: Optional[torch.Tensor] = None, rank: int = 0, world_size: int = 1,
+                 capture_only_labelled: bool = False):
+        self.generator, self.segmenter = generator, segmenter
+        self.config, self.seed, self.mean_latent = config, seed, mean_latent
+        self.rank, self.world_size = rank, world_size
+        # key 0 must always be present: the reference reads the batch size from activations[0]
+        # (black_white_handwritten_printed_text_segmenter.py:79)
+        self.capture_layers = sorted({0} | {int(k) for k in segmenter.catalog}) if capture_only_labelled else None
+        self.stats = {'pairs': 0, 'batches': 0}
+
+    def __iter__(self) -> Iterator[LabelledBatch]:
+        device = self.generator.input.input.device
+        for idx, latents in sharded_latent_stream(self.generator, self.config, self.seed, self.rank, self.world_size):
+            acts, image = generate_images(latents, self.generator, device=device, mean_latent=self.mean_latent,
+                                          capture_layers=self.capture_layers)
+            masks = self.segmenter.prepare_image_segmentation(acts)
+            masks = self.segmenter.merge_sub_images(masks)
+            self.stats['pairs'] += image.shape[0]
+            self.stats['batches'] += 1
+            yield LabelledBatch(idx, image, masks, acts)
+
+    def stats_vector(self) -> torch.Tensor:
+        """int64 [sum_k cluster pixel counts per labelled layer | pairs | batches] on the generator's device."""
+        device = self.generator.input.input.device
+        parts = [self.segmenter.cluster_pixel_counts.get(k, torch.zeros(self.segmenter.catalog[k].k, dtype=torch.int64, device=device))
+                 for k in sorted(self.segmenter.catalog)]
+        tail = torch.tensor([self.stats['pairs'], self.stats['batches']], dtype=torch.int64, device=device)
+        return torch.cat([p.to(device) for p in parts] + [tail])
+
+
+def reduce_stats(vec: torch.Tensor) -> torch.Tensor:
+    """The path's only collective: all-reduce(SUM) of the statistics vector (no-op without a process group)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(vec, op=dist.ReduceOp.SUM)
+    return vec
+
+
+def split_stats(vec: torch.Tensor, catalog_sizes: Dict[str, int]) -> Dict:
+    """Inverse of `stats_vector` layout."""
+    out, off = {'cluster_pixels': {}}, 0
+    for k in sorted(catalog_sizes):
+        out['cluster_pixels'][k] = vec[off:off + catalog_sizes[k]].tolist()
+        off += catalog_sizes[k]
+    out['pairs'], out['batches'] = int(vec[off]), int(vec[off + 1])
+    return out

@@ -1,0 +1,329 @@
+"""Activation -> semantic-class labelling on the device, with the reference's segmenter surface.
+
+Mirrors the GPU part of
+  scf/segmentation/gan_local_edit/factor_catalog.py:47-75         FactorCatalog.predict
+  scf/segmentation/base_dataset_segmenter.py:15-50                BaseDatasetSegmenter
+  scf/segmentation/base_cluster_based_dataset_segmenter.py:18-146 BaseClusterBasedDatasetSegmenter
+  scf/segmentation/black_white_handwritten_printed_text_segmenter.py:11-40
+`PredictedClusters` keeps the reference's shape: {layer_str: {class_name: bool Tensor[B, S, S]}}.
+The reference's per-layer chain (device->host copy, [N,k,C] temporary, argmin, host->device copy, k compare
+kernels per class, uint8 nearest interpolate) is one `sis_label_assign` launch per layer here.
+The CPU contour post-processing that follows in the reference (`create_segmentation_image`) is a SURVEY §8f
+"next" row and is not part of this package yet.
+"""
+import json
+import pickle
+from collections import defaultdict
+from pathlib import Path
+from typing import Dict, List, Optional, Set
+
+import numpy
+import torch
+
+from . import _lib
+
+PredictedClusters = Dict[str, Dict[str, torch.Tensor]]
+
+
+class FactorCatalog:
+    """Inference half of the reference's FactorCatalog: k centroids [k, C] and `predict`."""
+
+    def __init__(self, k: int, centroids=None):
+        self.k = k
+        self.cluster_centers = None
+        self._centroids_host = None
+        self.annotations = {}
+        if centroids is not None:
+            self.set_centroids(centroids)
+
+    def set_centroids(self, centroids):
+        c = torch.as_tensor(numpy.asarray(centroids.detach().cpu() if isinstance(centroids, torch.Tensor) else centroids),
+                            dtype=torch.float32).contiguous()
+        if c.dim() != 2:
+            raise ValueError('centroids must be [k, C]')
+        self._centroids_host = c
+        self.k = c.shape[0]
+        self.cluster_centers = None
+
+    def centroids_on(self, device) -> torch.Tensor:
+        if self._centroids_host is None:
+            raise RuntimeError('FactorCatalog has no centroids')
+        if self.cluster_centers is None or self.cluster_centers.device != torch.device(device):
+            self.cluster_centers = self._centroids_host.to(device)
+        return self.cluster_centers
+
+    def predict(self, X: torch.Tensor) -> torch.Tensor:
+        """[B, C, H, W] fp32 CUDA -> int64 [B, H, W] cluster ids (ties -> lowest id), all on the device."""
+        ids, _ = label_assign(X, self.centroids_on(X.device), want_ids_i64=True)
+        return ids
+
+    def __repr__(self):
+        return f'FactorCatalog(k={self.k})'
+
+
+def label_assign(act: torch.Tensor, centroids: torch.Tensor, class_bits: Optional[torch.Tensor] = None, n_class: int = 0,
+                 image_size: int = 0, mode: int = 0, want_ids_i64: bool = False, want_ids_u8: bool = False,
+                 want_margin: bool = False, hist: Optional[torch.Tensor] = None):
+    """One `sis_label_assign` launch.  Returns (ids or None, dict(masks=uint8 [n_class,B,S,S], margin=..., ids_u8=...))."""
+    _lib.require_cuda(act, 'activations')
+    _lib.require_cuda(centroids, 'centroids')
+    if act.dim() != 4:
+        raise RuntimeError('activations must be [B, C, H, W]')
+    x = act.contiguous().float()
+    c = centroids.contiguous().float()
+    b, ch, h, w = x.shape
+    if c.shape[1] != ch:
+        raise RuntimeError(f'centroids have {c.shape[1]} channels, activations {ch}')
+    dev = x.device
+    out_hw = (image_size, image_size) if mode == 1 else (h, w)
+    want_masks = class_bits is not None and n_class > 0
+    need_u8 = want_ids_u8 or (want_masks and mode == 0 and (image_size % h or image_size % w or h != w))
+    ids64 = torch.empty((b,) + out_hw, dtype=torch.int64, device=dev) if want_ids_i64 else None
+    ids8 = torch.empty((b,) + out_hw, dtype=torch.uint8, device=dev) if need_u8 else None
+    margin = torch.empty((b,) + out_hw, dtype=torch.float32, device=dev) if want_margin else None
+    masks = torch.empty((n_class, b, image_size, image_size), dtype=torch.uint8, device=dev) if want_masks else None
+    if hist is not None:
+        _lib.require_cuda(hist, 'hist')
+        if hist.dtype != torch.int64 or hist.numel() < c.shape[0] or not hist.is_contiguous():
+            raise RuntimeError('hist must be a contiguous int64 tensor with >= k entries')
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().sis_label_assign(
+            _lib.ptr(x), b, ch, h, w, _lib.ptr(c), c.shape[0], _lib.ptr(class_bits), n_class, image_size, mode,
+            _lib.ptr(ids8), _lib.ptr(ids64), _lib.ptr(masks), _lib.ptr(margin), _lib.ptr(hist),
+            _lib.current_stream_ptr(dev)))
+    return ids64, {'masks': masks, 'margin': margin, 'ids_u8': ids8}
+
+
+def extract_centroids_from_pickle(path) -> Dict[str, numpy.ndarray]:
+    """Read a reference catalog pickle (`catalogs/{k}.pkl`: {str(layer): FactorCatalog, 'id_to_size_map': ...},
+    scf/create_semantic_segmentation.py:123-137) WITHOUT importing sklearn or the reference: every unknown class is
+    replaced by a plain attribute bag, and `_factorization.cluster_centers_` is pulled out."""
+
+    class _Bag:
+        def __init__(self, *a, **k):
+            pass
+
+        def __setstate__(self, state):
+            if isinstance(state, dict):
+                self.__dict__.update(state)
+            elif isinstance(state, tuple) and len(state) == 2 and isinstance(state[1], dict):
+                self.__dict__.update(state[1] or {})
+                if isinstance(state[0], dict):
+                    self.__dict__.update(state[0])
+
+    class _Unpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            if module.split('.')[0] in ('numpy', 'builtins', 'collections', 'copyreg', '_codecs'):
+                return super().find_class(module, name)
+            return type(name, (_Bag,), {})
+
+    with open(path, 'rb') as f:
+        obj = _Unpickler(f).load()
+    out = {}
+    for key, val in obj.items():
+        fact = getattr(val, '_factorization', None)
+        centers = getattr(fact, 'cluster_centers_', None) if fact is not None else None
+        if centers is not None:
+            out[str(key)] = numpy.asarray(centers, dtype=numpy.float32)
+    return out
+
+
+def load_catalog_file(path) -> Dict[str, FactorCatalog]:
+    """`.npz` ({layer: float32 [k, C]}) or a reference `.pkl`."""
+    path = Path(path)
+    if path.suffix == '.npz':
+        with numpy.load(path) as z:
+            cents = {k: z[k] for k in z.files}
+    else:
+        cents = extract_centroids_from_pickle(path)
+    return {k: FactorCatalog(v.shape[0], v) for k, v in cents.items()}
+
+
+class BaseDatasetSegmenter:
+    """scf/segmentation/base_dataset_segmenter.py:15-50 (device part)."""
+
+    def __init__(self, base_dir, image_size: int, class_to_color_map: Dict):
+        self.base_dir = Path(base_dir) if base_dir is not None else None
+        self.image_size = image_size
+        self.debug = False
+        self.debug_images = {}
+        self.class_to_color_map = self.load_class_to_color_map(class_to_color_map)
+        self.class_id_map = self.build_class_id_map(self.class_to_color_map)
+
+    @staticmethod
+    def load_class_to_color_map(class_to_color_map: dict) -> dict:
+        def rgb(color):
+            if isinstance(color, str) and color.startswith('#') and len(color) == 7:
+                return tuple(int(color[i:i + 2], 16) for i in (1, 3, 5))
+            from PIL import ImageColor
+            return ImageColor.getrgb(color)
+        return {name: rgb(color) for name, color in class_to_color_map.items()}
+
+    @staticmethod
+    def build_class_id_map(class_to_color_map: dict) -> dict:
+        return {name: i for i, name in enumerate(class_to_color_map)}
+
+    def resize_to_image_size(self, tensors: PredictedClusters) -> PredictedClusters:
+        """Nearest resize of every class mask to image_size (base_dataset_segmenter.py:32-42)."""
+        lib = _lib.load()
+        resized = {}
+        for key, class_tensors in tensors.items():
+            out = {}
+            for class_name, t in class_tensors.items():
+                if t.shape[-1] < self.image_size:
+                    _lib.require_cuda(t, 'mask')
+                    src = t.contiguous().view(torch.uint8) if t.dtype == torch.bool else t.contiguous().to(torch.uint8)
+                    dst = torch.empty(t.shape[0], self.image_size, self.image_size, dtype=torch.uint8, device=t.device)
+                    with torch.cuda.device(t.device):
+                        _lib.check(lib.sis_nearest_resize_u8(_lib.ptr(src), t.shape[0], t.shape[-2], t.shape[-1],
+                                                             self.image_size, self.image_size, _lib.ptr(dst),
+                                                             _lib.current_stream_ptr(t.device)))
+                    t = dst.view(torch.bool) if t.dtype == torch.bool else dst.to(t.dtype)
+                out[class_name] = t
+            resized[key] = out
+        return resized
+
+    def create_segmentation_image(self, activations):
+        raise NotImplementedError('CPU contour post-processing is a SURVEY.md §8f "next" row')
+
+
+class ClusterSegmenter(BaseDatasetSegmenter):
+    """BaseClusterBasedDatasetSegmenter + BlackWhiteHandwrittenPrintedTextDatasetSegmenter, device part
+    (base_cluster_based_dataset_segmenter.py:18-146, black_white_handwritten_printed_text_segmenter.py:11-40)."""
+
+    def __init__(self, base_dir, image_size: int, class_to_color_map: Dict, keys_for_class_determination: List[str],
+                 keys_for_finegrained_segmentation: List[str], num_clusters: int, min_class_contour_area: int = 0,
+                 only_keep_overlapping: bool = True, keys_to_merge: Optional[Dict[str, List[str]]] = None,
+                 catalog: Optional[Dict[str, FactorCatalog]] = None, class_label_map: Optional[Dict] = None):
+        super().__init__(base_dir, image_size, class_to_color_map)
+        self.keys_for_class_determination = list(keys_for_class_determination)
+        self.keys_for_finegrained_segmentation = list(keys_for_finegrained_segmentation)
+        self.keys_for_generation = self.keys_for_class_determination + self.keys_for_finegrained_segmentation
+        self.num_clusters = num_clusters
+        self.min_class_contour_area = min_class_contour_area
+        self.only_keep_overlapping = only_keep_overlapping
+        self.handwriting_overlap_threshold = 0.5
+        self.catalog = self.adjust_catalog(catalog) if catalog is not None else self.load_catalog()
+        self.class_label_map = self.invert_class_label_map(class_label_map) if class_label_map is not None \
+            else self.load_class_label_map()
+        self.keys_to_merge = keys_to_merge or {}
+        merged_sources = [k for ks in self.keys_to_merge.values() for k in ks]
+        relevant = set(self.keys_for_generation + merged_sources)
+        self.keys_for_generation = set(self.keys_for_generation + merged_sources)
+        unlabelled = self.check_sanity_of_class_label_map(relevant)
+        assert not unlabelled, f'Some of the activation maps were not labelled completely (map_id: cluster_id):\n{unlabelled}'
+        self._bits_cache = {}
+        self.cluster_pixel_counts: Dict[str, torch.Tensor] = {}
+
+    # -- inputs on disk -------------------------------------------------------------------------------------
+    def adjust_catalog(self, catalog: dict) -> dict:
+        return {k: v for k, v in catalog.items() if k in self.keys_for_generation}
+
+    def load_catalog(self) -> dict:
+        base = self.base_dir / 'catalogs'
+        for suffix in ('.npz', '.pkl'):
+            f = base / f'{self.num_clusters}{suffix}'
+            if f.exists():
+                return self.adjust_catalog(load_catalog_file(f))
+        raise FileNotFoundError(f'no catalog {base}/{self.num_clusters}.npz|.pkl')
+
+    @staticmethod
+    def invert_class_label_map(class_label_map: Dict[str, Dict[str, str]]) -> Dict[str, Dict[str, List[int]]]:
+        """{layer: {cluster_id: class_name}} -> {layer: {class_name: [cluster ids]}} (…segmenter.py:56-67)."""
+        inverted = {}
+        for key, sub in class_label_map.items():
+            inv = defaultdict(list)
+            for sub_key, label_name in sub.items():
+                inv[label_name].append(int(sub_key))
+            inverted[key] = inv
+        return inverted
+
+    def load_class_label_map(self):
+        with (self.base_dir / f'merged_classes_{self.num_clusters}.json').open() as f:
+            return self.invert_class_label_map(json.load(f))
+
+    def check_sanity_of_class_label_map(self, relevant_keys: Set) -> Dict:
+        color_keys = list(self.class_to_color_map.keys())
+        unlabelled = {}
+        for key in relevant_keys:
+            for class_label in self.class_label_map[key]:
+                if class_label not in color_keys:
+                    unlabelled.setdefault(key, []).append(class_label)
+        return unlabelled
+
+    # -- device path ------------------------------------------------------------------------------------------
+    def _class_bits(self, layer_id: str, class_label_map, device):
+        """uint32 [k]: bit j set <=> cluster belongs to the j-th class of class_label_map[layer_id]."""
+        names = list(class_label_map[layer_id].keys())
+        key = (layer_id, tuple((n, tuple(class_label_map[layer_id][n])) for n in names), str(device))
+        if key not in self._bits_cache:
+            k = self.catalog[layer_id].k
+            bits = numpy.zeros(k, dtype=numpy.uint32)
+            if len(names) > 32:
+                raise RuntimeError('at most 32 classes per layer')
+            for j, n in enumerate(names):
+                for cid in class_label_map[layer_id][n]:
+                    if 0 <= cid < k:
+                        bits[cid] |= numpy.uint32(1 << j)
+            self._bits_cache[key] = (names, torch.from_numpy(bits.view(numpy.int32)).to(device))
+        return self._bits_cache[key]
+
+    def _label_layer(self, layer_id, act, class_label_map, image_size):
+        cat = self.catalog[layer_id]
+        names, bits = self._class_bits(layer_id, class_label_map, act.device)
+        hist = self.cluster_pixel_counts.get(layer_id)
+        if hist is None or hist.device != act.device:
+            hist = torch.zeros(cat.k, dtype=torch.int64, device=act.device)
+            self.cluster_pixel_counts[layer_id] = hist
+        _, out = label_assign(act, cat.centroids_on(act.device), class_bits=bits, n_class=len(names),
+                              image_size=image_size, hist=hist)
+        masks = out['masks'].view(torch.bool)
+        return {n: masks[j] for j, n in enumerate(names)}
+
+    def predict_clusters(self, activations: Dict[int, torch.Tensor], class_label_map) -> PredictedClusters:
+        """Per layer: cluster ids -> per-class bool masks at the layer's native resolution (…segmenter.py:119-138)."""
+        acts = {str(k): v for k, v in activations.items()}
+        return {layer_id: self._label_layer(layer_id, acts[layer_id], class_label_map, acts[layer_id].shape[-1])
+                for layer_id in self.catalog}
+
+    def prepare_image_segmentation(self, activations, class_label_map=None) -> PredictedClusters:
+        """predict_clusters + resize_to_image_size fused: one launch per layer writes the S x S masks directly."""
+        class_label_map = class_label_map if class_label_map is not None else self.class_label_map
+        acts = {str(k): v for k, v in activations.items()}
+        out = {}
+        for layer_id in self.catalog:
+            a = acts[layer_id]
+            size = self.image_size if a.shape[-1] < self.image_size else a.shape[-1]
+            out[layer_id] = self._label_layer(layer_id, a, class_label_map, size)
+        return out
+
+    def merge_sub_images(self, predicted_clusters: PredictedClusters) -> PredictedClusters:
+        """OR the class masks of several layers into a destination key (black_white…segmenter.py:31-40)."""
+        lib = _lib.load()
+        for dst_key, keys in self.keys_to_merge.items():
+            subs = [predicted_clusters[k] for k in keys]
+            merged = {}
+            for class_name in self.class_to_color_map:
+                acc = subs[0][class_name].contiguous().clone()
+                for s in subs[1:]:
+                    src = s[class_name].contiguous()
+                    with torch.cuda.device(acc.device):
+                        _lib.check(lib.sis_or_u8(_lib.ptr(acc), _lib.ptr(src), acc.numel(), _lib.current_stream_ptr(acc.device)))
+                merged[class_name] = acc
+            predicted_clusters[dst_key] = merged
+        return predicted_clusters
+
+
+def make_image(images: torch.Tensor) -> torch.Tensor:
+    """`pytorch_training.images.make_image` on the device: [B,3,S,S] fp32 -> uint8 [B,S,S,3]
+    (clamp(-1,1), (x+1)/2*255, truncation).  The caller moves it to the host (`.cpu().numpy()`) when needed."""
+    _lib.require_cuda(images, 'images')
+    squeeze = images.dim() == 3
+    x = (images[None] if squeeze else images).contiguous().float()
+    out = torch.empty(x.shape[0], x.shape[2], x.shape[3], 3, dtype=torch.uint8, device=x.device)
+    if x.shape[2] != x.shape[3] or x.shape[1] != 3:
+        raise RuntimeError('make_image expects [B, 3, S, S]')
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().sis_make_image_u8(_lib.ptr(x), x.shape[0], x.shape[2], _lib.ptr(out),
+                                                 _lib.current_stream_ptr(x.device)))
+    return out[0] if squeeze else out
