@@ -40,6 +40,13 @@ SIS_API int sis_version(void);
 /* Number of kernel launches issued by this library on the calling process since load (all threads). */
 SIS_API uint64_t sis_launch_count(void);
 
+/* Optional timing of the library's own launches with CUDA events recorded on the launching stream, by kernel
+ * category (0 mapping/modulation, 1 tcgen05 conv GEMM, 2 blur+act+split, 3 ToRGB, 4 fp32 conv, 5 labelling,
+ * 6 fp32 blur+act, 7 other).  Used by bench.py for the roofline figures; off by default (no events recorded).
+ * sis_profile_collect synchronises on the recorded events, sums per category and clears the log. */
+SIS_API int sis_profile_enable(int on);
+SIS_API int sis_profile_collect(double* ms_by_category, uint64_t* count_by_category, int n_categories);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Op 1 — replaces pybind `fused.fused_bias_act(input, bias, refer, act, grad, alpha, scale)`
  *   scf/networks/stylegan2/op/fused_bias_act.cpp:11-20 -> fused_bias_act_kernel.cu:18-98.

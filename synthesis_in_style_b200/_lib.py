@@ -39,6 +39,8 @@ _SIGNATURES = {
     'sis_last_error': (c_char_p, []),
     'sis_version': (c_int, []),
     'sis_launch_count': (c_uint64, []),
+    'sis_profile_enable': (c_int, [c_int]),
+    'sis_profile_collect': (c_int, [POINTER(ctypes.c_double), POINTER(c_uint64), c_int]),
     'sis_fused_bias_act': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int, c_int,
                                    c_float, c_float, c_void_p]),
     'sis_upfirdn2d_out_size': (c_int, [c_int] * 6),
@@ -87,6 +89,22 @@ def check(status: int):
     if status != 0:
         msg = load().sis_last_error()
         raise RuntimeError(f'libsis_b200: {msg.decode() if msg else "unknown error"} (status {status})')
+
+
+PROFILE_CATEGORIES = ('mapping', 'conv_tc', 'blur_split', 'torgb', 'conv_simt', 'label', 'blur_simt', 'other')
+
+
+def profile_enable(on: bool):
+    check(load().sis_profile_enable(int(on)))
+
+
+def profile_collect():
+    """{category: (total ms, launches)} since the last collect."""
+    n = len(PROFILE_CATEGORIES)
+    ms = (ctypes.c_double * n)()
+    cnt = (c_uint64 * n)()
+    check(load().sis_profile_collect(ms, cnt, n))
+    return {PROFILE_CATEGORIES[i]: (float(ms[i]), int(cnt[i])) for i in range(n)}
 
 
 def launch_count() -> int:

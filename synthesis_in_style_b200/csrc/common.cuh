@@ -50,6 +50,18 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n
 
 constexpr int kNumSMs = 148;
 
+// Optional per-kernel-category timing with CUDA events on the launching stream (bench.py's roofline leg).
+enum ProfCat { PROF_MAPPING = 0, PROF_CONV_TC = 1, PROF_BLUR_SPLIT = 2, PROF_TORGB = 3, PROF_CONV_SIMT = 4,
+               PROF_LABEL = 5, PROF_BLUR_SIMT = 6, PROF_OTHER = 7, PROF_NUM = 8 };
+extern bool g_prof_on;
+void prof_begin(int cat, cudaStream_t stream);
+void prof_end(int cat, cudaStream_t stream);
+struct ProfScope {
+    int cat; cudaStream_t stream; bool on;
+    ProfScope(int c, cudaStream_t s) : cat(c), stream(s), on(g_prof_on) { if (on) prof_begin(cat, stream); }
+    ~ProfScope() { if (on) prof_end(cat, stream); }
+};
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 

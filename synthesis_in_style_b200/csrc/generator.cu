@@ -329,6 +329,8 @@ extern "C" int sis_generator_forward(sis_generator* g, const sis_forward_args* a
     const bool tc = a->precision == SIS_PRECISION_BF16X3;
 
     // 1. styles -> w
+    ProfScope* prof_map = new ProfScope(PROF_MAPPING, stream);
+    struct ProfGuard { ProfScope** p; ~ProfGuard() { if (*p) { delete *p; *p = nullptr; } } } prof_guard{&prof_map};
     const float* w[2] = {a->d_styles[0], a->n_styles == 2 ? a->d_styles[1] : nullptr};
     LinearJob* d_jobs = g->jobs_dev.as<LinearJob>();
     if (!a->input_is_latent) {
@@ -349,6 +351,8 @@ extern "C" int sis_generator_forward(sis_generator* g, const sis_forward_args* a
                                    cudaMemcpyHostToDevice, stream));
     SIS_PROPAGATE(launch_linear_jobs(d_jobs + n_mlp_jobs, g->n_mod_jobs, B, g->max_mod_n, stream));
     SIS_PROPAGATE(launch_linear_jobs(d_jobs + n_mlp_jobs + g->n_mod_jobs, g->n_demod_jobs, B, g->max_demod_n, stream));
+
+    delete prof_map; prof_map = nullptr;
 
     // 4. layers
     auto act_dst = [&](int idx, int pp) -> float* {
@@ -383,15 +387,20 @@ extern "C" int sis_generator_forward(sis_generator* g, const sis_forward_args* a
             m.H = c.res_in; m.W = c.res_in; m.noise = noise; m.noise_bstride = nstride; m.noise_w = c.noise_w; m.bias = c.act_bias.as<float>();
             if (!c.up) {
                 m.out = y; m.OH = c.res_out; m.OW = c.res_out; m.pad = 1; m.zero_insert = 0; m.fuse_act = 1;
+                ProfScope prof(PROF_CONV_SIMT, stream);
                 SIS_PROPAGATE(launch_modconv3x3_simt(m, B, stream));
             } else {
                 const int th = c.res_out + 1;
                 m.out = g->upconv_tmp.as<float>(); m.OH = th; m.OW = th; m.pad = 2; m.zero_insert = 1; m.fuse_act = 0;
-                SIS_PROPAGATE(launch_modconv3x3_simt(m, B, stream));
+                {
+                    ProfScope prof(PROF_CONV_SIMT, stream);
+                    SIS_PROPAGATE(launch_modconv3x3_simt(m, B, stream));
+                }
                 BlurActArgs bl;
                 bl.in = g->upconv_tmp.as<float>(); bl.out = y; bl.planes = (int64_t)B * c.cout; bl.C = c.cout; bl.IH = th; bl.IW = th;
                 bl.OH = c.res_out; bl.OW = c.res_out; bl.blur_k = c.blur_k.as<float>(); bl.noise = noise; bl.noise_bstride = nstride;
                 bl.noise_w = c.noise_w; bl.bias = c.act_bias.as<float>();
+                ProfScope prof(PROF_BLUR_SIMT, stream);
                 SIS_PROPAGATE(launch_blur_noise_act(bl, stream));
             }
         }
@@ -403,6 +412,7 @@ extern "C" int sis_generator_forward(sis_generator* g, const sis_forward_args* a
             ToRgbArgs t;
             t.x = x; t.s = r.s; t.w = r.w_scaled.as<float>(); t.bias = r.bias.as<float>(); t.skip = skip; t.up_k = r.up ? r.up_k.as<float>() : nullptr;
             t.out = out; t.batch = B; t.C = r.cin; t.H = r.res; t.W = r.res;
+            ProfScope prof(PROF_TORGB, stream);
             SIS_PROPAGATE(launch_torgb(t, stream));
             skip = out;
             ++rgb_i;

@@ -308,6 +308,7 @@ extern "C" int sis_label_assign(const float* d_act, int batch, int channels, int
     SIS_REQUIRE((size_t)channels * 64 * 4 <= 200 * 1024 || k <= 32, "label_assign: centroid table does not fit shared memory");
     if ((int64_t)batch * h * w == 0) return SIS_OK;
     SIS_REQUIRE(d_act && d_centroids, "label_assign: activations / centroids must be CUDA tensors (null pointer)");
+    ProfScope prof(PROF_LABEL, stream);
     LabelArgs a;
     a.act = d_act; a.batch = batch; a.C = channels; a.H = h; a.W = w; a.centroids = d_centroids; a.k = k;
     a.class_bits = d_cluster_class_bits; a.n_class = n_class; a.S = image_size;

@@ -653,10 +653,13 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
         SIS_PROPAGATE(make_map(&maps[3], w.lo, 3, wdims, wbox));
     }
     int st;
-    if (BN == 256) st = launch_tc_bn<256>(th, tw, tb, maps, a, stream);
-    else if (BN == 128) st = launch_tc_bn<128>(th, tw, tb, maps, a, stream);
-    else if (BN == 64) st = launch_tc_bn<64>(th, tw, tb, maps, a, stream);
-    else st = launch_tc_bn<32>(th, tw, tb, maps, a, stream);
+    {
+        ProfScope prof(PROF_CONV_TC, stream);
+        if (BN == 256) st = launch_tc_bn<256>(th, tw, tb, maps, a, stream);
+        else if (BN == 128) st = launch_tc_bn<128>(th, tw, tb, maps, a, stream);
+        else if (BN == 64) st = launch_tc_bn<64>(th, tw, tb, maps, a, stream);
+        else st = launch_tc_bn<32>(th, tw, tb, maps, a, stream);
+    }
     SIS_PROPAGATE(st);
 
     if (call.up) {
@@ -667,6 +670,7 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
         bs.s_next = call.s_next; bs.next_hi = (bf16*)ws.a_hi[call.out_slot]; bs.next_lo = (bf16*)ws.a_lo[call.out_slot];
         const int64_t total = (int64_t)B * ceil_div(bs.OH, BS_TH) * ceil_div(bs.OW, BS_TW) * (bs.C / BS_C);
         const int grid = (int)std::min<int64_t>(total, (int64_t)kNumSMs * 4);
+        ProfScope prof(PROF_BLUR_SPLIT, stream);
         blur_act_split_kernel<<<grid, 256, 0, stream>>>(bs);
         SIS_CHECK_LAUNCH();
     }
