@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py — labelled image pairs/sec at 256^2 (BASELINE.json metric), one JSON line on rank 0.
+
+A step = one pass of the hot path over one batch of synthetic input: StyleGAN2-256 generator forward (random-init
+weights, noise/bias parameters perturbed so every path is live) with all 14 activation captures, followed by the
+nearest-centroid labelling of layers 8, 9, 12, 13 (k=4, 3 classes) into 256x256 class masks
+(BASELINE.json configs[1]: batch 32 on one B200).  N ranks = N independent batch shards (weak scaling); the only
+collective is the final all-reduce of the statistics vector.
+
+  value      pairs/s with the step's inputs (latents, noise) already resident in HBM
+  e2e        same metric through the public API with HOST buffers: pinned-host latents copied in every step, noise
+             drawn on the device as the reference does, image + masks copied back to pinned host memory every step
+  roofline   dominant kernel (tcgen05 modulated-conv GEMM): algorithmic conv FLOPs / its CUDA-event time
+  cpu_baseline  the oracle (CPU restatement of the reference) on this box's host cores, bounded sample
+  --impl reference   the oracle alone, all host threads (the reference has no CPU path of its own)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SIZE, STYLE_DIM, N_MLP, BATCH = 256, 512, 8, 32
+LABEL_LAYERS = {'8': 4, '9': 4, '12': 4, '13': 4}
+CLASS_MAP = {'0': 'background', '1': 'printed_text', '2': 'handwritten_text', '3': 'background'}
+COLORS = {'background': '#000000', 'printed_text': '#0000FF', 'handwritten_text': '#FF0000'}
+METRIC = 'labelled image pairs/sec at 256^2'
+UNIT = 'pairs/s'
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {'hbm_gbs': d['hbm_gbs'], 'bf16_burst': d['bf16_tflops'], 'bf16_sustained': d['bf16_tflops_sustained'], 'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'bf16_burst': 1590.0, 'bf16_sustained': 1400.0, 'source': 'fallback'}
+
+
+def synthetic_catalog(seed=5):
+    """unit-norm centroids, torch.manual_seed(5); F.normalize(randn(k, C))."""
+    from oracle import stylegan2_oracle as so
+    ch = so.get_channels(2)
+    g = torch.Generator().manual_seed(seed)
+    cat = {}
+    for layer, k in LABEL_LAYERS.items():
+        res = 4 if int(layer) <= 1 else 2 ** ((int(layer) - 2) // 2 + 3)
+        cat[layer] = torch.nn.functional.normalize(torch.randn(k, ch[res], generator=g), dim=1)
+    return cat
+
+
+def oracle_state():
+    from oracle import stylegan2_oracle as so
+    spec = so.GeneratorSpec(SIZE, STYLE_DIM, N_MLP, 2)
+    sd = so.perturb_zero_params(so.init_state_dict(spec, seed=0), seed=1234)
+    return spec, sd
+
+
+def oracle_step(spec, sd, catalog, inv_map, batch):
+    """One CPU pass of the reference's path (generator + labelling) on `batch` samples."""
+    from oracle import labelling_oracle as lo
+    from oracle import stylegan2_oracle as so
+    z = torch.randn(batch, STYLE_DIM)
+    noise = so.make_noise(spec)
+    img, acts = so.generator_forward(sd, spec, [z], noise=noise, return_intermediate_activations=True)
+    masks = lo.prepare_image_segmentation(acts, catalog, inv_map, SIZE)
+    return img, masks
+
+
+def time_oracle(steps, warmup, batch):
+    from oracle import labelling_oracle as lo
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec, sd = oracle_state()
+    catalog = synthetic_catalog()
+    inv = lo.invert_class_label_map({layer: CLASS_MAP for layer in LABEL_LAYERS})
+    torch.manual_seed(1)
+    for _ in range(warmup):
+        oracle_step(spec, sd, catalog, inv, batch)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle_step(spec, sd, catalog, inv, batch)
+    dt = time.perf_counter() - t0
+    return steps * batch / dt, dt / steps * 1e3
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
+        'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index):
+        self.gpu_index, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        rows = [l for (t, l) in self.lines if t_begin <= t <= t_end] or [l for (_, l) in self.lines]
+        for l in rows:
+            f = [x.strip() for x in l.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': smax, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def make_config(world, B):
+    return {'workload': 'StyleGAN2 256x256 random-init generator, batch 32 per GPU, 14 activation captures, '
+                        'nearest-centroid labelling of layers 8,9,12,13 (k=4) to 256x256 class masks (BASELINE configs[1])',
+            'batch_per_gpu': B, 'global_batch': B * world, 'image_size': SIZE, 'k': 4, 'label_layers': list(LABEL_LAYERS),
+            'parallelism': f'batch-index sharding over {world} GPU(s), no data-path collective',
+            'l2': 'per-step working set (>= 3.9 GB of captured activations) exceeds the 126 MB L2; no explicit flush'}
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the oracle port on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    batch = 1
+    value, ms = time_oracle(args.steps, max(1, min(args.warmup, 2)), batch)
+    cores = torch.get_num_threads()
+    sample = f'each step = {batch} image(s) (not the 32 of the GPU arm) of the 256^2 config (generator + labelling of layers 8,9,12,13), fp32, {cores} threads'
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': make_config(max(1, world), BATCH),
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--precision', default='bf16x3', choices=['bf16x3', 'fp32'])
+    ap.add_argument('--batch', type=int, default=BATCH)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-steps', type=int, default=3)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from synthesis_in_style_b200 import _lib, dataset_creation as dc, labelling
+    from synthesis_in_style_b200.model import Generator
+    from oracle import stylegan2_oracle as so   # bench's cpu_baseline leg + shared synthetic-weight recipe
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    B = args.batch
+    spec, sd = oracle_state()
+    g = Generator(SIZE, STYLE_DIM, N_MLP, precision=args.precision)
+    g.load_state_dict(sd)
+    g = g.to(dev).eval()
+    catalog = {k: labelling.FactorCatalog(v.shape[0], v) for k, v in synthetic_catalog().items()}
+    seg = labelling.ClusterSegmenter(None, SIZE, COLORS, keys_for_class_determination=['8', '9'],
+                                     keys_for_finegrained_segmentation=['12', '13'], num_clusters=4, keys_to_merge={},
+                                     catalog=catalog, class_label_map={layer: CLASS_MAP for layer in LABEL_LAYERS})
+    cfg = {'batch_size': B, 'latent_size': STYLE_DIM}
+    total_steps = args.warmup + args.steps
+    # this rank's shard of the reference's single (latent, noise) stream: batch index = rank + i*world
+    stream = dc.sharded_latent_stream(g, cfg, seed=1, rank=rank, world_size=world)
+    batches = [next(stream)[1].to(dev) for _ in range(total_steps)]
+
+    def step_resident(lat):
+        with torch.no_grad():
+            img, acts = g([lat.latent], noise=lat.noise, return_intermediate_activations=True)
+        masks = seg.prepare_image_segmentation(acts)
+        return img, masks
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------------------------------------------------------- value: inputs resident in HBM
+    for i in range(args.warmup):
+        step_resident(batches[i])
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    launches0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_begin = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        step_resident(batches[args.warmup + i])
+    stats = dc.reduce_stats(torch.cat([seg.cluster_pixel_counts[k] for k in sorted(seg.cluster_pixel_counts)]).clone())
+    e1.record()
+    barrier()
+    t_end = time.perf_counter()
+    launches = _lib.launch_count() - launches0
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    clocks = sampler.stop(t_begin, t_end) if rank == 0 else None
+    value = world * args.steps * B / (ms_total / 1e3)
+
+    # ---------------------------------------------------------------- e2e: host buffers in and out
+    h_z = torch.empty(B, STYLE_DIM).pin_memory()
+    h_img = torch.empty(B, 3, SIZE, SIZE).pin_memory()
+    n_cls = len(COLORS)
+    h_masks = {k: torch.empty(n_cls, B, SIZE, SIZE, dtype=torch.uint8).pin_memory() for k in LABEL_LAYERS}
+    h2d = h_z.numel() * 4
+    d2h = h_img.numel() * 4 + sum(m.numel() for m in h_masks.values())
+    host_rng = torch.Generator().manual_seed(1 + rank)
+
+    def step_e2e():
+        h_z.copy_(torch.randn(B, STYLE_DIM, generator=host_rng))
+        lat = dc.Latents(h_z.to(dev, non_blocking=True), g.make_noise())
+        acts, img = dc.generate_images(lat, g, device=dev)
+        masks = seg.prepare_image_segmentation(acts)
+        h_img.copy_(img, non_blocking=True)
+        for k in LABEL_LAYERS:
+            stacked = torch.stack([masks[k][c] for c in COLORS]).view(torch.uint8)
+            h_masks[k].copy_(stacked, non_blocking=True)
+
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_e2e()
+    e1.record()
+    barrier()
+    ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps * B / (float(ms2.item()) / 1e3)
+
+    # ---------------------------------------------------------------- roofline: per-kernel CUDA-event times
+    roofline, kernels = None, None
+    if rank == 0:
+        peaks = load_peaks()
+        _lib.profile_enable(True)
+        torch.cuda.synchronize()
+        for i in range(args.profile_steps):
+            step_resident(batches[args.warmup + (i % args.steps)])
+        torch.cuda.synchronize()
+        prof = _lib.profile_collect()
+        _lib.profile_enable(False)
+        n = args.profile_steps
+        flops_img = so.conv_flops_per_image(spec)
+        rgb_flops = 2.0 * sum((2 ** i) ** 2 * spec.channels[2 ** i] * 3 for i in range(2, spec.log_size + 1))
+        conv_flops_step = (flops_img - rgb_flops) * B
+        kernels = {k: {'ms_per_step': v[0] / n, 'launches_per_step': v[1] / n} for k, v in prof.items() if v[1]}
+        conv_key = 'conv_tc' if args.precision == 'bf16x3' else 'conv_simt'
+        conv_ms = kernels[conv_key]['ms_per_step']
+        achieved = conv_flops_step / (conv_ms / 1e3) / 1e12
+        peak = peaks['bf16_sustained']
+        traffic = None
+        tp = os.path.join(ROOT, 'profiles', 'traffic.json')
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(conv_key)
+        roofline = {'bound': 'tensor', 'kernel': 'modconv_tc_kernel' if conv_key == 'conv_tc' else 'modconv3x3_simt_kernel',
+                    'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
+                    'peak_source': f'{peaks["source"]} bf16 sustained (kernel timed inside a long step)',
+                    'passes': 3 if conv_key == 'conv_tc' else 1,
+                    'note': 'algorithmic FLOPs (2*MACs, SURVEY 8d) of all 13 StyledConv launches per step / their summed '
+                            'CUDA-event time; the bf16x3 split issues 3 MMA passes per algorithmic FLOP, so tensor-pipe '
+                            'work is 3x achieved',
+                    'share_of_step': conv_ms / sum(v['ms_per_step'] for v in kernels.values())}
+        # HBM-side view of the memory-bound kernels (bytes model in DESIGN.md)
+        hbm = {}
+        act_bytes = sum(B * spec.channels[4 if i <= 1 else 2 ** ((i - 2) // 2 + 3)] * (4 if i <= 1 else 2 ** ((i - 2) // 2 + 3)) ** 2 * 4
+                        for i in range(spec.n_latent))
+        if 'label' in kernels:
+            lbl_bytes = sum(B * spec.channels[r] * r * r * 4 + B * r * r + n_cls * B * SIZE * SIZE for r in (64, 64, 256, 256))
+            hbm['label'] = {'GB/s': lbl_bytes / (kernels['label']['ms_per_step'] / 1e3) / 1e9}
+        if 'torgb' in kernels:
+            rgb_bytes = sum(B * spec.channels[r] * r * r * 4 + B * 3 * r * r * 4 + B * 3 * (r // 2) ** 2 * 4 for r in (4, 8, 16, 32, 64, 128, 256))
+            hbm['torgb'] = {'GB/s': rgb_bytes / (kernels['torgb']['ms_per_step'] / 1e3) / 1e9}
+        if 'blur_split' in kernels:
+            bl_bytes = sum(B * spec.channels[r] * ((r + 1) ** 2 * 4 + r * r * 8) for r in (8, 16, 32, 64, 128, 256))
+            hbm['blur_split'] = {'GB/s': bl_bytes / (kernels['blur_split']['ms_per_step'] / 1e3) / 1e9}
+        for v in hbm.values():
+            v['frac_of_hbm_peak'] = v['GB/s'] / peaks['hbm_gbs']
+        roofline['memory_bound_kernels'] = hbm
+        roofline['captured_activation_bytes_per_step'] = act_bytes
+
+    # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, ms_cpu = time_oracle(3, 1, 1)
+        cpu = {'value': v, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+               'sample': '3 timed + 1 warm-up steps of 1 image (256^2 generator + labelling of layers 8,9,12,13), oracle fp32'}
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'bf16x3 (3-term bf16 split, fp32 accumulate)' if args.precision == 'bf16x3' else 'f32', 'data': 'synthetic',
+                'config': make_config(world, B),
+                'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                        'ms_per_step': float(ms2.item()) / args.steps},
+                'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'kernels': kernels, 'cpu_baseline': cpu,
+                'stats_allreduce_sum': int(stats.sum().item())}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,93 @@
+#!/usr/bin/env python
+"""Summarise ncu outputs (read here, no GPU) into small tracked files under profiles/.
+  launches CSV (gpu__time_duration.sum per launch)  -> per-kernel totals / shares of the profiled command
+  .ncu-rep full captures                             -> one row per launch with the metrics the roofline uses
+Usage: scripts/summarize_ncu.py <tag>   (reads gpurun_out/*_<tag>.*, writes profiles/<tag>_*.md)
+"""
+import csv
+import io
+import os
+import re
+import subprocess
+import sys
+from collections import OrderedDict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1] if len(sys.argv) > 1 else 'r01'
+G = os.path.join(ROOT, 'gpurun_out')
+P = os.path.join(ROOT, 'profiles')
+os.makedirs(P, exist_ok=True)
+
+
+def short(name):
+    name = re.sub(r'^void ', '', name)
+    name = re.sub(r'\(.*$', '', name)
+    return name.replace('sis::', '')[:90]
+
+
+def launches():
+    path = os.path.join(G, f'launches_{tag}.csv')
+    if not os.path.exists(path):
+        return
+    lines = [l for l in open(path) if not l.startswith('==')]
+    rows = list(csv.DictReader(io.StringIO(''.join(lines))))
+    per = OrderedDict()
+    total = 0.0
+    for r in rows:
+        if r.get('Metric Name') != 'gpu__time_duration.sum':
+            continue
+        v = float(r['Metric Value'].replace(',', ''))
+        unit = r.get('Metric Unit', 'ns')
+        v_us = v / 1e3 if unit in ('ns', 'nsecond') else (v if unit in ('us', 'usecond') else v * 1e3)
+        k = short(r['Kernel Name'])
+        d = per.setdefault(k, [0, 0.0])
+        d[0] += 1; d[1] += v_us
+        total += v_us
+    out = [f'# ncu launch list `{tag}` — `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --profile-steps 1`',
+           '', '`ncu --metrics gpu__time_duration.sum --clock-control none` (cold-cache, serialised: compare SHARES, not absolutes).',
+           f'{sum(d[0] for d in per.values())} launches, {total / 1e3:.2f} ms total.', '',
+           '| kernel | launches | total us | share |', '|---|---:|---:|---:|']
+    for k, (n, us) in sorted(per.items(), key=lambda kv: -kv[1][1]):
+        out.append(f'| `{k}` | {n} | {us:.1f} | {100 * us / total:.1f} % |')
+    open(os.path.join(P, f'{tag}_launches.md'), 'w').write('\n'.join(out) + '\n')
+    print('\n'.join(out[:30]))
+
+
+METRICS = OrderedDict([
+    ('gpu__time_duration.sum', 'time'),
+    ('dram__bytes_read.sum', 'dram_rd'),
+    ('dram__bytes_write.sum', 'dram_wr'),
+    ('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'dram_%'),
+    ('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active', 'tensor_%'),
+    ('lts__throughput.avg.pct_of_peak_sustained_elapsed', 'l2_%'),
+    ('l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'l1_%'),
+    ('sm__warps_active.avg.pct_of_peak_sustained_active', 'warps_%'),
+    ('launch__registers_per_thread', 'regs'),
+    ('launch__grid_size', 'grid'),
+])
+
+
+def reps():
+    for f in sorted(os.listdir(G)):
+        if not (f.endswith(f'_{tag}.ncu-rep')):
+            continue
+        res = subprocess.run(['ncu', '-i', os.path.join(G, f), '--page', 'raw', '--csv'], capture_output=True, text=True)
+        rows = list(csv.reader(io.StringIO(res.stdout)))
+        if len(rows) < 3:
+            continue
+        hdr, units = rows[0], rows[1]
+        col = {h: i for i, h in enumerate(hdr)}
+        out = [f'# ncu --set full capture `{f}`', '', '`--clock-control none --import-source on`; one row per launch; '
+               'units as reported by ncu (' + ', '.join(f'{v}: {units[col[k]]}' for k, v in METRICS.items() if k in col and units[col[k]]) + ').', '',
+               '| kernel | ' + ' | '.join(METRICS.values()) + ' |', '|---|' + '---:|' * len(METRICS)]
+        for r in rows[2:]:
+            vals = [r[col[k]] if k in col else '-' for k in METRICS]
+            vals = [f'{float(v):.3f}' if re.match(r'^-?\d+\.\d+$', v) else v for v in vals]
+            out.append(f'| `{short(r[col["Kernel Name"]])}` | ' + ' | '.join(vals) + ' |')
+        name = f.replace('.ncu-rep', '.md')
+        open(os.path.join(P, name), 'w').write('\n'.join(out) + '\n')
+        print('\n'.join(out))
+
+
+launches()
+reps()

@@ -1,0 +1,110 @@
+"""GPU parity of the whole labelled-pair path (generate -> label) against the oracle pipeline on the same seeds, the
+equivalence of the sharded run with the single-stream run, and size-independent properties at the full bench size."""
+import pytest
+import torch
+
+from oracle import labelling_oracle as lo
+from oracle import stylegan2_oracle as so
+from synthesis_in_style_b200 import dataset_creation as dc
+from synthesis_in_style_b200 import labelling
+from synthesis_in_style_b200.model import Generator
+
+pytestmark = pytest.mark.gpu
+NAMES = {'background': '#000000', 'printed_text': '#0000FF', 'handwritten_text': '#FF0000'}
+CLASS_MAP = {'0': 'background', '1': 'printed_text', '2': 'handwritten_text', '3': 'background'}
+
+
+def make_setup(size, layers, device, precision='bf16x3', seed_centroids=5):
+    spec = so.GeneratorSpec(size, 512, 8, 2)
+    sd = so.perturb_zero_params(so.init_state_dict(spec, seed=0), seed=1234)
+    g = Generator(size, 512, 8, precision=precision)
+    g.load_state_dict(sd)
+    g = g.to(device).eval()
+    gen = torch.Generator().manual_seed(seed_centroids)
+    cents = {}
+    for layer in layers:
+        c, _ = g.activation_shape(int(layer))
+        cents[layer] = torch.nn.functional.normalize(torch.randn(4, c, generator=gen), dim=1)
+    seg = labelling.ClusterSegmenter(None, size, NAMES, keys_for_class_determination=layers[:2], keys_for_finegrained_segmentation=layers[2:],
+                                     num_clusters=4, keys_to_merge={}, catalog={k: labelling.FactorCatalog(4, v) for k, v in cents.items()},
+                                     class_label_map={k: CLASS_MAP for k in layers})
+    return spec, sd, g, seg, cents
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16x3'])
+def test_pipeline_matches_oracle_on_same_seeds(cuda_device, precision):
+    """Config 2 shape at reduced batch: 256^2, layers 8,9,12,13, k=4; labels bit-exact where margin > 1e-3, >= 99.9 % overall."""
+    layers = ['8', '9', '12', '13']
+    spec, sd, g, seg, cents = make_setup(256, layers, cuda_device, precision)
+    cfg = {'batch_size': 2, 'latent_size': 512}
+    pipe = dc.LabelledPairGenerator(g, seg, cfg, seed=1)
+    got = next(iter(pipe))
+    # oracle on the same stream.  The device noise stream (Philox) is replayed by drawing it again on the device.
+    it = iter(dc.build_latent_and_noise_generator(g, cfg, seed=1))
+    lat = next(it)
+    z, noise = lat.latent.cpu(), [n.cpu() for n in lat.noise]
+    want_img, want_acts = so.generator_forward(sd, spec, [z], noise=noise, return_intermediate_activations=True)
+    inv = lo.invert_class_label_map({k: CLASS_MAP for k in layers})
+    want_masks = lo.prepare_image_segmentation(want_acts, cents, inv, 256)
+    assert float((got.image.cpu() - want_img).abs().max()) <= 2e-2
+    total = agree = 0
+    for layer in layers:
+        ids_want, margin = lo.predict_with_margin(want_acts[int(layer)], cents[layer])
+        ids_got = seg.catalog[layer].predict(got.activations[int(layer)]).cpu()
+        safe = margin > 1e-3
+        assert torch.equal(ids_got[safe], ids_want[safe]), (layer, int((ids_got[safe] != ids_want[safe]).sum()))
+        total += ids_want.numel(); agree += int((ids_got == ids_want).sum())
+        for cn in NAMES:
+            m = got.masks[layer][cn]
+            assert m.shape == (2, 256, 256) and m.dtype == torch.bool
+            assert float((m.cpu() == want_masks[layer][cn]).float().mean()) >= 0.999
+    assert agree / total >= 0.999
+
+
+def test_sharded_run_equals_single_stream(cuda_device):
+    layers = ['4', '5', '6', '7']
+    spec, sd, g, seg, cents = make_setup(32, layers, cuda_device)
+    cfg = {'batch_size': 3, 'latent_size': 512}
+    single = []
+    for i, b in zip(range(4), dc.LabelledPairGenerator(g, seg, cfg, seed=1)):
+        single.append(b)
+    for rank in range(2):
+        pipe = dc.LabelledPairGenerator(g, seg, cfg, seed=1, rank=rank, world_size=2, capture_only_labelled=True)
+        for i, b in zip(range(2), pipe):
+            ref = single[b.batch_index]
+            assert b.batch_index % 2 == rank
+            assert torch.equal(b.image, ref.image)
+            assert sorted(b.activations) == [0, 4, 5, 6, 7]
+            for layer in layers:
+                for cn in NAMES:
+                    assert torch.equal(b.masks[layer][cn], ref.masks[layer][cn])
+        vec = pipe.stats_vector()
+        assert int(vec[-2]) == 6 and int(vec[-1]) == 2
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE config 2 at full size (256^2, batch 32): properties that do not need the oracle."""
+    layers = ['8', '9', '12', '13']
+    spec, sd, g, seg, cents = make_setup(256, layers, cuda_device)
+    cfg = {'batch_size': 32, 'latent_size': 512}
+    a = next(iter(dc.LabelledPairGenerator(g, seg, cfg, seed=1)))
+    b = next(iter(dc.LabelledPairGenerator(g, seg, cfg, seed=1)))
+    assert torch.equal(a.image, b.image)                       # deterministic
+    assert torch.isfinite(a.image).all()
+    for layer in layers:
+        stack = torch.stack([a.masks[layer][cn] for cn in NAMES]).to(torch.int32)
+        assert int(stack.sum(0).min()) == 1 and int(stack.sum(0).max()) == 1     # classes partition every pixel
+        ids = seg.catalog[layer].predict(a.activations[int(layer)])
+        h = a.activations[int(layer)].shape[-1]
+        # nearest resize: every (256/h)^2 block is constant and equals the native-resolution class
+        native = (ids == 1)
+        up = native.repeat_interleave(256 // h, 1).repeat_interleave(256 // h, 2)
+        assert torch.equal(up, a.masks[layer]['printed_text'])
+    # batch independence: sample i of a batch-32 run equals the same latent run alone (noise is shared per batch)
+    it = iter(dc.build_latent_and_noise_generator(g, cfg, seed=1))
+    lat = next(it).to(cuda_device)
+    with torch.no_grad():
+        img1, _ = g([lat.latent[5:6]], noise=lat.noise)
+    torch.testing.assert_close(img1[0], a.image[5], rtol=0, atol=1e-4)
+    counts = seg.cluster_pixel_counts
+    assert all(int(counts[l].sum()) % (32 * a.activations[int(l)].shape[-1] ** 2) == 0 for l in layers)
