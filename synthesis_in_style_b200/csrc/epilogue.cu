@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(32 * RGB_SLICES) torgb_kernel(ToRgbArgs a) {
         if (valid) {
             const float* xb = a.x + ((int64_t)b * a.C) * hw + pix;
             const float* sb = a.s + (int64_t)b * a.C;
-#pragma unroll 4
+#pragma unroll 8
             for (int c = c_begin; c < c_end; ++c) {
                 const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(xb + (int64_t)c * hw));
                 const float s = __ldg(sb + c);

@@ -31,6 +31,8 @@ struct ConvLayer {
     std::string prefix;
     DevBuf w_scaled, wsq, mod_w, mod_b, act_bias, blur_k;
     float noise_w = 0.0f;
+    float blur_host[16] = {0};
+    bool blur_separable = false;
     TcConvWeights tc;        // bf16 hi/lo packs for the tcgen05 path
     float* s = nullptr;      // [B, cin]  (workspace slices)
     float* d = nullptr;      // [B, cout]
@@ -62,7 +64,7 @@ struct sis_generator {
     DevBuf style_tmp[2], style_jobs;
     int64_t style_rows_cap = 0;
     std::vector<LinearJob> host_jobs;  // [mlp*2 styles][mod jobs][demod jobs]
-    int n_mod_jobs = 0, n_demod_jobs = 0, max_mod_n = 0, max_demod_n = 0;
+    int n_mod_jobs = 0, n_demod_jobs = 0, max_mod_n = 0, max_demod_n = 0, max_demod_k = 0;
     TcWorkspace tc_ws;
 };
 
@@ -193,7 +195,10 @@ extern "C" int sis_generator_prepare(sis_generator* g, void* stream_) {
         SIS_PROPAGATE(copy_param(g, c.prefix + ".conv.modulation.weight", (int64_t)c.cin * sd, c.mod_w, mod_scale, stream));
         SIS_PROPAGATE(copy_param(g, c.prefix + ".conv.modulation.bias", c.cin, c.mod_b, 1.0f, stream));
         SIS_PROPAGATE(copy_param(g, c.prefix + ".activate.bias", c.cout, c.act_bias, 1.0f, stream));
-        if (c.up) SIS_PROPAGATE(copy_param(g, c.prefix + ".conv.blur.kernel", 16, c.blur_k, 1.0f, stream));
+        if (c.up) {
+            SIS_PROPAGATE(copy_param(g, c.prefix + ".conv.blur.kernel", 16, c.blur_k, 1.0f, stream));
+            SIS_CHECK_CUDA(cudaMemcpyAsync(c.blur_host, c.blur_k.p, 16 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        }
         const float* nw;
         SIS_PROPAGATE(get_param(g, c.prefix + ".noise.weight", 1, &nw));
         SIS_CHECK_CUDA(cudaMemcpyAsync(&c.noise_w, nw, sizeof(float), cudaMemcpyDeviceToHost, stream));
@@ -207,7 +212,19 @@ extern "C" int sis_generator_prepare(sis_generator* g, void* stream_) {
         SIS_PROPAGATE(copy_param(g, r.prefix + ".bias", 3, r.bias, 1.0f, stream));
         if (r.up) SIS_PROPAGATE(copy_param(g, r.prefix + ".upsample.kernel", 16, r.up_k, 1.0f, stream));
     }
-    SIS_CHECK_CUDA(cudaStreamSynchronize(stream));  // noise weights are read on the host
+    SIS_CHECK_CUDA(cudaStreamSynchronize(stream));  // noise weights and blur taps are read on the host
+    for (auto& c : g->convs) {
+        if (!c.up) continue;
+        // rank-1 test k[i][j] == k[i][0]*k[0][j]/k[0][0]: the reference's make_kernel([1,3,3,1]) always passes
+        const float* k = c.blur_host;
+        float mx = 0.0f;
+        for (int i = 0; i < 16; ++i) mx = std::max(mx, std::fabs(k[i]));
+        bool sep = k[15] != 0.0f;   // flipped taps: element [0][0] of the flipped kernel is k[3][3]
+        for (int i = 0; i < 4 && sep; ++i)
+            for (int j = 0; j < 4; ++j)
+                if (std::fabs(k[i * 4 + j] - k[i * 4 + 3] * k[12 + j] / k[15]) > 1e-6f * mx) sep = false;
+        c.blur_separable = sep;
+    }
     g->prepared = true;
     g->ws_batch = -1;
     return SIS_OK;
@@ -229,7 +246,7 @@ static int run_style_mlp(sis_generator* g, const float* z, float* w_out, int64_t
     }
     if (g->n_mlp) {
         SIS_CHECK_CUDA(cudaMemcpyAsync(d_jobs, h_jobs, sizeof(LinearJob) * g->n_mlp, cudaMemcpyHostToDevice, stream));
-        for (int i = 0; i < g->n_mlp; ++i) SIS_PROPAGATE(launch_linear_jobs(d_jobs + i, 1, (int)n, sd, stream));
+        for (int i = 0; i < g->n_mlp; ++i) SIS_PROPAGATE(launch_linear_jobs(d_jobs + i, 1, (int)n, sd, sd, sd % 4 == 0, stream));
     }
     return SIS_OK;
 }
@@ -284,7 +301,7 @@ static int ensure_workspace(sis_generator* g, int B) {
     g->n_demod_jobs = (int)g->convs.size();
     g->host_jobs.assign(n_mlp_jobs + g->n_mod_jobs + g->n_demod_jobs, LinearJob());
     SIS_PROPAGATE(g->jobs_dev.reserve(g->host_jobs.size() * sizeof(LinearJob)));
-    g->max_mod_n = 0; g->max_demod_n = 0;
+    g->max_mod_n = 0; g->max_demod_n = 0; g->max_demod_k = 0;
     int ji = n_mlp_jobs;
     const float* lat = g->latent.as<float>();
     const int ldl = g->n_latent * sd;
@@ -302,6 +319,7 @@ static int ensure_workspace(sis_generator* g, int B) {
         j.A = c.s; j.lda = c.cin; j.W = c.wsq.as<float>(); j.bias = nullptr; j.C = c.d; j.ldc = c.cout;
         j.M = B; j.N = c.cout; j.K = c.cin; j.square_a = 1; j.epilogue = LINEAR_EPI_RSQRT_EPS;
         g->max_demod_n = std::max(g->max_demod_n, c.cout);
+        g->max_demod_k = std::max(g->max_demod_k, c.cin);
     }
     g->ws_batch = B;
     return SIS_OK;
@@ -349,8 +367,8 @@ extern "C" int sis_generator_forward(sis_generator* g, const sis_forward_args* a
     const int n_mlp_jobs = 2 * g->n_mlp;
     SIS_CHECK_CUDA(cudaMemcpyAsync(d_jobs + n_mlp_jobs, g->host_jobs.data() + n_mlp_jobs, sizeof(LinearJob) * (g->n_mod_jobs + g->n_demod_jobs),
                                    cudaMemcpyHostToDevice, stream));
-    SIS_PROPAGATE(launch_linear_jobs(d_jobs + n_mlp_jobs, g->n_mod_jobs, B, g->max_mod_n, stream));
-    SIS_PROPAGATE(launch_linear_jobs(d_jobs + n_mlp_jobs + g->n_mod_jobs, g->n_demod_jobs, B, g->max_demod_n, stream));
+    SIS_PROPAGATE(launch_linear_jobs(d_jobs + n_mlp_jobs, g->n_mod_jobs, B, g->max_mod_n, sd, sd % 4 == 0, stream));
+    SIS_PROPAGATE(launch_linear_jobs(d_jobs + n_mlp_jobs + g->n_mod_jobs, g->n_demod_jobs, B, g->max_demod_n, g->max_demod_k, true, stream));
 
     delete prof_map; prof_map = nullptr;
 
@@ -377,7 +395,7 @@ extern "C" int sis_generator_forward(sis_generator* g, const sis_forward_args* a
             TcConvCall call;
             call.batch = B; call.cin = c.cin; call.cout = c.cout; call.res_in = c.res_in; call.res_out = c.res_out; call.up = c.up;
             call.demod = c.d; call.noise = noise; call.noise_bstride = nstride; call.noise_w = c.noise_w; call.bias = c.act_bias.as<float>();
-            call.blur_k = c.up ? c.blur_k.as<float>() : nullptr; call.out_f32 = y; call.s_next = s_next;
+            call.blur_k = c.up ? c.blur_k.as<float>() : nullptr; call.blur_separable = c.blur_separable; call.out_f32 = y; call.s_next = s_next;
             call.in_slot = (int)(L & 1); call.out_slot = (int)((L + 1) & 1);
             call.upconv_tmp = g->upconv_tmp.as<float>();
             SIS_PROPAGATE(tc_modconv(g->tc_ws, c.tc, call, stream));

@@ -44,7 +44,8 @@ struct ToRgbArgs {
 };
 
 int launch_pixel_norm(float* out, const float* z, int64_t rows, int dim, cudaStream_t stream);
-int launch_linear_jobs(const LinearJob* d_jobs, int n_jobs, int max_m, int max_n, cudaStream_t stream);
+// small_m_ok: every job has K % 4 == 0, 16-byte aligned A rows / W rows (then the weight-streaming kernel is used)
+int launch_linear_jobs(const LinearJob* d_jobs, int n_jobs, int max_m, int max_n, int max_k, bool small_m_ok, cudaStream_t stream);
 int launch_assemble_latent(float* latent, const float* w0, const float* w1, int wplus, int inject_index,
                            float truncation, const float* tlat, int tlat_rows, int batch, int n_latent, int dim,
                            cudaStream_t stream);

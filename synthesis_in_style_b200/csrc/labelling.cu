@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(32 * LBL_SLICES) label_native_kernel(LabelArgs
             for (int p = 0; p < PPT; ++p) acc[kk][p] = 0.0f;
         if (valid) {
             const float* xb = a.act + ((int64_t)b * a.C) * hw + pix;
-#pragma unroll 2
+#pragma unroll 8
             for (int c = c_begin; c < c_end; ++c) {
                 float xv[PPT];
                 if (PPT == 4) {

@@ -94,6 +94,69 @@ __global__ void __launch_bounds__(256) linear_nt_kernel(const LinearJob* __restr
     }
 }
 
+// Small-M variant (M <= 32 rows per block, K % 4 == 0): the GEMMs of this path have M = batch (32) and N, K <= 512, so
+// the work is streaming the weight matrix once.  One warp = one output column: its weight row is read with
+// coalesced 128-bit loads, the activation tile [32][K] sits in shared memory, every lane keeps 32 row accumulators
+// and the 32x32 (row, lane) partials are transposed through shared memory so that lane m finishes row m.
+constexpr int SM_COLS = 8;      // output columns (= warps) per block
+constexpr int SM_ROWS = 32;     // rows per block
+
+__global__ void __launch_bounds__(32 * SM_COLS) linear_small_m_kernel(const LinearJob* __restrict__ jobs) {
+    const LinearJob job = jobs[blockIdx.z];
+    const int m0 = blockIdx.y * SM_ROWS, n0 = blockIdx.x * SM_COLS;
+    if (m0 >= job.M || n0 >= job.N) return;
+    extern __shared__ __align__(16) float smem_lin[];
+    float* xs = smem_lin;                                  // [32][K]
+    float* red = smem_lin + (size_t)SM_ROWS * job.K;       // [SM_COLS][32][33]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int K = job.K, K4 = K >> 2;
+    for (int i = tid; i < SM_ROWS * K4; i += 32 * SM_COLS) {
+        const int r = i / K4, c4 = i - r * K4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m0 + r < job.M) {
+            const float* src = job.A + (int64_t)(m0 + r) * job.lda + c4 * 4;
+            v = make_float4(src[0], src[1], src[2], src[3]);
+            if (job.square_a) { v.x *= v.x; v.y *= v.y; v.z *= v.z; v.w *= v.w; }
+        }
+        reinterpret_cast<float4*>(xs)[i] = v;
+    }
+    __syncthreads();
+    const int n = n0 + warp;
+    float acc[SM_ROWS];
+#pragma unroll
+    for (int m = 0; m < SM_ROWS; ++m) acc[m] = 0.0f;
+    if (n < job.N) {
+        const float4* wrow = reinterpret_cast<const float4*>(job.W + (int64_t)n * K);
+        for (int c4 = lane; c4 < K4; c4 += 32) {
+            const float4 w = __ldg(wrow + c4);
+#pragma unroll
+            for (int m = 0; m < SM_ROWS; ++m) {
+                const float4 x = reinterpret_cast<const float4*>(xs)[m * K4 + c4];
+                acc[m] = fmaf(w.x, x.x, acc[m]); acc[m] = fmaf(w.y, x.y, acc[m]);
+                acc[m] = fmaf(w.z, x.z, acc[m]); acc[m] = fmaf(w.w, x.w, acc[m]);
+            }
+        }
+    }
+    float* myred = red + (size_t)warp * 32 * 33;
+#pragma unroll
+    for (int m = 0; m < SM_ROWS; ++m) myred[m * 33 + lane] = acc[m];
+    __syncwarp();
+    if (n < job.N && m0 + lane < job.M) {
+        float v = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v += myred[lane * 33 + j];
+        if (job.epilogue == LINEAR_EPI_BIAS) {
+            if (job.bias) v = __fadd_rn(v, job.bias[n]);
+        } else if (job.epilogue == LINEAR_EPI_BIAS_LRELU) {
+            if (job.bias) v = __fadd_rn(v, job.bias[n]);
+            v = lrelu_scale(v, 0.2f, 1.41421356237309504880f);
+        } else {
+            v = rsqrtf(v + 1e-8f);
+        }
+        job.C[(int64_t)(m0 + lane) * job.ldc + n] = v;
+    }
+}
+
 // latent[b, l, :] (model.py:502-528).  truncation uses the reference's separately rounded sub, mul, add.
 __global__ void __launch_bounds__(128) assemble_latent_kernel(float* __restrict__ latent, const float* __restrict__ w0,
                                                               const float* __restrict__ w1, int wplus, int inject_index,
@@ -148,10 +211,21 @@ int launch_pixel_norm(float* out, const float* z, int64_t rows, int dim, cudaStr
     return SIS_OK;
 }
 
-int launch_linear_jobs(const LinearJob* d_jobs, int n_jobs, int max_m, int max_n, cudaStream_t stream) {
+int launch_linear_jobs(const LinearJob* d_jobs, int n_jobs, int max_m, int max_n, int max_k, bool small_m_ok, cudaStream_t stream) {
     if (n_jobs == 0 || max_m == 0 || max_n == 0) return SIS_OK;
-    dim3 grid(ceil_div(max_n, LBN), ceil_div(max_m, LBM), n_jobs);
-    linear_nt_kernel<<<grid, 256, 0, stream>>>(d_jobs);
+    const size_t smem = ((size_t)SM_ROWS * max_k + (size_t)SM_COLS * 32 * 33) * sizeof(float);
+    if (small_m_ok && smem <= 200 * 1024) {
+        static bool configured = false;
+        if (!configured) {
+            SIS_CHECK_CUDA(cudaFuncSetAttribute(linear_small_m_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            configured = true;
+        }
+        dim3 grid(ceil_div(max_n, SM_COLS), ceil_div(max_m, SM_ROWS), n_jobs);
+        linear_small_m_kernel<<<grid, 32 * SM_COLS, smem, stream>>>(d_jobs);
+    } else {
+        dim3 grid(ceil_div(max_n, LBN), ceil_div(max_m, LBM), n_jobs);
+        linear_nt_kernel<<<grid, 256, 0, stream>>>(d_jobs);
+    }
     SIS_CHECK_LAUNCH();
     return SIS_OK;
 }

@@ -347,22 +347,119 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
 // ------------------------------------------------------------------------------- blur + activation + split
 // Second half of the up-sampling StyledConv: Blur(4x4, pad (1,1)) + noise + bias + lrelu*sqrt2 over the NHWC fp32
 // scratch, writing the fp32 NCHW capture and the next conv's pre-scaled bf16 hi/lo NHWC planes in one pass.
-// Block = 8x16 output pixels x 32 channels; lane = channel (conflict-free smem, 128 B coalesced NHWC rows).
 struct BlurSplitArgs {
     const float* in; int IH, IW;          // [B][IH][IW][C]
     float* out_f32; int OH, OW, C, batch; // [B][C][OH][OW]
     const float* blur_k; const float* noise; int64_t noise_bstride; float noise_w; const float* bias;
     const float* s_next; bf16* next_hi; bf16* next_lo;   // [B][OH][OW][C]
 };
-constexpr int BS_TH = 8, BS_TW = 16, BS_C = 32;
+constexpr int BS_TH = 8, BS_TW = 16, BS_C = 64;
 constexpr int BS_IH = BS_TH + 3, BS_IW = BS_TW + 3;
+constexpr int BS_OPITCH = BS_TH * BS_TW + 1;                      // 129: transposing writes are 2-way conflicted at worst
+constexpr int BS_SMEM = BS_IH * BS_IW * BS_C * 4;                 // 53,504 B
 
-__global__ void __launch_bounds__(256) blur_act_split_kernel(BlurSplitArgs a) {
-    __shared__ float sin_[BS_IH * BS_IW][BS_C];          // 26.1 KB
-    __shared__ float sout[BS_C][BS_TH * BS_TW + 1];      // 16.1 KB
-    __shared__ float sk[16];
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2): two channels per lane per instruction
+using u64 = unsigned long long;
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<u64&>(d)) : "l"(reinterpret_cast<u64&>(a)), "l"(reinterpret_cast<u64&>(b)), "l"(reinterpret_cast<u64&>(c)));
+    return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    float2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<u64&>(d)) : "l"(reinterpret_cast<u64&>(a)), "l"(reinterpret_cast<u64&>(b)));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    float2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<u64&>(d)) : "l"(reinterpret_cast<u64&>(a)), "l"(reinterpret_cast<u64&>(b)));
+    return d;
+}
+__device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+
+// Block = 8x16 output pixels x 64 channels, 8 warps; lane = 2 channels (LDS.64, packed fp32x2 math, 32-bit bf16x2
+// stores).  The 11x19x64 fp32 input tile is staged with 16-byte cp.async (all chunks in flight at once).  Warp w owns
+// output columns 2w, 2w+1 and walks down the rows.  Separable taps (the reference's [1,3,3,1] outer product always
+// is): a horizontal 4-tap pass per input row, then a vertical 4-tap pass over a sliding register window = 8 FMAs per
+// output instead of 16; a non-separable `blur.kernel` takes the generic 16-tap path.  The bf16 hi/lo NHWC planes are
+// written straight from registers (128 B per pixel per plane); the fp32 NCHW capture goes through a shared-memory
+// transpose that re-uses the input tile's storage.
+template <bool SEP>
+__device__ __forceinline__ void blur_columns(const BlurSplitArgs& a, const float* stile, const float* sk, const float* skx,
+                                             const float* sky, int b, int y0, int x0, int c0, int warp, int lane,
+                                             float2 (&res)[2][BS_TH]) {
+    const float2 bias = *reinterpret_cast<const float2*>(a.bias + c0 + 2 * lane);
+    const float2 sn = a.s_next ? *reinterpret_cast<const float2*>(a.s_next + (int64_t)b * a.C + c0 + 2 * lane) : make_float2(0.f, 0.f);
+    const float2* st2 = reinterpret_cast<const float2*>(stile);    // [pix][32 lanes]
+#pragma unroll
+    for (int cx = 0; cx < 2; ++cx) {
+        const int px = warp * 2 + cx;
+        const int ox = x0 + px;
+        float2 win[4][SEP ? 1 : 4];
+#pragma unroll
+        for (int r = 0; r < BS_IH; ++r) {
+            // shift the window up and bring in input row r
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < (SEP ? 1 : 4); ++kx) win[ky][kx] = win[ky + 1][kx];
+            if (SEP) {
+                float2 h = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int kx = 0; kx < 4; ++kx) h = ffma2(st2[(r * BS_IW + px + kx) * 32 + lane], splat2(skx[kx]), h);
+                win[3][0] = h;
+            } else {
+#pragma unroll
+                for (int kx = 0; kx < 4; ++kx) win[3][kx] = st2[(r * BS_IW + px + kx) * 32 + lane];
+            }
+            if (r >= 3) {
+                const int py = r - 3;
+                float2 v = make_float2(0.f, 0.f);
+                if (SEP) {
+#pragma unroll
+                    for (int ky = 0; ky < 4; ++ky) v = ffma2(win[ky][0], splat2(sky[ky]), v);
+                } else {
+#pragma unroll
+                    for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < 4; ++kx) v = ffma2(win[ky][kx], splat2(sk[ky * 4 + kx]), v);
+                }
+                const int oy = y0 + py;
+                if (oy < a.OH && ox < a.OW) {
+                    const float nz = a.noise_w * __ldg(a.noise + (int64_t)b * a.noise_bstride + (int64_t)oy * a.OW + ox);
+                    v = fadd2(fadd2(v, splat2(nz)), bias);
+                    // lrelu(x)*sqrt2 = max(x*sqrt2, x*0.2*sqrt2)
+                    const float2 p = fmul2(v, splat2(1.41421356237309504880f)), q = fmul2(v, splat2(0.2f * 1.41421356237309504880f));
+                    v = make_float2(fmaxf(p.x, q.x), fmaxf(p.y, q.y));
+                    if (a.s_next) {
+                        const float2 xs = fmul2(v, sn);
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(xs.x, xs.y);
+                        const float2 hf = __bfloat1622float2(h);
+                        const __nv_bfloat162 l = __floats2bfloat162_rn(xs.x - hf.x, xs.y - hf.y);
+                        const int64_t off = (((int64_t)b * a.OH + oy) * a.OW + ox) * a.C + c0 + 2 * lane;
+                        *reinterpret_cast<__nv_bfloat162*>(a.next_hi + off) = h;
+                        *reinterpret_cast<__nv_bfloat162*>(a.next_lo + off) = l;
+                    }
+                }
+                res[cx][py] = v;
+            }
+        }
+    }
+}
+
+template <bool SEP>
+__global__ void __launch_bounds__(256, 3) blur_act_split_kernel(BlurSplitArgs a) {
+    extern __shared__ __align__(16) float stile[];    // [11*19][64] fp32; re-used as sout[64][129]
+    __shared__ float sk[16], skx[4], sky[4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 16) sk[tid] = a.blur_k[(3 - tid / 4) * 4 + (3 - tid % 4)];   // flipped taps
+    __syncthreads();
+    if (tid < 4) { sky[tid] = sk[tid * 4]; skx[tid] = SEP ? sk[tid] / sk[0] : 0.0f; }   // k[i][j] = sky[i] * skx[j]
     const int tiles_x = (a.OW + BS_TW - 1) / BS_TW, tiles_y = (a.OH + BS_TH - 1) / BS_TH;
     const int cgroups = a.C / BS_C;
     const int64_t total = (int64_t)a.batch * tiles_y * tiles_x * cgroups;
@@ -373,48 +470,39 @@ __global__ void __launch_bounds__(256) blur_act_split_kernel(BlurSplitArgs a) {
         const int ty = (int)(r % tiles_y);
         const int b = (int)(r / tiles_y);
         const int y0 = ty * BS_TH, x0 = tx * BS_TW, c0 = cg * BS_C;
-        __syncthreads();
-        for (int i = warp; i < BS_IH * BS_IW; i += 8) {
-            const int iy = y0 + i / BS_IW - 1, ix = x0 + i % BS_IW - 1;
-            float v = 0.0f;
+        __syncthreads();     // previous tile's transpose reads are done (and the tap tables are visible)
+        // ---- stage the input tile: chunk q = (pixel, 16-byte part); 16 parts per pixel
+        for (int q = tid; q < BS_IH * BS_IW * 16; q += 256) {
+            const int pix = q >> 4, part = q & 15;
+            const int iy = y0 + pix / BS_IW - 1, ix = x0 + pix % BS_IW - 1;
+            float* dst = stile + pix * BS_C + part * 4;
             if (iy >= 0 && ix >= 0 && iy < a.IH && ix < a.IW)
-                v = __ldg(a.in + (((int64_t)b * a.IH + iy) * a.IW + ix) * a.C + c0 + lane);
-            sin_[i][lane] = v;
+                cp_async_16(dst, a.in + (((int64_t)b * a.IH + iy) * a.IW + ix) * a.C + c0 + part * 4);
+            else
+                *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        cp_async_wait_all();
         __syncthreads();
-        const float bias = a.bias[c0 + lane];
-        const float sn = a.s_next ? a.s_next[(int64_t)b * a.C + c0 + lane] : 0.0f;
-#pragma unroll 2
-        for (int p = warp; p < BS_TH * BS_TW; p += 8) {
-            const int py = p / BS_TW, px = p % BS_TW;
-            float v = 0.0f;
+        float2 res[2][BS_TH];
+        blur_columns<SEP>(a, stile, sk, skx, sky, b, y0, x0, c0, warp, lane, res);
+        __syncthreads();     // everyone is done reading the input tile
+        float* sout = stile; // [64][129]
 #pragma unroll
-            for (int ky = 0; ky < 4; ++ky)
+        for (int cx = 0; cx < 2; ++cx)
 #pragma unroll
-                for (int kx = 0; kx < 4; ++kx) v = __fmaf_rn(sin_[(py + ky) * BS_IW + px + kx][lane], sk[ky * 4 + kx], v);
-            const int oy = y0 + py, ox = x0 + px;
-            if (oy < a.OH && ox < a.OW) {
-                v = __fadd_rn(v, __fmul_rn(a.noise_w, __ldg(a.noise + (int64_t)b * a.noise_bstride + (int64_t)oy * a.OW + ox)));
-                v = __fadd_rn(v, bias);
-                v = lrelu_scale(v, 0.2f, 1.41421356237309504880f);
-                if (a.s_next) {
-                    const float xs = __fmul_rn(v, sn);
-                    const bf16 h = __float2bfloat16_rn(xs);
-                    const bf16 l = __float2bfloat16_rn(xs - __bfloat162float(h));
-                    const int64_t off = (((int64_t)b * a.OH + oy) * a.OW + ox) * a.C + c0 + lane;
-                    a.next_hi[off] = h; a.next_lo[off] = l;
-                }
+            for (int py = 0; py < BS_TH; ++py) {
+                const int p = py * BS_TW + warp * 2 + cx;
+                sout[(2 * lane) * BS_OPITCH + p] = res[cx][py].x;
+                sout[(2 * lane + 1) * BS_OPITCH + p] = res[cx][py].y;
             }
-            sout[lane][p] = v;
-        }
         __syncthreads();
-        // NCHW capture: each warp writes 4 channels; lanes = 32 consecutive tile pixels (2 rows of 16)
+        // ---- NCHW capture: warp -> 8 channels, lanes -> 32 consecutive tile pixels (2 rows of 16)
         for (int ci = warp; ci < BS_C; ci += 8) {
             float* dst = a.out_f32 + ((int64_t)b * a.C + c0 + ci) * a.OH * a.OW;
 #pragma unroll
             for (int p = lane; p < BS_TH * BS_TW; p += 32) {
                 const int oy = y0 + p / BS_TW, ox = x0 + p % BS_TW;
-                if (oy < a.OH && ox < a.OW) dst[(int64_t)oy * a.OW + ox] = sout[ci][p];
+                if (oy < a.OH && ox < a.OW) dst[(int64_t)oy * a.OW + ox] = sout[ci * BS_OPITCH + p];
             }
         }
     }
@@ -668,10 +756,19 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
         bs.out_f32 = call.out_f32; bs.OH = call.res_out; bs.OW = call.res_out; bs.C = call.cout; bs.batch = B;
         bs.blur_k = call.blur_k; bs.noise = call.noise; bs.noise_bstride = call.noise_bstride; bs.noise_w = call.noise_w; bs.bias = call.bias;
         bs.s_next = call.s_next; bs.next_hi = (bf16*)ws.a_hi[call.out_slot]; bs.next_lo = (bf16*)ws.a_lo[call.out_slot];
+        SIS_REQUIRE(bs.C % BS_C == 0, "tc_modconv: the blur pass needs Cout %% 64 == 0 (got %d)", bs.C);
+        static int blocks_per_sm[2] = {0, 0};
+        const int sep = call.blur_separable ? 1 : 0;
+        auto kern = sep ? blur_act_split_kernel<true> : blur_act_split_kernel<false>;
+        if (!blocks_per_sm[sep]) {
+            SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BS_SMEM));
+            SIS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[sep], kern, 256, BS_SMEM));
+            if (blocks_per_sm[sep] < 1) blocks_per_sm[sep] = 1;
+        }
         const int64_t total = (int64_t)B * ceil_div(bs.OH, BS_TH) * ceil_div(bs.OW, BS_TW) * (bs.C / BS_C);
-        const int grid = (int)std::min<int64_t>(total, (int64_t)kNumSMs * 4);
+        const int grid = (int)std::min<int64_t>(total, (int64_t)kNumSMs * blocks_per_sm[sep]);   // exactly one resident wave
         ProfScope prof(PROF_BLUR_SPLIT, stream);
-        blur_act_split_kernel<<<grid, 256, 0, stream>>>(bs);
+        kern<<<grid, 256, BS_SMEM, stream>>>(bs);
         SIS_CHECK_LAUNCH();
     }
     return SIS_OK;

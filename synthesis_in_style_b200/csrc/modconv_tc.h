@@ -32,6 +32,7 @@ struct TcConvCall {
     const float* noise; int64_t noise_bstride; float noise_w;
     const float* bias;         // [cout]
     const float* blur_k;       // [4,4] (up only)
+    bool blur_separable;       // blur_k is an outer product (checked on the host at prepare time)
     float* out_f32;            // [B, cout, res_out, res_out] NCHW (the captured activation)
     const float* s_next;       // [B, cout] style of the next conv (null for the last layer)
     int in_slot, out_slot;
