@@ -184,9 +184,77 @@ __global__ void __launch_bounds__(32 * RGB_SLICES) torgb_kernel(ToRgbArgs a) {
     }
 }
 
+// Wide variant for large maps: one thread = 4 consecutive pixels x ALL channels (no channel slicing, no barrier in
+// the main loop); a block reads 4 KB contiguous per channel plane; 128-bit loads and stores.
+__device__ __forceinline__ float torgb_skip_tap(const ToRgbArgs& a, const float* sp, int y, int x) {
+    // Upsample: upfirdn2d(skip, k*4, up=2, pad=(2,1)) (model.py:34-52): mid = o - 1
+    const int SH = a.H / 2, SW = a.W / 2;
+    const int mid_y = y - 1, mid_x = x - 1;
+    const int iy0 = (mid_y < 0) ? -1 : (mid_y >> 1), ix0 = (mid_x < 0) ? -1 : (mid_x >> 1);
+    const int ky0 = (iy0 + 1) * 2 - mid_y - 1, kx0 = (ix0 + 1) * 2 - mid_x - 1;
+    float u = 0.0f;
+#pragma unroll
+    for (int yy = 0; yy < 2; ++yy)
+#pragma unroll
+        for (int xx = 0; xx < 2; ++xx) {
+            const int iy = iy0 + yy, ix = ix0 + xx;
+            float sv = 0.0f;
+            if (iy >= 0 && ix >= 0 && iy < SH && ix < SW) sv = __ldg(sp + (int64_t)iy * SW + ix);
+            const int ky = ky0 + yy * 2, kx = kx0 + xx * 2;
+            u = __fmaf_rn(sv, __ldg(a.up_k + (3 - ky) * 4 + (3 - kx)), u);
+        }
+    return u;
+}
+
+__global__ void __launch_bounds__(256) torgb_wide_kernel(ToRgbArgs a) {
+    extern __shared__ float smem[];
+    float* swr = smem;                                  // [3][C]  scale*W
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 3 * a.C; i += 256) swr[i] = a.w[i];
+    __syncthreads();
+    const int64_t hw = (int64_t)a.H * a.W;
+    const int64_t quads_per_sample = hw >> 2;
+    const int64_t q = (int64_t)blockIdx.x * 256 + tid;
+    if (q >= quads_per_sample * a.batch) return;
+    const int b = (int)(q / quads_per_sample);
+    const int64_t pix = (q - (int64_t)b * quads_per_sample) << 2;
+    const float* xb = a.x + ((int64_t)b * a.C) * hw + pix;
+    const float* sb = a.s + (int64_t)b * a.C;
+    float acc[3][4] = {};
+#pragma unroll 8
+    for (int c = 0; c < a.C; ++c) {
+        const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(xb + (int64_t)c * hw));
+        const float s = __ldg(sb + c);
+        const float w0 = __fmul_rn(swr[c], s), w1 = __fmul_rn(swr[a.C + c], s), w2 = __fmul_rn(swr[2 * a.C + c], s);
+        acc[0][0] = fmaf(w0, v.x, acc[0][0]); acc[0][1] = fmaf(w0, v.y, acc[0][1]);
+        acc[0][2] = fmaf(w0, v.z, acc[0][2]); acc[0][3] = fmaf(w0, v.w, acc[0][3]);
+        acc[1][0] = fmaf(w1, v.x, acc[1][0]); acc[1][1] = fmaf(w1, v.y, acc[1][1]);
+        acc[1][2] = fmaf(w1, v.z, acc[1][2]); acc[1][3] = fmaf(w1, v.w, acc[1][3]);
+        acc[2][0] = fmaf(w2, v.x, acc[2][0]); acc[2][1] = fmaf(w2, v.y, acc[2][1]);
+        acc[2][2] = fmaf(w2, v.z, acc[2][2]); acc[2][3] = fmaf(w2, v.w, acc[2][3]);
+    }
+    const int y = (int)(pix / a.W), x = (int)(pix - (int64_t)y * a.W);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        float o[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            float v = __fadd_rn(acc[j][p], a.bias[j]);
+            if (a.skip) v = __fadd_rn(v, torgb_skip_tap(a, a.skip + ((int64_t)b * 3 + j) * (hw >> 2), y, x + p));
+            o[p] = v;
+        }
+        *reinterpret_cast<float4*>(a.out + ((int64_t)b * 3 + j) * hw + pix) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 int launch_torgb(const ToRgbArgs& a, cudaStream_t stream) {
     SIS_REQUIRE((a.H * a.W) % 4 == 0, "torgb: H*W must be a multiple of 4");
     int64_t quads = (int64_t)a.H * a.W / 4 * a.batch;
+    if (a.W % 4 == 0 && quads >= (int64_t)kNumSMs * 512 && 3 * a.C * sizeof(float) <= 48 * 1024) {
+        torgb_wide_kernel<<<(unsigned)ceil_div64(quads, 256), 256, 3 * a.C * sizeof(float), stream>>>(a);
+        SIS_CHECK_LAUNCH();
+        return SIS_OK;
+    }
     int64_t blocks = ceil_div64(quads, 32);
     int64_t cap = (int64_t)kNumSMs * 8;
     int grid = (int)(blocks < cap ? blocks : cap);

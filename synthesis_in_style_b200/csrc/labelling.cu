@@ -158,6 +158,109 @@ __global__ void __launch_bounds__(32 * LBL_SLICES) label_native_kernel(LabelArgs
     if (a.hist && tid < a.k && shist[tid]) atomicAdd(a.hist + tid, (unsigned long long)shist[tid]);
 }
 
+// Wide variant for large maps (>= ~150k pixel quads: enough threads without slicing the channels): one thread = 4
+// consecutive pixels x ALL channels.  A block of 256 threads reads 4 KB contiguous per channel plane (DRAM-friendly),
+// keeps 8 independent 128-bit loads in flight per thread, needs no shared-memory reduction and no barrier, and
+// finalises in registers: packed 4-pixel stores for ids and masks (32-bit for rep 1, 128-bit rows for rep 4).
+template <int KMAX>
+__global__ void __launch_bounds__(256) label_wide_kernel(LabelArgs a) {
+    extern __shared__ float smem[];
+    float* sc = smem;                                   // [C][KMAX]
+    unsigned* shist = reinterpret_cast<unsigned*>(smem + (size_t)a.C * KMAX);   // [KMAX]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < a.C * KMAX; i += 256) {
+        int c = i / KMAX, kk = i - c * KMAX;
+        sc[i] = kk < a.k ? a.centroids[(int64_t)kk * a.C + c] : 0.0f;
+    }
+    if (tid < KMAX) shist[tid] = 0;
+    __syncthreads();
+    const int64_t hw = (int64_t)a.H * a.W;
+    const int64_t quads_per_sample = hw >> 2;
+    const int64_t total = quads_per_sample * a.batch;
+    const int64_t q = (int64_t)blockIdx.x * 256 + tid;
+    const bool valid = q < total;
+    int ids[4] = {-1, -1, -1, -1};
+    if (valid) {
+        const int b = (int)(q / quads_per_sample);
+        const int64_t pix = (q - (int64_t)b * quads_per_sample) << 2;
+        const float* xb = a.act + ((int64_t)b * a.C) * hw + pix;
+        float acc[KMAX][4];
+#pragma unroll
+        for (int kk = 0; kk < KMAX; ++kk)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[kk][p] = 0.0f;
+#pragma unroll 8
+        for (int c = 0; c < a.C; ++c) {
+            const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(xb + (int64_t)c * hw));
+            const float xv[4] = {v.x, v.y, v.z, v.w};
+            const float* cc = sc + (size_t)c * KMAX;
+#pragma unroll
+            for (int kk = 0; kk < KMAX; ++kk) {
+                const float m = cc[kk];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float df = __fsub_rn(xv[p], m);
+                    acc[kk][p] = __fmaf_rn(df, df, acc[kk][p]);
+                }
+            }
+        }
+        float best[4], second[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) { best[p] = INFINITY; second[p] = INFINITY; ids[p] = 0; }
+#pragma unroll
+        for (int kk = 0; kk < KMAX; ++kk) {
+            if (kk < a.k) {
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float d = acc[kk][p];
+                    if (d < best[p]) { second[p] = best[p]; best[p] = d; ids[p] = kk; }
+                    else if (d < second[p]) { second[p] = d; }
+                }
+            }
+        }
+        const int64_t n0 = (int64_t)b * hw + pix;       // flat [B,H,W] index of the first pixel
+        if (a.ids_u8) *reinterpret_cast<uint32_t*>(a.ids_u8 + n0) = (uint32_t)ids[0] | ((uint32_t)ids[1] << 8) | ((uint32_t)ids[2] << 16) | ((uint32_t)ids[3] << 24);
+        if (a.ids_i64) {
+#pragma unroll
+            for (int p = 0; p < 4; ++p) a.ids_i64[n0 + p] = ids[p];
+        }
+        if (a.margin) *reinterpret_cast<float4*>(a.margin + n0) = make_float4(second[0] - best[0], second[1] - best[1], second[2] - best[2], second[3] - best[3]);
+        if (a.masks) {
+            uint32_t bits[4];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) bits[p] = __ldg(a.class_bits + ids[p]);
+            const int rep = a.S / a.H;
+            const int y = (int)(pix / a.W), x = (int)(pix - (int64_t)y * a.W);
+            const int64_t plane = (int64_t)a.S * a.S;
+            for (int j = 0; j < a.n_class; ++j) {
+                uint8_t* dst = a.masks + ((int64_t)j * a.batch + b) * plane + (int64_t)y * rep * a.S + (int64_t)x * rep;
+                const uint32_t m0 = (bits[0] >> j) & 1u, m1 = (bits[1] >> j) & 1u, m2 = (bits[2] >> j) & 1u, m3 = (bits[3] >> j) & 1u;
+                if (rep == 1) {
+                    *reinterpret_cast<uint32_t*>(dst) = m0 | (m1 << 8) | (m2 << 16) | (m3 << 24);
+                } else if (rep == 4) {
+                    const uint4 row = make_uint4(m0 * 0x01010101u, m1 * 0x01010101u, m2 * 0x01010101u, m3 * 0x01010101u);
+#pragma unroll
+                    for (int ry = 0; ry < 4; ++ry) *reinterpret_cast<uint4*>(dst + (int64_t)ry * a.S) = row;
+                } else {
+                    const uint32_t mm[4] = {m0, m1, m2, m3};
+                    for (int ry = 0; ry < rep; ++ry)
+                        for (int p = 0; p < 4; ++p)
+                            for (int rx = 0; rx < rep; ++rx) dst[(int64_t)ry * a.S + p * rep + rx] = (uint8_t)mm[p];
+                }
+            }
+        }
+    }
+    if (a.hist) {
+        for (int kk = 0; kk < a.k; ++kk) {
+            const unsigned c = (unsigned)(ids[0] == kk) + (unsigned)(ids[1] == kk) + (unsigned)(ids[2] == kk) + (unsigned)(ids[3] == kk);
+            const unsigned tot = __reduce_add_sync(0xffffffffu, c);
+            if ((tid & 31) == 0 && tot) atomicAdd(&shist[kk], tot);
+        }
+        __syncthreads();
+        if (tid < a.k && shist[tid]) atomicAdd(a.hist + tid, (unsigned long long)shist[tid]);
+    }
+}
+
 // masks for a non-integer resize ratio: gather from the ids (rare; power-of-two sizes never take it)
 __global__ void __launch_bounds__(256) masks_gather_kernel(uint8_t* __restrict__ masks, const uint8_t* __restrict__ ids,
                                                            const uint32_t* __restrict__ class_bits, int n_class,
@@ -281,6 +384,17 @@ static int launch_native(const LabelArgs& a, cudaStream_t stream) {
 }
 
 template <int KMAX>
+static int launch_wide(const LabelArgs& a, cudaStream_t stream) {
+    size_t smem = ((size_t)a.C * KMAX + KMAX) * sizeof(float);
+    auto kern = label_wide_kernel<KMAX>;
+    if (smem > 48 * 1024) SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int64_t quads = (int64_t)a.H * a.W / 4 * a.batch;
+    kern<<<(unsigned)ceil_div64(quads, 256), 256, smem, stream>>>(a);
+    SIS_CHECK_LAUNCH();
+    return SIS_OK;
+}
+
+template <int KMAX>
 static int launch_bilinear(const LabelArgs& a, cudaStream_t stream) {
     size_t smem = (size_t)a.C * KMAX * sizeof(float);
     auto kern = label_bilinear_kernel<KMAX>;
@@ -332,7 +446,17 @@ extern "C" int sis_label_assign(const float* d_act, int batch, int channels, int
         a.masks = nullptr;
     }
     int st;
-    if (vec4) {
+    // wide path: enough pixel quads to fill the GPU without slicing channels, integer (or no) mask replication,
+    // rows that are a multiple of 4 pixels, k small enough for 4 x k register accumulators
+    const int64_t quads = (int64_t)h * w / 4 * batch;
+    const bool wide_ok = vec4 && k <= 16 && w % 4 == 0 && quads >= (int64_t)kNumSMs * 512 &&
+                         (!a.masks || (int_ratio && ((((uintptr_t)a.masks) & 15) == 0))) &&
+                         (!a.ids_u8 || ((((uintptr_t)a.ids_u8) & 3) == 0)) && (!a.margin || ((((uintptr_t)a.margin) & 15) == 0));
+    if (wide_ok) {
+        if (k <= 4) st = launch_wide<4>(a, stream);
+        else if (k <= 8) st = launch_wide<8>(a, stream);
+        else st = launch_wide<16>(a, stream);
+    } else if (vec4) {
         if (k <= 4) st = launch_native<4, 4>(a, stream);
         else if (k <= 8) st = launch_native<8, 4>(a, stream);
         else if (k <= 16) st = launch_native<16, 4>(a, stream);

@@ -384,78 +384,17 @@ __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 
 // Block = 8x16 output pixels x 64 channels, 8 warps; lane = 2 channels (LDS.64, packed fp32x2 math, 32-bit bf16x2
 // stores).  The 11x19x64 fp32 input tile is staged with 16-byte cp.async (all chunks in flight at once).  Warp w owns
-// output columns 2w, 2w+1 and walks down the rows.  Separable taps (the reference's [1,3,3,1] outer product always
-// is): a horizontal 4-tap pass per input row, then a vertical 4-tap pass over a sliding register window = 8 FMAs per
-// output instead of 16; a non-separable `blur.kernel` takes the generic 16-tap path.  The bf16 hi/lo NHWC planes are
-// written straight from registers (128 B per pixel per plane); the fp32 NCHW capture goes through a shared-memory
-// transpose that re-uses the input tile's storage.
-template <bool SEP>
-__device__ __forceinline__ void blur_columns(const BlurSplitArgs& a, const float* stile, const float* sk, const float* skx,
-                                             const float* sky, int b, int y0, int x0, int c0, int warp, int lane,
-                                             float2 (&res)[2][BS_TH]) {
-    const float2 bias = *reinterpret_cast<const float2*>(a.bias + c0 + 2 * lane);
-    const float2 sn = a.s_next ? *reinterpret_cast<const float2*>(a.s_next + (int64_t)b * a.C + c0 + 2 * lane) : make_float2(0.f, 0.f);
-    const float2* st2 = reinterpret_cast<const float2*>(stile);    // [pix][32 lanes]
-#pragma unroll
-    for (int cx = 0; cx < 2; ++cx) {
-        const int px = warp * 2 + cx;
-        const int ox = x0 + px;
-        float2 win[4][SEP ? 1 : 4];
-#pragma unroll
-        for (int r = 0; r < BS_IH; ++r) {
-            // shift the window up and bring in input row r
-#pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-                for (int kx = 0; kx < (SEP ? 1 : 4); ++kx) win[ky][kx] = win[ky + 1][kx];
-            if (SEP) {
-                float2 h = make_float2(0.f, 0.f);
-#pragma unroll
-                for (int kx = 0; kx < 4; ++kx) h = ffma2(st2[(r * BS_IW + px + kx) * 32 + lane], splat2(skx[kx]), h);
-                win[3][0] = h;
-            } else {
-#pragma unroll
-                for (int kx = 0; kx < 4; ++kx) win[3][kx] = st2[(r * BS_IW + px + kx) * 32 + lane];
-            }
-            if (r >= 3) {
-                const int py = r - 3;
-                float2 v = make_float2(0.f, 0.f);
-                if (SEP) {
-#pragma unroll
-                    for (int ky = 0; ky < 4; ++ky) v = ffma2(win[ky][0], splat2(sky[ky]), v);
-                } else {
-#pragma unroll
-                    for (int ky = 0; ky < 4; ++ky)
-#pragma unroll
-                        for (int kx = 0; kx < 4; ++kx) v = ffma2(win[ky][kx], splat2(sk[ky * 4 + kx]), v);
-                }
-                const int oy = y0 + py;
-                if (oy < a.OH && ox < a.OW) {
-                    const float nz = a.noise_w * __ldg(a.noise + (int64_t)b * a.noise_bstride + (int64_t)oy * a.OW + ox);
-                    v = fadd2(fadd2(v, splat2(nz)), bias);
-                    // lrelu(x)*sqrt2 = max(x*sqrt2, x*0.2*sqrt2)
-                    const float2 p = fmul2(v, splat2(1.41421356237309504880f)), q = fmul2(v, splat2(0.2f * 1.41421356237309504880f));
-                    v = make_float2(fmaxf(p.x, q.x), fmaxf(p.y, q.y));
-                    if (a.s_next) {
-                        const float2 xs = fmul2(v, sn);
-                        const __nv_bfloat162 h = __floats2bfloat162_rn(xs.x, xs.y);
-                        const float2 hf = __bfloat1622float2(h);
-                        const __nv_bfloat162 l = __floats2bfloat162_rn(xs.x - hf.x, xs.y - hf.y);
-                        const int64_t off = (((int64_t)b * a.OH + oy) * a.OW + ox) * a.C + c0 + 2 * lane;
-                        *reinterpret_cast<__nv_bfloat162*>(a.next_hi + off) = h;
-                        *reinterpret_cast<__nv_bfloat162*>(a.next_lo + off) = l;
-                    }
-                }
-                res[cx][py] = v;
-            }
-        }
-    }
-}
-
+// the output column pair (2w, 2w+1) and walks down the rows, sharing the 5 input columns the pair needs.  Separable
+// taps (the reference's [1,3,3,1] outer product always is): a horizontal 4-tap pass per input row, then a vertical
+// 4-tap pass over a sliding register window = 8 FMAs per output instead of 16; a non-separable `blur.kernel` takes the
+// generic 16-tap path.  The bf16 hi/lo NHWC planes are written straight from registers (128 B per pixel per plane);
+// the fp32 NCHW capture goes through a shared-memory transpose that re-uses the input tile's storage.  All index
+// arithmetic is hoisted out of the per-element loops: the kernel is HBM-bound only if its instruction count is small.
 template <bool SEP>
 __global__ void __launch_bounds__(256, 3) blur_act_split_kernel(BlurSplitArgs a) {
     extern __shared__ __align__(16) float stile[];    // [11*19][64] fp32; re-used as sout[64][129]
     __shared__ float sk[16], skx[4], sky[4];
+    __shared__ float snz[BS_TH * BS_TW];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 16) sk[tid] = a.blur_k[(3 - tid / 4) * 4 + (3 - tid % 4)];   // flipped taps
     __syncthreads();
@@ -463,6 +402,10 @@ __global__ void __launch_bounds__(256, 3) blur_act_split_kernel(BlurSplitArgs a)
     const int tiles_x = (a.OW + BS_TW - 1) / BS_TW, tiles_y = (a.OH + BS_TH - 1) / BS_TH;
     const int cgroups = a.C / BS_C;
     const int64_t total = (int64_t)a.batch * tiles_y * tiles_x * cgroups;
+    const uint32_t stile_u32 = smem_u32(stile);
+    const float2* st2 = reinterpret_cast<const float2*>(stile);    // [pix][32 lanes]
+    const int part = tid & 15;
+
     for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int cg = (int)(tile % cgroups);
         int64_t r = tile / cgroups;
@@ -471,38 +414,119 @@ __global__ void __launch_bounds__(256, 3) blur_act_split_kernel(BlurSplitArgs a)
         const int b = (int)(r / tiles_y);
         const int y0 = ty * BS_TH, x0 = tx * BS_TW, c0 = cg * BS_C;
         __syncthreads();     // previous tile's transpose reads are done (and the tap tables are visible)
-        // ---- stage the input tile: chunk q = (pixel, 16-byte part); 16 parts per pixel
-        for (int q = tid; q < BS_IH * BS_IW * 16; q += 256) {
-            const int pix = q >> 4, part = q & 15;
-            const int iy = y0 + pix / BS_IW - 1, ix = x0 + pix % BS_IW - 1;
-            float* dst = stile + pix * BS_C + part * 4;
-            if (iy >= 0 && ix >= 0 && iy < a.IH && ix < a.IW)
-                cp_async_16(dst, a.in + (((int64_t)b * a.IH + iy) * a.IW + ix) * a.C + c0 + part * 4);
-            else
-                *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        // ---- stage the input tile: 16 threads per pixel (16-byte parts), 16 pixels per pass
+        {
+            const float* src_base = a.in + (int64_t)b * a.IH * a.IW * a.C + c0 + part * 4;
+#pragma unroll 2
+            for (int pi = tid >> 4; pi < BS_IH * BS_IW; pi += 16) {
+                const int ry = pi / BS_IW, rx = pi - ry * BS_IW;
+                const int iy = y0 + ry - 1, ix = x0 + rx - 1;
+                const uint32_t dst = stile_u32 + (uint32_t)(pi * BS_C + part * 4) * 4u;
+                if ((unsigned)iy < (unsigned)a.IH && (unsigned)ix < (unsigned)a.IW)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src_base + (int64_t)(iy * a.IW + ix) * a.C) : "memory");
+                else
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "f"(0.0f) : "memory");
+            }
+            if (tid < BS_TH * BS_TW) {
+                const int oy = y0 + (tid >> 4), ox = x0 + (tid & 15);
+                snz[tid] = (oy < a.OH && ox < a.OW) ? a.noise_w * __ldg(a.noise + (int64_t)b * a.noise_bstride + (int64_t)oy * a.OW + ox) : 0.0f;
+            }
         }
         cp_async_wait_all();
         __syncthreads();
+
+        // ---- blur: column pair (px, px+1), rows top to bottom
         float2 res[2][BS_TH];
-        blur_columns<SEP>(a, stile, sk, skx, sky, b, y0, x0, c0, warp, lane, res);
+        {
+            const int px = warp * 2;
+            const float2 bias = *reinterpret_cast<const float2*>(a.bias + c0 + 2 * lane);
+            const float2 sn = a.s_next ? *reinterpret_cast<const float2*>(a.s_next + (int64_t)b * a.C + c0 + 2 * lane) : make_float2(0.f, 0.f);
+            const bool colok0 = x0 + px < a.OW, colok1 = x0 + px + 1 < a.OW;
+            // NHWC element offset of (b, y0, x0+px, c0+2*lane); advances by OW*C per row, C per column
+            const int64_t off0 = (((int64_t)b * a.OH + y0) * a.OW + x0 + px) * a.C + c0 + 2 * lane;
+            const int64_t row_stride = (int64_t)a.OW * a.C;
+            float2 win[2][4][SEP ? 1 : 4];
+#pragma unroll
+            for (int rr = 0; rr < BS_IH; ++rr) {
+                float2 in5[5];
+#pragma unroll
+                for (int j = 0; j < 5; ++j) in5[j] = st2[(rr * BS_IW + px + j) * 32 + lane];
+#pragma unroll
+                for (int cx = 0; cx < 2; ++cx) {
+#pragma unroll
+                    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                        for (int kx = 0; kx < (SEP ? 1 : 4); ++kx) win[cx][ky][kx] = win[cx][ky + 1][kx];
+                    if (SEP) {
+                        float2 h = make_float2(0.f, 0.f);
+#pragma unroll
+                        for (int kx = 0; kx < 4; ++kx) h = ffma2(in5[cx + kx], splat2(skx[kx]), h);
+                        win[cx][3][0] = h;
+                    } else {
+#pragma unroll
+                        for (int kx = 0; kx < 4; ++kx) win[cx][3][kx] = in5[cx + kx];
+                    }
+                }
+                if (rr >= 3) {
+                    const int py = rr - 3;
+                    const bool rowok = y0 + py < a.OH;
+#pragma unroll
+                    for (int cx = 0; cx < 2; ++cx) {
+                        float2 v = make_float2(0.f, 0.f);
+                        if (SEP) {
+#pragma unroll
+                            for (int ky = 0; ky < 4; ++ky) v = ffma2(win[cx][ky][0], splat2(sky[ky]), v);
+                        } else {
+#pragma unroll
+                            for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+                                for (int kx = 0; kx < 4; ++kx) v = ffma2(win[cx][ky][kx], splat2(sk[ky * 4 + kx]), v);
+                        }
+                        v = fadd2(fadd2(v, splat2(snz[py * BS_TW + px + cx])), bias);
+                        // lrelu(x)*sqrt2 = max(x*sqrt2, x*0.2*sqrt2)
+                        const float2 p = fmul2(v, splat2(1.41421356237309504880f)), q = fmul2(v, splat2(0.2f * 1.41421356237309504880f));
+                        v = make_float2(fmaxf(p.x, q.x), fmaxf(p.y, q.y));
+                        res[cx][py] = v;
+                        if (a.s_next && rowok && (cx ? colok1 : colok0)) {
+                            const float2 xs = fmul2(v, sn);
+                            const __nv_bfloat162 h = __floats2bfloat162_rn(xs.x, xs.y);
+                            const float2 hf = __bfloat1622float2(h);
+                            const __nv_bfloat162 l = __floats2bfloat162_rn(xs.x - hf.x, xs.y - hf.y);
+                            const int64_t off = off0 + py * row_stride + cx * a.C;
+                            *reinterpret_cast<__nv_bfloat162*>(a.next_hi + off) = h;
+                            *reinterpret_cast<__nv_bfloat162*>(a.next_lo + off) = l;
+                        }
+                    }
+                }
+            }
+        }
         __syncthreads();     // everyone is done reading the input tile
         float* sout = stile; // [64][129]
+        {
+            float* w0 = sout + (2 * lane) * BS_OPITCH + warp * 2;
 #pragma unroll
-        for (int cx = 0; cx < 2; ++cx)
+            for (int cx = 0; cx < 2; ++cx)
 #pragma unroll
-            for (int py = 0; py < BS_TH; ++py) {
-                const int p = py * BS_TW + warp * 2 + cx;
-                sout[(2 * lane) * BS_OPITCH + p] = res[cx][py].x;
-                sout[(2 * lane + 1) * BS_OPITCH + p] = res[cx][py].y;
-            }
+                for (int py = 0; py < BS_TH; ++py) {
+                    w0[py * BS_TW + cx] = res[cx][py].x;
+                    w0[BS_OPITCH + py * BS_TW + cx] = res[cx][py].y;
+                }
+        }
         __syncthreads();
-        // ---- NCHW capture: warp -> 8 channels, lanes -> 32 consecutive tile pixels (2 rows of 16)
-        for (int ci = warp; ci < BS_C; ci += 8) {
-            float* dst = a.out_f32 + ((int64_t)b * a.C + c0 + ci) * a.OH * a.OW;
+        // ---- NCHW capture: warp -> channels warp, warp+8, ...; lanes -> 2 rows x 16 pixels, 4 row pairs
+        {
+            const int ox = x0 + (lane & 15), oyb = y0 + (lane >> 4);
+            const bool colok = ox < a.OW;
+            const int64_t plane = (int64_t)a.OH * a.OW;
+            float* dst = a.out_f32 + ((int64_t)b * a.C + c0 + warp) * plane + (int64_t)oyb * a.OW + ox;
+            const float* sp = sout + warp * BS_OPITCH + lane;
 #pragma unroll
-            for (int p = lane; p < BS_TH * BS_TW; p += 32) {
-                const int oy = y0 + p / BS_TW, ox = x0 + p % BS_TW;
-                if (oy < a.OH && ox < a.OW) dst[(int64_t)oy * a.OW + ox] = sout[ci * BS_OPITCH + p];
+            for (int j = 0; j < BS_C / 8; ++j) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (colok && oyb + 2 * i < a.OH) dst[(int64_t)(2 * i) * a.OW] = sp[32 * i];
+                dst += 8 * plane;
+                sp += 8 * BS_OPITCH;
             }
         }
     }
