@@ -21,6 +21,7 @@
 // issuer + TMEM allocator, warps 2-5 = epilogue (TMEM lane quarter = warp_id % 4).
 #include <cuda.h>
 #include <cstring>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 #include "modconv_tc.h"
@@ -103,14 +104,17 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-// K-major, 128B-swizzled operand tile: 8-row atoms of 1024 B (SBO), LBO unused (=1), descriptor version 1.
+// K-major swizzled operand tile whose rows are ROW_BYTES (= swizzle width: 128 or 64) long: 8-row atoms of
+// 8*ROW_BYTES (SBO), LBO unused (=1), descriptor version 1, layout type SWIZZLE_128B (2) / SWIZZLE_64B (4).
+template <int ROW_BYTES>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+    static_assert(ROW_BYTES == 128 || ROW_BYTES == 64, "swizzle width");
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;                 // leading byte offset (16 B units), ignored for swizzled K-major
-    d |= (uint64_t)(1024 >> 4) << 32;       // stride byte offset between 8-row groups
-    d |= (uint64_t)1 << 46;                 // version = 1 (Blackwell)
-    d |= (uint64_t)2 << 61;                 // SWIZZLE_128B
+    d |= (uint64_t)1 << 16;                             // leading byte offset (16 B units), ignored for swizzled K-major
+    d |= (uint64_t)((8 * ROW_BYTES) >> 4) << 32;        // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                             // version = 1 (Blackwell)
+    d |= (uint64_t)(ROW_BYTES == 128 ? 2 : 4) << 61;
     return d;
 }
 
@@ -135,22 +139,31 @@ struct TcKernelArgs {
     unsigned int* error;
 };
 
-constexpr int BM = 128, BK = 64, UMMA_K = 16;
-constexpr int A_TILE_BYTES = BM * BK * 2;   // 16 KB
+constexpr int BM = 128, UMMA_K = 16;
 constexpr int TC_THREADS = 192;
 
-template <int BN> struct TcCfg {
-    static constexpr int B_TILE_BYTES = BN * BK * 2;
+// BK = K elements per pipeline stage = one swizzle row (64 -> 128 B rows, 32 -> 64 B rows; measured: the 64 B rows
+// are slower, the L2 -> SM path is request-bound).  CG = tcgen05 cta_group: with CG = 2 a CTA pair computes a
+// 256 x BN tile: each CTA stages its own 128 pixel rows of A but only HALF of the weight tile (BN/2 rows), and the
+// pair's MMA (M = 256, issued by the even CTA) reads B from both CTAs' shared memory.  That cuts the L2 -> SM bytes
+// per MMA by a third (BN = 256: 96 -> 64 KB per K-step), which is what bounds the 1-CTA kernel (~40 B/clk/SM).
+template <int BN, int BK, int CG> struct TcCfg {
+    static constexpr int A_TILE_BYTES = BM * BK * 2;
+    static constexpr int B_ROWS = BN / CG;                       // weight rows staged by this CTA
+    static constexpr int B_TILE_BYTES = B_ROWS * BK * 2;
     static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-    static constexpr int STAGES = (220 * 1024) / STAGE_BYTES > 6 ? 6 : (220 * 1024) / STAGE_BYTES;
+    static constexpr int STAGES = (216 * 1024) / STAGE_BYTES > 8 ? 8 : (216 * 1024) / STAGE_BYTES;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
-struct TileCoord { int sub, b0, y0, x0, n0; };
+struct TileCoord { int sub, b0, y0, x0, n0; bool dummy; };
 
-template <int BN, int TH, int TW, int TB>
-__device__ __forceinline__ TileCoord decode_tile(const TcKernelArgs& a, int t) {
+// Tile t of this CTA.  CG = 1: t is a tile index.  CG = 2: t is a PAIR index and `rank` selects the m-tile of the pair
+// (2*mp + rank); an odd m-tile count leaves rank 1 of the last pair with a dummy tile (it recomputes rank 0's tile and
+// stores nothing).
+template <int BN, int TH, int TW, int TB, int CG>
+__device__ __forceinline__ TileCoord decode_tile(const TcKernelArgs& a, int t, int rank) {
     int p = 0;
 #pragma unroll
     for (int i = 1; i < 4; ++i)
@@ -158,8 +171,12 @@ __device__ __forceinline__ TileCoord decode_tile(const TcKernelArgs& a, int t) {
     const TcSubProblem& s = a.sub[p];
     const int local = t - s.tile_begin;
     const int m_tiles = a.b_tiles * s.tiles_y * s.tiles_x;
-    const int m = local % m_tiles, n = local / m_tiles;
+    const int m_units = (m_tiles + CG - 1) / CG;
+    int m = (local % m_units) * CG + rank;
+    const int n = local / m_units;
     TileCoord c;
+    c.dummy = m >= m_tiles;
+    if (c.dummy) m = m_tiles - 1;
     c.sub = p;
     c.x0 = (m % s.tiles_x) * TW;
     c.y0 = ((m / s.tiles_x) % s.tiles_y) * TH;
@@ -168,72 +185,149 @@ __device__ __forceinline__ TileCoord decode_tile(const TcKernelArgs& a, int t) {
     return c;
 }
 
-template <int BN, int TH, int TW, int TB>
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of the same shared-memory location in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-pair bit of a shared::cluster address -> even CTA
+
+template <int CG>
+__device__ __forceinline__ void tma_load_4d_cg(const void* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+    if (CG == 1) {
+        tma_load_4d(map, bar, dst, c0, c1, c2, c3);
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+            ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void tma_load_3d_cg(const void* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+    if (CG == 1) {
+        tma_load_3d(map, bar, dst, c0, c1, c2);
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+            ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2) : "memory");
+    }
+}
+template <int CG>
+__device__ __forceinline__ void umma_bf16_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (CG == 1) {
+        umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    }
+}
+// tcgen05.commit: arrive on `bar` when all previously issued MMAs retire; CG = 2 arrives on the barrier at the same
+// offset in BOTH CTAs of the pair.
+template <int CG>
+__device__ __forceinline__ void umma_commit_cg(uint64_t* bar) {
+    if (CG == 1) {
+        umma_commit(bar);
+    } else {
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+    }
+}
+
+template <int BN, int TH, int TW, int TB, int BK, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 modconv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                   const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                   const __grid_constant__ TcKernelArgs a) {
     static_assert(TH * TW * TB == BM, "tile box must hold 128 pixels");
-    using Cfg = TcCfg<BN>;
+    static_assert(CG == 1 || CG == 2, "cta_group");
+    using Cfg = TcCfg<BN, BK, CG>;
     constexpr int STAGES = Cfg::STAGES;
+    constexpr int A_TILE_BYTES = Cfg::A_TILE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + STAGES * Cfg::STAGE_BYTES);
-    uint64_t* full_bar = bars;                 // [STAGES]
+    uint64_t* full_bar = bars;                 // [STAGES]  (CG = 2: only the even CTA's are used)
     uint64_t* empty_bar = bars + STAGES;       // [STAGES]
     uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]
-    uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+    uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]       (CG = 2: only the even CTA's are used)
     uint32_t* tmem_ptr_smem = (uint32_t*)(bars + 2 * STAGES + 4);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
+    const bool leader = rank == 0;
+    const int unit0 = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // first tile (pair) of this CTA
+    const int unit_stride = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
         tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4 * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == 0) {
-        // ============================== TMA producer ==============================
+        // ============================== TMA producer (both CTAs of a pair) ==============================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-                const TileCoord c = decode_tile<BN, TH, TW, TB>(a, t);
+            for (int t = unit0; t < a.total_tiles; t += unit_stride) {
+                const TileCoord c = decode_tile<BN, TH, TW, TB, CG>(a, t, rank);
                 const TcSubProblem& s = a.sub[c.sub];
+                const int wrow = c.n0 + rank * Cfg::B_ROWS;
                 for (int tap = 0; tap < s.ntaps; ++tap) {
                     const int ax = c.x0 + s.dx[tap], ay = c.y0 + s.dy[tap], wi = s.widx[tap];
                     for (int kc = 0; kc < a.kchunks; ++kc) {
                         mbar_wait(&empty_bar[stage], phase ^ 1, a.error, 0x100 + stage);
                         uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
-                        mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                        tma_load_4d(&map_a_hi, &full_bar[stage], st, kc * BK, ax, ay, c.b0);
-                        tma_load_4d(&map_a_lo, &full_bar[stage], st + A_TILE_BYTES, kc * BK, ax, ay, c.b0);
-                        tma_load_3d(&map_w_hi, &full_bar[stage], st + 2 * A_TILE_BYTES, kc * BK, c.n0, wi);
-                        tma_load_3d(&map_w_lo, &full_bar[stage], st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES, kc * BK, c.n0, wi);
+                        // one arming per stage: the even CTA expects the bytes of BOTH CTAs on its barrier
+                        if (leader) mbar_expect_tx(&full_bar[stage], CG * Cfg::STAGE_BYTES);
+                        tma_load_4d_cg<CG>(&map_a_hi, &full_bar[stage], st, kc * BK, ax, ay, c.b0);
+                        tma_load_4d_cg<CG>(&map_a_lo, &full_bar[stage], st + A_TILE_BYTES, kc * BK, ax, ay, c.b0);
+                        tma_load_3d_cg<CG>(&map_w_hi, &full_bar[stage], st + 2 * A_TILE_BYTES, kc * BK, wrow, wi);
+                        tma_load_3d_cg<CG>(&map_w_lo, &full_bar[stage], st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES, kc * BK, wrow, wi);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ============================== MMA issuer ==============================
-        if (lane == 0) {
-            // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128
-            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        // ============================== MMA issuer (even CTA of a pair only) ==============================
+        if (lane == 0 && leader) {
+            // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128*CG
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
-            for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-                const TileCoord c = decode_tile<BN, TH, TW, TB>(a, t);
+            for (int t = unit0; t < a.total_tiles; t += unit_stride) {
+                const TileCoord c = decode_tile<BN, TH, TW, TB, CG>(a, t, 0);
                 const int kblocks = a.sub[c.sub].ntaps * a.kchunks;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1, a.error, 0x200 + acc);
                 tc_fence_after();
@@ -242,20 +336,20 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                     mbar_wait(&full_bar[stage], phase, a.error, 0x300 + stage);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::STAGE_BYTES);
-                    const uint64_t d_ah = make_smem_desc(sa), d_al = make_smem_desc(sa + A_TILE_BYTES);
-                    const uint64_t d_bh = make_smem_desc(sa + 2 * A_TILE_BYTES);
-                    const uint64_t d_bl = make_smem_desc(sa + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES);
+                    const uint64_t d_ah = make_smem_desc<BK * 2>(sa), d_al = make_smem_desc<BK * 2>(sa + A_TILE_BYTES);
+                    const uint64_t d_bh = make_smem_desc<BK * 2>(sa + 2 * A_TILE_BYTES);
+                    const uint64_t d_bl = make_smem_desc<BK * 2>(sa + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES);
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B per K step inside the swizzle row
-                        umma_bf16(d_tmem, d_ah + koff, d_bh + koff, idesc, (kb | k) ? 1u : 0u);
-                        umma_bf16(d_tmem, d_ah + koff, d_bl + koff, idesc, 1u);
-                        umma_bf16(d_tmem, d_al + koff, d_bh + koff, idesc, 1u);
+                        umma_bf16_cg<CG>(d_tmem, d_ah + koff, d_bh + koff, idesc, (kb | k) ? 1u : 0u);
+                        umma_bf16_cg<CG>(d_tmem, d_ah + koff, d_bl + koff, idesc, 1u);
+                        umma_bf16_cg<CG>(d_tmem, d_al + koff, d_bh + koff, idesc, 1u);
                     }
-                    umma_commit(&empty_bar[stage]);     // frees this smem stage when the MMAs above retire
+                    umma_commit_cg<CG>(&empty_bar[stage]);     // frees this smem stage (in both CTAs) when the MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);           // accumulator complete -> epilogue
+                umma_commit_cg<CG>(&tfull_bar[acc]);           // accumulator complete -> epilogue (both CTAs)
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -264,12 +358,13 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
         const int row = quarter * 32 + lane;            // GEMM row = pixel of the tile box
         const int tw = row % TW, th = (row / TW) % TH, tb = row / (TW * TH);
+        const uint32_t tempty_leader = (CG == 2) ? map_to_cta(smem_u32(&tempty_bar[0]), 0) : 0u;
         int acc = 0; uint32_t acc_phase = 0;
-        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-            const TileCoord c = decode_tile<BN, TH, TW, TB>(a, t);
+        for (int t = unit0; t < a.total_tiles; t += unit_stride) {
+            const TileCoord c = decode_tile<BN, TH, TW, TB, CG>(a, t, rank);
             const TcSubProblem& s = a.sub[c.sub];
             const int b = c.b0 + tb, yy = c.y0 + th, xx = c.x0 + tw;
-            const bool valid = b < a.batch && yy < s.oh && xx < s.ow;
+            const bool valid = !c.dummy && b < a.batch && yy < s.oh && xx < s.ow;
             const int oy = yy * s.ostride + s.ooff_y, ox = xx * s.ostride + s.ooff_x;
             mbar_wait(&tfull_bar[acc], acc_phase, a.error, 0x400 + acc);
             tc_fence_after();
@@ -331,16 +426,22 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                if (CG == 1) mbar_arrive(&tempty_bar[acc]);
+                else mbar_arrive_cluster(tempty_leader + (uint32_t)(acc * 8));   // the even CTA's MMA thread waits on it
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();   // CG = 2: the peer may still read this CTA's smem / TMEM
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        if (CG == 1)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
     }
 }
 
@@ -577,7 +678,7 @@ static PFN_encodeTiled get_encode_fn() {
     return fn;
 }
 
-static int make_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint32_t* box) {
+static int make_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint32_t* box, int swizzle_bytes) {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return SIS_ERR_CUDA; }
     cuuint64_t gdim[5]; cuuint64_t gstride[4]; cuuint32_t bdim[5]; cuuint32_t estr[5];
@@ -588,7 +689,8 @@ static int make_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims
         if (i < rank - 1) gstride[i] = stride;    // byte stride of dimension i+1
     }
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, gdim, gstride, bdim, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r, rank); return SIS_ERR_CUDA; }
     return SIS_OK;
@@ -674,32 +776,57 @@ int tc_prescale_split(TcWorkspace& ws, int slot, const float* x, const float* s,
     return SIS_OK;
 }
 
-template <int BN, int TH, int TW, int TB>
+template <int BN, int TH, int TW, int TB, int BK, int CG>
 static int launch_tc(const CUtensorMap maps[4], const TcKernelArgs& a, cudaStream_t stream) {
-    using Cfg = TcCfg<BN>;
-    auto kern = modconv_tc_kernel<BN, TH, TW, TB>;
+    using Cfg = TcCfg<BN, BK, CG>;
+    auto kern = modconv_tc_kernel<BN, TH, TW, TB, BK, CG>;
     static bool configured = false;
     if (!configured) {
         SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
-    const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
-    kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, stream>>>(maps[0], maps[1], maps[2], maps[3], a);
+    // persistent: one CTA (CG = 1) or one CTA pair (CG = 2) per SM (pair); a.total_tiles counts tiles resp. pair tiles
+    int grid = a.total_tiles * CG < kNumSMs ? a.total_tiles * CG : kNumSMs;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    SIS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], a));
     SIS_CHECK_LAUNCH();
     return SIS_OK;
 }
 
-template <int BN>
+template <int BN, int BK, int CG>
 static int launch_tc_bn(int th, int tw, int tb, const CUtensorMap maps[4], const TcKernelArgs& a, cudaStream_t stream) {
-    if (th == 4 && tw == 4 && tb == 8) return launch_tc<BN, 4, 4, 8>(maps, a, stream);
-    if (th == 8 && tw == 8 && tb == 2) return launch_tc<BN, 8, 8, 2>(maps, a, stream);
-    if (th == 8 && tw == 16 && tb == 1) return launch_tc<BN, 8, 16, 1>(maps, a, stream);
+    if (th == 4 && tw == 4 && tb == 8) return launch_tc<BN, 4, 4, 8, BK, CG>(maps, a, stream);
+    if (th == 8 && tw == 8 && tb == 2) return launch_tc<BN, 8, 8, 2, BK, CG>(maps, a, stream);
+    if (th == 8 && tw == 16 && tb == 1) return launch_tc<BN, 8, 16, 1, BK, CG>(maps, a, stream);
     set_error("tc_modconv: unsupported tile box %dx%dx%d", th, tw, tb);
     return SIS_ERR_UNSUPPORTED;
 }
 
+template <int BK, int CG>
+static int launch_tc_any(int BN, int th, int tw, int tb, const CUtensorMap maps[4], const TcKernelArgs& a, cudaStream_t stream) {
+    if (BN == 256) return launch_tc_bn<256, BK, CG>(th, tw, tb, maps, a, stream);
+    if (BN == 128) return launch_tc_bn<128, BK, CG>(th, tw, tb, maps, a, stream);
+    if (BN == 64) return launch_tc_bn<64, BK, CG>(th, tw, tb, maps, a, stream);
+    return launch_tc_bn<32, BK, CG>(th, tw, tb, maps, a, stream);
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, cudaStream_t stream) {
-    SIS_REQUIRE(call.cin % BK == 0, "tc_modconv: Cin must be a multiple of 64 (got %d)", call.cin);
+    // Tunables for A/B runs: SIS_TC_BK (64 default | 32: stage depth along K), SIS_TC_CG (2 default | 1: CTA pairs)
+    static int bk_env = 0, cg_env = 0;
+    if (!bk_env) { bk_env = env_int("SIS_TC_BK", 64) == 32 ? 32 : 64; cg_env = env_int("SIS_TC_CG", 2) == 1 ? 1 : 2; }
+    const int BK = (call.cin % 64 == 0) ? bk_env : 32;
+    SIS_REQUIRE(call.cin % BK == 0, "tc_modconv: Cin must be a multiple of 32 (got %d)", call.cin);
     SIS_REQUIRE(call.cout % 32 == 0, "tc_modconv: Cout must be a multiple of 32 (got %d)", call.cout);
     SIS_REQUIRE(w.hi && w.cin == call.cin && w.cout == call.cout, "tc_modconv: weights not packed for this layer");
     const int B = call.batch, H = call.res_in;
@@ -711,14 +838,19 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
     if (ext <= 4) { th = 4; tw = 4; tb = 8; }
     else if (ext <= 8) { th = 8; tw = 8; tb = 2; }
     else { th = 8; tw = 16; tb = 1; }
+    const int b_tiles = ceil_div(B, tb), n_tiles = call.cout / BN;
+    // CTA pairs only when there is at least one full wave of pair tiles and each CTA's weight half is a legal UMMA N
+    const int64_t plain_m_tiles = (int64_t)b_tiles * ceil_div(ext, th) * ceil_div(ext, tw);
+    const int CG = (cg_env == 2 && BN >= 64 && plain_m_tiles * n_tiles >= 2 * kNumSMs) ? 2 : 1;
 
     TcKernelArgs a;
     memset(&a, 0, sizeof(a));
     a.batch = B; a.cin = call.cin; a.cout = call.cout; a.kchunks = call.cin / BK;
-    a.b_tiles = ceil_div(B, tb); a.n_tiles = call.cout / BN;
+    a.b_tiles = b_tiles; a.n_tiles = n_tiles;
     a.demod = call.demod; a.noise = call.noise; a.noise_bstride = call.noise_bstride; a.noise_w = call.noise_w; a.bias = call.bias;
     a.error = ws.d_error;
-    int tiles = 0;
+    int tiles = 0;   // tiles (CG = 1) or pair tiles (CG = 2)
+    auto units = [&](const TcSubProblem& s) { return ceil_div(a.b_tiles * s.tiles_y * s.tiles_x, CG) * a.n_tiles; };
     if (!call.up) {
         a.mode = 0; a.nsub = 1;
         TcSubProblem& s = a.sub[0];
@@ -727,7 +859,7 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
             for (int kx = 0; kx < 3; ++kx) { int t = ky * 3 + kx; s.dy[t] = (signed char)(ky - 1); s.dx[t] = (signed char)(kx - 1); s.widx[t] = (signed char)t; }
         s.oh = H; s.ow = H; s.ostride = 1; s.ooff_y = 0; s.ooff_x = 0;
         s.tiles_y = ceil_div(H, th); s.tiles_x = ceil_div(H, tw); s.tile_begin = 0;
-        tiles = a.b_tiles * s.tiles_y * s.tiles_x * a.n_tiles;
+        tiles = units(s);
         a.out_f32 = call.out_f32; a.out_h = H; a.out_w = H;
         a.s_next = call.s_next; a.next_hi = (bf16*)ws.a_hi[call.out_slot]; a.next_lo = (bf16*)ws.a_lo[call.out_slot];
     } else {
@@ -747,7 +879,7 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
                 s.ostride = 2; s.ooff_y = py; s.ooff_x = px;
                 s.tiles_y = ceil_div(s.oh, th); s.tiles_x = ceil_div(s.ow, tw);
                 s.tile_begin = tiles;
-                tiles += a.b_tiles * s.tiles_y * s.tiles_x * a.n_tiles;
+                tiles += units(s);
             }
         a.out_f32 = call.upconv_tmp; a.out_h = 2 * H + 1; a.out_w = 2 * H + 1;
     }
@@ -757,20 +889,18 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
     {
         const uint64_t adims[4] = {(uint64_t)call.cin, (uint64_t)H, (uint64_t)H, (uint64_t)B};
         const uint32_t abox[4] = {(uint32_t)BK, (uint32_t)tw, (uint32_t)th, (uint32_t)tb};
-        SIS_PROPAGATE(make_map(&maps[0], ws.a_hi[call.in_slot], 4, adims, abox));
-        SIS_PROPAGATE(make_map(&maps[1], ws.a_lo[call.in_slot], 4, adims, abox));
+        SIS_PROPAGATE(make_map(&maps[0], ws.a_hi[call.in_slot], 4, adims, abox, BK * 2));
+        SIS_PROPAGATE(make_map(&maps[1], ws.a_lo[call.in_slot], 4, adims, abox, BK * 2));
         const uint64_t wdims[3] = {(uint64_t)call.cin, (uint64_t)call.cout, 9};
-        const uint32_t wbox[3] = {(uint32_t)BK, (uint32_t)BN, 1};
-        SIS_PROPAGATE(make_map(&maps[2], w.hi, 3, wdims, wbox));
-        SIS_PROPAGATE(make_map(&maps[3], w.lo, 3, wdims, wbox));
+        const uint32_t wbox[3] = {(uint32_t)BK, (uint32_t)(BN / CG), 1};     // CG = 2: each CTA stages half the rows
+        SIS_PROPAGATE(make_map(&maps[2], w.hi, 3, wdims, wbox, BK * 2));
+        SIS_PROPAGATE(make_map(&maps[3], w.lo, 3, wdims, wbox, BK * 2));
     }
     int st;
     {
         ProfScope prof(PROF_CONV_TC, stream);
-        if (BN == 256) st = launch_tc_bn<256>(th, tw, tb, maps, a, stream);
-        else if (BN == 128) st = launch_tc_bn<128>(th, tw, tb, maps, a, stream);
-        else if (BN == 64) st = launch_tc_bn<64>(th, tw, tb, maps, a, stream);
-        else st = launch_tc_bn<32>(th, tw, tb, maps, a, stream);
+        if (CG == 2) st = (BK == 64) ? launch_tc_any<64, 2>(BN, th, tw, tb, maps, a, stream) : launch_tc_any<32, 2>(BN, th, tw, tb, maps, a, stream);
+        else st = (BK == 64) ? launch_tc_any<64, 1>(BN, th, tw, tb, maps, a, stream) : launch_tc_any<32, 1>(BN, th, tw, tb, maps, a, stream);
     }
     SIS_PROPAGATE(st);
 
