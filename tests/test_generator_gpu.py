@@ -129,3 +129,73 @@ def test_generator_api_surface(cuda_device):
         g.to_rgbs[1].bias.add_(0.5)
         after, _ = g([z], randomize_noise=False)
     torch.testing.assert_close(after, before + 0.5, rtol=0, atol=1e-5)
+
+
+def _labels_agree(acts, want_acts, layers, k=4, seed=5):
+    """north-star label criterion on the given layers with seeded unit-norm centroids."""
+    from oracle import labelling_oracle as lo
+    from synthesis_in_style_b200 import labelling
+    g = torch.Generator().manual_seed(seed)
+    total = agree = 0
+    for layer in layers:
+        c = want_acts[layer].shape[1]
+        cent = torch.nn.functional.normalize(torch.randn(k, c, generator=g), dim=1)
+        want, margin = lo.predict_with_margin(want_acts[layer], cent)
+        got = labelling.FactorCatalog(k, cent).predict(acts[layer]).cpu()
+        safe = margin > 1e-3
+        assert torch.equal(got[safe], want[safe]), (layer, int((got[safe] != want[safe]).sum()))
+        total += want.numel(); agree += int((got == want).sum())
+    assert agree / total >= 0.999
+
+
+def test_generator_512_config3(cuda_device):
+    """BASELINE config 3 (512^2 config-f, multi-layer capture of the 64..512 px maps) at batch 2 against the oracle."""
+    spec = so.GeneratorSpec(512, 512, 8, 2)
+    sd = so.perturb_zero_params(so.init_state_dict(spec, seed=0), seed=1234)
+    g = Generator(512, 512, 8)
+    g.load_state_dict(sd)
+    g = g.to(cuda_device).eval()
+    torch.manual_seed(1)
+    z = torch.randn(2, 512)
+    noise = so.make_noise(spec)
+    want_img, want_acts = so.generator_forward(sd, spec, [z], noise=noise, return_intermediate_activations=True)
+    layers = list(range(8, 16))
+    with torch.no_grad():
+        img, acts = g([z.to(cuda_device)], noise=[n.to(cuda_device) for n in noise], return_intermediate_activations=True,
+                      capture_layers=[0] + layers)
+    assert sorted(acts) == [0] + layers
+    assert float((img.cpu() - want_img).abs().max()) <= IMG_ATOL
+    assert psnr(img.cpu().clamp(-1, 1), want_img.clamp(-1, 1)) >= 40.0
+    for k in layers:
+        e = float((acts[k].cpu() - want_acts[k]).abs().max())
+        assert e <= TIGHT['bf16x3'] * max(1.0, float(want_acts[k].abs().max())), (k, e)
+    _labels_agree(acts, want_acts, [8, 9, 14, 15])
+
+
+def test_generator_1024_config4(cuda_device):
+    """BASELINE config 4 (1024^2, truncation 0.7 with an injected mean latent, style mixing with an explicit
+    inject_index) at batch 1 against the oracle."""
+    spec = so.GeneratorSpec(1024, 512, 8, 2)
+    sd = so.perturb_zero_params(so.init_state_dict(spec, seed=0), seed=1234)
+    g = Generator(1024, 512, 8)
+    g.load_state_dict(sd)
+    g = g.to(cuda_device).eval()
+    torch.manual_seed(7)
+    ml = so.mean_latent(sd, spec, 256)
+    torch.manual_seed(1)
+    za, zb = torch.randn(1, 512), torch.randn(1, 512)
+    noise = so.make_noise(spec)
+    kw = dict(truncation=0.7, inject_index=6, return_intermediate_activations=True)
+    want_img, want_acts = so.generator_forward(sd, spec, [za, zb], noise=noise, truncation_latent=ml, **kw)
+    with torch.no_grad():
+        torch.manual_seed(7)
+        ml_gpu = g.mean_latent(256)       # same CPU->device semantics are NOT guaranteed (device RNG); compare loosely
+        img, acts = g([za.to(cuda_device), zb.to(cuda_device)], noise=[n.to(cuda_device) for n in noise],
+                      truncation_latent=ml.to(cuda_device), capture_layers=[0, 16, 17], **kw)
+    assert ml_gpu.shape == (1, 512) and torch.isfinite(ml_gpu).all()
+    assert float((img.cpu() - want_img).abs().max()) <= IMG_ATOL
+    assert psnr(img.cpu().clamp(-1, 1), want_img.clamp(-1, 1)) >= 40.0
+    for k in (16, 17):
+        e = float((acts[k].cpu() - want_acts[k]).abs().max())
+        assert e <= TIGHT['bf16x3'] * max(1.0, float(want_acts[k].abs().max())), (k, e)
+    _labels_agree(acts, want_acts, [16, 17])
