@@ -141,7 +141,7 @@ def make_config(world, B):
             'l2': 'per-step working set (>= 3.9 GB of captured activations) exceeds the 126 MB L2; no explicit flush'}
 
 
-def run_reference(args, rank, world):
+def run_reference(args, rank, world, out):
     """Reference arm: the oracle port on the host cores (rank 0 only)."""
     if rank != 0:
         return
@@ -156,10 +156,20 @@ def run_reference(args, rank, world):
             'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=out, flush=True)
+
+
+def claim_stdout():
+    """Native libraries (NCCL's version banner, ...) write to fd 1; the contract is ONE JSON line on stdout.  Keep a
+    private handle on the real stdout for that line and point fd 1 at stderr for everything else."""
+    real = os.fdopen(os.dup(1), 'w')
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return real
 
 
 def main():
+    out = claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
@@ -176,7 +186,7 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.impl == 'reference':
-        run_reference(args, rank, world)
+        run_reference(args, rank, world, out)
         return
 
     import torch.distributed as dist
@@ -243,30 +253,21 @@ def main():
     value = world * args.steps * B / (ms_total / 1e3)
 
     # ---------------------------------------------------------------- e2e: host buffers in and out
-    h_z = torch.empty(B, STYLE_DIM).pin_memory()
-    h_img = torch.empty(B, 3, SIZE, SIZE).pin_memory()
+    # Public API: LabelledPairGenerator.iter_host — pinned-host latents in, device noise as the reference draws it,
+    # fp32 image + 4 x [3, B, S, S] uint8 mask stacks out to pinned host memory every step (copies on a side stream).
     n_cls = len(COLORS)
-    h_masks = {k: torch.empty(n_cls, B, SIZE, SIZE, dtype=torch.uint8).pin_memory() for k in LABEL_LAYERS}
-    h2d = h_z.numel() * 4
-    d2h = h_img.numel() * 4 + sum(m.numel() for m in h_masks.values())
-    host_rng = torch.Generator().manual_seed(1 + rank)
-
-    def step_e2e():
-        h_z.copy_(torch.randn(B, STYLE_DIM, generator=host_rng))
-        lat = dc.Latents(h_z.to(dev, non_blocking=True), g.make_noise())
-        acts, img = dc.generate_images(lat, g, device=dev)
-        masks = seg.prepare_image_segmentation(acts)
-        h_img.copy_(img, non_blocking=True)
-        for k in LABEL_LAYERS:
-            stacked = torch.stack([masks[k][c] for c in COLORS]).view(torch.uint8)
-            h_masks[k].copy_(stacked, non_blocking=True)
-
-    for _ in range(2):
-        step_e2e()
+    h2d = B * STYLE_DIM * 4
+    d2h = B * 3 * SIZE * SIZE * 4 + len(LABEL_LAYERS) * n_cls * B * SIZE * SIZE
+    pipe = dc.LabelledPairGenerator(g, seg, cfg, seed=1, rank=rank, world_size=world)
+    host_iter = pipe.iter_host(depth=2)
+    for _ in range(3):
+        next(host_iter)
     barrier()
+    checksum = 0
     e0.record()
     for _ in range(args.steps):
-        step_e2e()
+        hb = next(host_iter)
+        checksum += int(hb.masks['13'][1, 0, 0, 0])      # touch the host result of every step
     e1.record()
     barrier()
     ms2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -341,7 +342,7 @@ def main():
                         'ms_per_step': float(ms2.item()) / args.steps},
                 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'kernels': kernels, 'cpu_baseline': cpu,
                 'stats_allreduce_sum': int(stats.sum().item())}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

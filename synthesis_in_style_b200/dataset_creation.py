@@ -100,6 +100,14 @@ class LabelledBatch:
     activations: Dict[int, torch.Tensor]
 
 
+@dataclass
+class HostBatch:
+    batch_index: int
+    image: torch.Tensor                      # pinned host [B, 3, S, S] fp32
+    masks: Dict[str, torch.Tensor]           # pinned host {layer: uint8 [n_class, B, S, S]}
+    class_names: Dict[str, List[str]]        # {layer: class name of each mask plane}
+
+
 class LabelledPairGenerator:
     """GPU part of `build_dataset`'s loop: generate -> label, per batch, for this rank's shard."""
 
@@ -124,6 +132,54 @@ class LabelledPairGenerator:
             self.stats['pairs'] += image.shape[0]
             self.stats['batches'] += 1
             yield LabelledBatch(idx, image, masks, acts)
+
+    def iter_host(self, depth: int = 2) -> Iterator['HostBatch']:
+        """The same loop with HOST buffers on both sides, as `build_dataset` needs them (its next steps are CPU code):
+        latents are staged in pinned memory and copied in, the fp32 image and the per-layer uint8 mask stacks are
+        copied out to pinned memory on a side stream, with `depth` batches in flight so the copies overlap the next
+        batch's kernels.  A yielded HostBatch stays valid until the next one is requested."""
+        if self.segmenter.keys_to_merge:
+            raise NotImplementedError('iter_host does not merge layers; use __iter__ for keys_to_merge configs')
+        device = self.generator.input.input.device
+        g, seg = self.generator, self.segmenter
+        B, S = self.config['batch_size'], g.size
+        copy_stream = torch.cuda.Stream(device=device)
+        slots = [{'z': torch.empty(B, self.config['latent_size']).pin_memory(), 'image': torch.empty(B, 3, S, S).pin_memory(),
+                  'masks': {}} for _ in range(depth + 1)]
+        in_flight = []
+
+        def finish(slot):
+            slot['done'].synchronize()
+            slot['keep'] = None
+            return HostBatch(slot['index'], slot['image'], dict(slot['masks']), slot['names'])
+
+        n = 0
+        for idx, latents in sharded_latent_stream(g, self.config, self.seed, self.rank, self.world_size):
+            slot = slots[n % (depth + 1)]
+            slot['z'].copy_(latents.latent)
+            lat = Latents(slot['z'].to(device, non_blocking=True), latents.noise)
+            acts, image = generate_images(lat, g, device=device, mean_latent=self.mean_latent, capture_layers=self.capture_layers)
+            stacked = seg.label_layers_stacked(acts)
+            ready = torch.cuda.Event()
+            ready.record(torch.cuda.current_stream(device))
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ready)
+                slot['image'].copy_(image, non_blocking=True)
+                for layer, (names, m) in stacked.items():
+                    if layer not in slot['masks']:
+                        slot['masks'][layer] = torch.empty(m.shape, dtype=torch.uint8).pin_memory()
+                    slot['masks'][layer].copy_(m, non_blocking=True)
+                slot['done'] = torch.cuda.Event()
+                slot['done'].record(copy_stream)
+            # the device tensors must outlive the asynchronous copies
+            slot['keep'], slot['index'] = (image, stacked, lat), idx
+            slot['names'] = {layer: names for layer, (names, _) in stacked.items()}
+            in_flight.append(slot)
+            self.stats['pairs'] += B
+            self.stats['batches'] += 1
+            n += 1
+            if len(in_flight) >= depth:
+                yield finish(in_flight.pop(0))
 
     def stats_vector(self) -> torch.Tensor:
         """int64 [sum_k cluster pixel counts per labelled layer | pairs | batches] on the generator's device."""

@@ -277,25 +277,31 @@ class ClusterSegmenter(BaseDatasetSegmenter):
             self.cluster_pixel_counts[layer_id] = hist
         _, out = label_assign(act, cat.centroids_on(act.device), class_bits=bits, n_class=len(names),
                               image_size=image_size, hist=hist)
-        masks = out['masks'].view(torch.bool)
-        return {n: masks[j] for j, n in enumerate(names)}
+        return names, out['masks']
 
-    def predict_clusters(self, activations: Dict[int, torch.Tensor], class_label_map) -> PredictedClusters:
-        """Per layer: cluster ids -> per-class bool masks at the layer's native resolution (…segmenter.py:119-138)."""
-        acts = {str(k): v for k, v in activations.items()}
-        return {layer_id: self._label_layer(layer_id, acts[layer_id], class_label_map, acts[layer_id].shape[-1])
-                for layer_id in self.catalog}
-
-    def prepare_image_segmentation(self, activations, class_label_map=None) -> PredictedClusters:
-        """predict_clusters + resize_to_image_size fused: one launch per layer writes the S x S masks directly."""
+    def label_layers_stacked(self, activations, class_label_map=None, native: bool = False):
+        """{layer: (class names, uint8 [n_class, B, S, S])}: the kernel's own output layout, one tensor per layer
+        (what `LabelledPairGenerator.iter_host` copies to pinned memory in one transfer)."""
         class_label_map = class_label_map if class_label_map is not None else self.class_label_map
         acts = {str(k): v for k, v in activations.items()}
         out = {}
         for layer_id in self.catalog:
             a = acts[layer_id]
-            size = self.image_size if a.shape[-1] < self.image_size else a.shape[-1]
+            size = a.shape[-1] if (native or a.shape[-1] >= self.image_size) else self.image_size
             out[layer_id] = self._label_layer(layer_id, a, class_label_map, size)
         return out
+
+    @staticmethod
+    def _as_predicted(stacked) -> PredictedClusters:
+        return {layer: {n: masks.view(torch.bool)[j] for j, n in enumerate(names)} for layer, (names, masks) in stacked.items()}
+
+    def predict_clusters(self, activations: Dict[int, torch.Tensor], class_label_map) -> PredictedClusters:
+        """Per layer: cluster ids -> per-class bool masks at the layer's native resolution (…segmenter.py:119-138)."""
+        return self._as_predicted(self.label_layers_stacked(activations, class_label_map, native=True))
+
+    def prepare_image_segmentation(self, activations, class_label_map=None) -> PredictedClusters:
+        """predict_clusters + resize_to_image_size fused: one launch per layer writes the S x S masks directly."""
+        return self._as_predicted(self.label_layers_stacked(activations, class_label_map))
 
     def merge_sub_images(self, predicted_clusters: PredictedClusters) -> PredictedClusters:
         """OR the class masks of several layers into a destination key (black_white…segmenter.py:31-40)."""

@@ -108,3 +108,20 @@ def test_full_size_properties(cuda_device):
     torch.testing.assert_close(img1[0], a.image[5], rtol=0, atol=1e-4)
     counts = seg.cluster_pixel_counts
     assert all(int(counts[l].sum()) % (32 * a.activations[int(l)].shape[-1] ** 2) == 0 for l in layers)
+
+
+def test_iter_host_equals_device_iteration(cuda_device):
+    """The pipelined host-buffer iterator (pinned in/out, side-stream copies) returns the same pairs in order."""
+    layers = ['4', '5', '6', '7']
+    spec, sd, g, seg, cents = make_setup(32, layers, cuda_device)
+    cfg = {'batch_size': 3, 'latent_size': 512}
+    ref = [b for _, b in zip(range(5), dc.LabelledPairGenerator(g, seg, cfg, seed=1))]
+    host = dc.LabelledPairGenerator(g, seg, cfg, seed=1).iter_host(depth=2)
+    for i in range(5):
+        hb = next(host)
+        assert hb.batch_index == ref[i].batch_index == i
+        assert hb.image.is_pinned() and torch.equal(hb.image, ref[i].image.cpu())
+        for layer in layers:
+            assert hb.class_names[layer] == list(NAMES)
+            for j, cn in enumerate(hb.class_names[layer]):
+                assert torch.equal(hb.masks[layer][j].bool(), ref[i].masks[layer][cn].cpu())
