@@ -124,8 +124,17 @@ struct TcSubProblem {
     signed char dy[9], dx[9], widx[9];
     int oh, ow;                 // extent of this sub-problem's output grid
     int ostride, ooff_y, ooff_x;
-    int tiles_y, tiles_x;
+    int tiles_y, tiles_x;       // tiled A mode: spatial tiles of the box
     int tile_begin;
+    int base_dy, base_dx;       // im2col A mode: smallest tap offset (the traversal box starts there); tap offset = d - base
+    int m_tiles;                // im2col A mode: ceil(B*oh*ow / 128) runs of 128 flattened pixels
+};
+
+// A-operand tensor maps: one (hi, lo) pair per sub-problem (the im2col maps of the 4 transposed-conv phases have
+// different traversal boxes; tiled mode uses pair 0 for everything) and the weight pack maps.
+struct TcMaps {
+    CUtensorMap a[4][2];
+    CUtensorMap w[2];
 };
 
 struct TcKernelArgs {
@@ -133,6 +142,7 @@ struct TcKernelArgs {
     int nsub, total_tiles;
     int batch, cin, cout, b_tiles, n_tiles, kchunks;
     int mode;                   // 0 plain (fused activation), 1 transposed-conv phase (demod only)
+    int im2col;                 // A tiles are 128 consecutive pixels of the flattened (b, y, x) output grid (TMA im2col mode)
     const float* demod; const float* noise; int64_t noise_bstride; float noise_w; const float* bias;
     float* out_f32; int out_h, out_w;
     const float* s_next; bf16* next_hi; bf16* next_lo;
@@ -157,7 +167,7 @@ template <int BN, int BK, int CG> struct TcCfg {
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
-struct TileCoord { int sub, b0, y0, x0, n0; bool dummy; };
+struct TileCoord { int sub, b0, y0, x0, n0; int p0; bool dummy; };
 
 // Tile t of this CTA.  CG = 1: t is a tile index.  CG = 2: t is a PAIR index and `rank` selects the m-tile of the pair
 // (2*mp + rank); an odd m-tile count leaves rank 1 of the last pair with a dummy tile (it recomputes rank 0's tile and
@@ -170,7 +180,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcKernelArgs& a, int t, i
         if (i < a.nsub && t >= a.sub[i].tile_begin) p = i;
     const TcSubProblem& s = a.sub[p];
     const int local = t - s.tile_begin;
-    const int m_tiles = a.b_tiles * s.tiles_y * s.tiles_x;
+    const int m_tiles = a.im2col ? s.m_tiles : a.b_tiles * s.tiles_y * s.tiles_x;
     const int m_units = (m_tiles + CG - 1) / CG;
     int m = (local % m_units) * CG + rank;
     const int n = local / m_units;
@@ -178,9 +188,17 @@ __device__ __forceinline__ TileCoord decode_tile(const TcKernelArgs& a, int t, i
     c.dummy = m >= m_tiles;
     if (c.dummy) m = m_tiles - 1;
     c.sub = p;
-    c.x0 = (m % s.tiles_x) * TW;
-    c.y0 = ((m / s.tiles_x) % s.tiles_y) * TH;
-    c.b0 = (m / (s.tiles_x * s.tiles_y)) * TB;
+    if (a.im2col) {
+        c.p0 = m * BM;                              // first flattened pixel of the run
+        c.x0 = c.p0 % s.ow;
+        c.y0 = (c.p0 / s.ow) % s.oh;
+        c.b0 = c.p0 / (s.ow * s.oh);
+    } else {
+        c.p0 = 0;
+        c.x0 = (m % s.tiles_x) * TW;
+        c.y0 = ((m / s.tiles_x) % s.tiles_y) * TH;
+        c.b0 = (m / (s.tiles_x * s.tiles_y)) * TB;
+    }
     c.n0 = n * BN;
     return c;
 }
@@ -213,6 +231,21 @@ __device__ __forceinline__ void tma_load_4d_cg(const void* map, uint64_t* bar, v
         asm volatile(
             "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
             ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+    }
+}
+// TMA im2col mode: 128 consecutive pixels (W fastest, then H, then N) of the traversal box starting at the base pixel
+// (c1, c2, c3), each shifted by the filter offset (off_w, off_h); pixels outside the tensor are zero-filled.
+template <int CG>
+__device__ __forceinline__ void tma_load_im2col_cg(const void* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3,
+                                                   unsigned short off_w, unsigned short off_h) {
+    if (CG == 1) {
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+            ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(off_w), "h"(off_h) : "memory");
+    } else {
+        asm volatile(
+            "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+            ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(off_w), "h"(off_h) : "memory");
     }
 }
 template <int CG>
@@ -251,9 +284,7 @@ __device__ __forceinline__ void umma_commit_cg(uint64_t* bar) {
 
 template <int BN, int TH, int TW, int TB, int BK, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-modconv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
-                  const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
-                  const __grid_constant__ TcKernelArgs a) {
+modconv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcKernelArgs a) {
     static_assert(TH * TW * TB == BM, "tile box must hold 128 pixels");
     static_assert(CG == 1 || CG == 2, "cta_group");
     using Cfg = TcCfg<BN, BK, CG>;
@@ -275,8 +306,8 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
     const int unit_stride = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&map_a_hi); tma_prefetch_desc(&map_a_lo);
-        tma_prefetch_desc(&map_w_hi); tma_prefetch_desc(&map_w_lo);
+        for (int i = 0; i < a.nsub; ++i) { tma_prefetch_desc(&maps.a[i][0]); tma_prefetch_desc(&maps.a[i][1]); }
+        tma_prefetch_desc(&maps.w[0]); tma_prefetch_desc(&maps.w[1]);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4 * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -303,17 +334,25 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
                 const TileCoord c = decode_tile<BN, TH, TW, TB, CG>(a, t, rank);
                 const TcSubProblem& s = a.sub[c.sub];
                 const int wrow = c.n0 + rank * Cfg::B_ROWS;
+                const CUtensorMap* ma_hi = &maps.a[a.im2col ? c.sub : 0][0];
+                const CUtensorMap* ma_lo = &maps.a[a.im2col ? c.sub : 0][1];
                 for (int tap = 0; tap < s.ntaps; ++tap) {
                     const int ax = c.x0 + s.dx[tap], ay = c.y0 + s.dy[tap], wi = s.widx[tap];
+                    const unsigned short ow_ = (unsigned short)(s.dx[tap] - s.base_dx), oh_ = (unsigned short)(s.dy[tap] - s.base_dy);
                     for (int kc = 0; kc < a.kchunks; ++kc) {
                         mbar_wait(&empty_bar[stage], phase ^ 1, a.error, 0x100 + stage);
                         uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
                         // one arming per stage: the even CTA expects the bytes of BOTH CTAs on its barrier
                         if (leader) mbar_expect_tx(&full_bar[stage], CG * Cfg::STAGE_BYTES);
-                        tma_load_4d_cg<CG>(&map_a_hi, &full_bar[stage], st, kc * BK, ax, ay, c.b0);
-                        tma_load_4d_cg<CG>(&map_a_lo, &full_bar[stage], st + A_TILE_BYTES, kc * BK, ax, ay, c.b0);
-                        tma_load_3d_cg<CG>(&map_w_hi, &full_bar[stage], st + 2 * A_TILE_BYTES, kc * BK, wrow, wi);
-                        tma_load_3d_cg<CG>(&map_w_lo, &full_bar[stage], st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES, kc * BK, wrow, wi);
+                        if (a.im2col) {
+                            tma_load_im2col_cg<CG>(ma_hi, &full_bar[stage], st, kc * BK, c.x0 + s.base_dx, c.y0 + s.base_dy, c.b0, ow_, oh_);
+                            tma_load_im2col_cg<CG>(ma_lo, &full_bar[stage], st + A_TILE_BYTES, kc * BK, c.x0 + s.base_dx, c.y0 + s.base_dy, c.b0, ow_, oh_);
+                        } else {
+                            tma_load_4d_cg<CG>(ma_hi, &full_bar[stage], st, kc * BK, ax, ay, c.b0);
+                            tma_load_4d_cg<CG>(ma_lo, &full_bar[stage], st + A_TILE_BYTES, kc * BK, ax, ay, c.b0);
+                        }
+                        tma_load_3d_cg<CG>(&maps.w[0], &full_bar[stage], st + 2 * A_TILE_BYTES, kc * BK, wrow, wi);
+                        tma_load_3d_cg<CG>(&maps.w[1], &full_bar[stage], st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES, kc * BK, wrow, wi);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -363,7 +402,13 @@ modconv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_con
         for (int t = unit0; t < a.total_tiles; t += unit_stride) {
             const TileCoord c = decode_tile<BN, TH, TW, TB, CG>(a, t, rank);
             const TcSubProblem& s = a.sub[c.sub];
-            const int b = c.b0 + tb, yy = c.y0 + th, xx = c.x0 + tw;
+            int b, yy, xx;
+            if (a.im2col) {
+                const int p = c.p0 + row;
+                xx = p % s.ow; yy = (p / s.ow) % s.oh; b = p / (s.ow * s.oh);
+            } else {
+                b = c.b0 + tb; yy = c.y0 + th; xx = c.x0 + tw;
+            }
             const bool valid = !c.dummy && b < a.batch && yy < s.oh && xx < s.ow;
             const int oy = yy * s.ostride + s.ooff_y, ox = xx * s.ostride + s.ooff_x;
             mbar_wait(&tfull_bar[acc], acc_phase, a.error, 0x400 + acc);
@@ -698,6 +743,37 @@ static int make_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims
     return SIS_OK;
 }
 
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeIm2col get_encode_im2col_fn() {
+    static PFN_encodeIm2col fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    fn = (PFN_encodeIm2col)p;
+    return fn;
+}
+
+// NHWC bf16 plane [B][H][W][C] as an im2col tensor map: traversal box [lower, dim-1+upper] in W and H, 128 pixels x
+// `channels` per load (corner arrays in W, H order as CUTLASS passes them).
+static int make_im2col_map(CUtensorMap* map, void* base, int C, int W, int H, int B, int lower_w, int lower_h, int upper_w, int upper_h,
+                           int channels, int swizzle_bytes) {
+    PFN_encodeIm2col enc = get_encode_im2col_fn();
+    if (!enc) { set_error("cuTensorMapEncodeIm2col entry point not available"); return SIS_ERR_CUDA; }
+    const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * W, (cuuint64_t)C * 2 * W * H};
+    const int lower[2] = {lower_w, lower_h}, upper[2] = {upper_w, upper_h};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, base, gdim, gstride, lower, upper, (cuuint32_t)channels, (cuuint32_t)BM, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeIm2col failed with CUresult %d", (int)r); return SIS_ERR_CUDA; }
+    return SIS_OK;
+}
+
 struct TcTensorMapCacheEntry { CUtensorMap m; };
 
 int tc_pack_weights(TcConvWeights& w, const float* d_weight, int cin, int cout, bool up, float scale, cudaStream_t stream) {
@@ -779,7 +855,7 @@ int tc_prescale_split(TcWorkspace& ws, int slot, const float* x, const float* s,
 }
 
 template <int BN, int TH, int TW, int TB, int BK, int CG>
-static int launch_tc(const CUtensorMap maps[4], const TcKernelArgs& a, cudaStream_t stream) {
+static int launch_tc(const TcMaps& maps, const TcKernelArgs& a, cudaStream_t stream) {
     using Cfg = TcCfg<BN, BK, CG>;
     auto kern = modconv_tc_kernel<BN, TH, TW, TB, BK, CG>;
     static bool configured = false;
@@ -796,13 +872,13 @@ static int launch_tc(const CUtensorMap maps[4], const TcKernelArgs& a, cudaStrea
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    SIS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps[0], maps[1], maps[2], maps[3], a));
+    SIS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, a));
     SIS_CHECK_LAUNCH();
     return SIS_OK;
 }
 
 template <int BN, int BK, int CG>
-static int launch_tc_bn(int th, int tw, int tb, const CUtensorMap maps[4], const TcKernelArgs& a, cudaStream_t stream) {
+static int launch_tc_bn(int th, int tw, int tb, const TcMaps& maps, const TcKernelArgs& a, cudaStream_t stream) {
     if (th == 4 && tw == 4 && tb == 8) return launch_tc<BN, 4, 4, 8, BK, CG>(maps, a, stream);
     if (th == 8 && tw == 8 && tb == 2) return launch_tc<BN, 8, 8, 2, BK, CG>(maps, a, stream);
     if (th == 8 && tw == 16 && tb == 1) return launch_tc<BN, 8, 16, 1, BK, CG>(maps, a, stream);
@@ -811,7 +887,7 @@ static int launch_tc_bn(int th, int tw, int tb, const CUtensorMap maps[4], const
 }
 
 template <int BK, int CG>
-static int launch_tc_any(int BN, int th, int tw, int tb, const CUtensorMap maps[4], const TcKernelArgs& a, cudaStream_t stream) {
+static int launch_tc_any(int BN, int th, int tw, int tb, const TcMaps& maps, const TcKernelArgs& a, cudaStream_t stream) {
     if (BN == 256) return launch_tc_bn<256, BK, CG>(th, tw, tb, maps, a, stream);
     if (BN == 128) return launch_tc_bn<128, BK, CG>(th, tw, tb, maps, a, stream);
     if (BN == 64) return launch_tc_bn<64, BK, CG>(th, tw, tb, maps, a, stream);
@@ -825,25 +901,38 @@ static int env_int(const char* name, int dflt) {
 
 int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, cudaStream_t stream) {
     // Tunables for A/B runs: SIS_TC_BK (64 default | 32: stage depth along K), SIS_TC_CG (2 default | 1: CTA pairs)
-    static int bk_env = 0, cg_env = 0;
-    if (!bk_env) { bk_env = env_int("SIS_TC_BK", 64) == 32 ? 32 : 64; cg_env = env_int("SIS_TC_CG", 2) == 1 ? 1 : 2; }
+    //                       SIS_TC_IM2COL (1 default | 0: spatial-box A tiles instead of flattened 128-pixel runs)
+    static int bk_env = 0, cg_env = 0, im2col_env = 1;
+    if (!bk_env) {
+        bk_env = env_int("SIS_TC_BK", 64) == 32 ? 32 : 64; cg_env = env_int("SIS_TC_CG", 2) == 1 ? 1 : 2;
+        im2col_env = env_int("SIS_TC_IM2COL", 1) != 0;
+    }
+    const bool im2col = im2col_env != 0;
     const int BK = (call.cin % 64 == 0) ? bk_env : 32;
     SIS_REQUIRE(call.cin % BK == 0, "tc_modconv: Cin must be a multiple of 32 (got %d)", call.cin);
     SIS_REQUIRE(call.cout % 32 == 0, "tc_modconv: Cout must be a multiple of 32 (got %d)", call.cout);
     SIS_REQUIRE(w.hi && w.cin == call.cin && w.cout == call.cout, "tc_modconv: weights not packed for this layer");
     const int B = call.batch, H = call.res_in;
-    const int BN = call.cout >= 256 ? 256 : call.cout;
-    SIS_REQUIRE(BN == 256 || BN == 128 || BN == 64 || BN == 32, "tc_modconv: unsupported Cout %d", call.cout);
     // tile box by the GEMM grid extent (plain: H; transposed phases: up to H+1)
     const int ext = call.up ? H + 1 : H;
     int th, tw, tb;
-    if (ext <= 4) { th = 4; tw = 4; tb = 8; }
-    else if (ext <= 8) { th = 8; tw = 8; tb = 2; }
-    else { th = 8; tw = 16; tb = 1; }
-    const int b_tiles = ceil_div(B, tb), n_tiles = call.cout / BN;
+    if (im2col || ext > 8) { th = 8; tw = 16; tb = 1; }      // im2col mode ignores the box (one kernel variant)
+    else if (ext <= 4) { th = 4; tw = 4; tb = 8; }
+    else { th = 8; tw = 8; tb = 2; }
+    const int b_tiles = ceil_div(B, tb);
+    // N tile: as wide as possible (fewest re-reads of the A tile) while the launch still fills the 148 SMs; the 4x4 and
+    // 8x8 layers only have a handful of pixel tiles, so they run narrow N tiles on many CTAs instead of 8 fat ones
+    const int64_t m_tiles_all = im2col ? ceil_div64((int64_t)B * (call.up ? (2 * H + 1) * (2 * H + 1) : H * H), BM)
+                                       : (int64_t)b_tiles * ceil_div(ext, th) * ceil_div(ext, tw) * (call.up ? 4 : 1);
+    int BN = 32;
+    for (int cand = 256; cand >= 32; cand /= 2) {
+        if (call.cout % cand) continue;
+        if (m_tiles_all * (call.cout / cand) >= kNumSMs || cand == 32) { BN = cand; break; }
+    }
+    SIS_REQUIRE(call.cout % BN == 0, "tc_modconv: unsupported Cout %d", call.cout);
+    const int n_tiles = call.cout / BN;
     // CTA pairs only when there is at least one full wave of pair tiles and each CTA's weight half is a legal UMMA N
-    const int64_t plain_m_tiles = (int64_t)b_tiles * ceil_div(ext, th) * ceil_div(ext, tw);
-    const int CG = (cg_env == 2 && BN >= 64 && plain_m_tiles * n_tiles >= 2 * kNumSMs) ? 2 : 1;
+    const int CG = (cg_env == 2 && BN >= 64 && m_tiles_all * n_tiles >= 2 * kNumSMs) ? 2 : 1;
 
     TcKernelArgs a;
     memset(&a, 0, sizeof(a));
@@ -851,8 +940,14 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
     a.b_tiles = b_tiles; a.n_tiles = n_tiles;
     a.demod = call.demod; a.noise = call.noise; a.noise_bstride = call.noise_bstride; a.noise_w = call.noise_w; a.bias = call.bias;
     a.error = ws.d_error;
+    a.im2col = im2col ? 1 : 0;
     int tiles = 0;   // tiles (CG = 1) or pair tiles (CG = 2)
-    auto units = [&](const TcSubProblem& s) { return ceil_div(a.b_tiles * s.tiles_y * s.tiles_x, CG) * a.n_tiles; };
+    auto units = [&](TcSubProblem& s) {
+        s.m_tiles = (int)ceil_div64((int64_t)B * s.oh * s.ow, BM);
+        s.base_dy = 127; s.base_dx = 127;
+        for (int t = 0; t < s.ntaps; ++t) { s.base_dy = std::min<int>(s.base_dy, s.dy[t]); s.base_dx = std::min<int>(s.base_dx, s.dx[t]); }
+        return ceil_div(im2col ? s.m_tiles : a.b_tiles * s.tiles_y * s.tiles_x, CG) * a.n_tiles;
+    };
     if (!call.up) {
         a.mode = 0; a.nsub = 1;
         TcSubProblem& s = a.sub[0];
@@ -887,16 +982,27 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
     }
     a.total_tiles = tiles;
 
-    CUtensorMap maps[4];
+    TcMaps maps;
+    memset(&maps, 0, sizeof(maps));
     {
-        const uint64_t adims[4] = {(uint64_t)call.cin, (uint64_t)H, (uint64_t)H, (uint64_t)B};
-        const uint32_t abox[4] = {(uint32_t)BK, (uint32_t)tw, (uint32_t)th, (uint32_t)tb};
-        SIS_PROPAGATE(make_map(&maps[0], ws.a_hi[call.in_slot], 4, adims, abox, BK * 2));
-        SIS_PROPAGATE(make_map(&maps[1], ws.a_lo[call.in_slot], 4, adims, abox, BK * 2));
+        if (im2col) {
+            // traversal box of sub-problem s: base pixels [base_d, base_d + extent - 1] = [lower, dim - 1 + upper]
+            for (int i = 0; i < a.nsub; ++i) {
+                const TcSubProblem& s = a.sub[i];
+                const int lw = s.base_dx, lh = s.base_dy, uw = s.base_dx + s.ow - H, uh = s.base_dy + s.oh - H;
+                SIS_PROPAGATE(make_im2col_map(&maps.a[i][0], ws.a_hi[call.in_slot], call.cin, H, H, B, lw, lh, uw, uh, BK, BK * 2));
+                SIS_PROPAGATE(make_im2col_map(&maps.a[i][1], ws.a_lo[call.in_slot], call.cin, H, H, B, lw, lh, uw, uh, BK, BK * 2));
+            }
+        } else {
+            const uint64_t adims[4] = {(uint64_t)call.cin, (uint64_t)H, (uint64_t)H, (uint64_t)B};
+            const uint32_t abox[4] = {(uint32_t)BK, (uint32_t)tw, (uint32_t)th, (uint32_t)tb};
+            SIS_PROPAGATE(make_map(&maps.a[0][0], ws.a_hi[call.in_slot], 4, adims, abox, BK * 2));
+            SIS_PROPAGATE(make_map(&maps.a[0][1], ws.a_lo[call.in_slot], 4, adims, abox, BK * 2));
+        }
         const uint64_t wdims[3] = {(uint64_t)call.cin, (uint64_t)call.cout, 9};
         const uint32_t wbox[3] = {(uint32_t)BK, (uint32_t)(BN / CG), 1};     // CG = 2: each CTA stages half the rows
-        SIS_PROPAGATE(make_map(&maps[2], w.hi, 3, wdims, wbox, BK * 2));
-        SIS_PROPAGATE(make_map(&maps[3], w.lo, 3, wdims, wbox, BK * 2));
+        SIS_PROPAGATE(make_map(&maps.w[0], w.hi, 3, wdims, wbox, BK * 2));
+        SIS_PROPAGATE(make_map(&maps.w[1], w.lo, 3, wdims, wbox, BK * 2));
     }
     int st;
     {
