@@ -69,10 +69,15 @@ METRICS = OrderedDict([
 
 def reps():
     for f in sorted(os.listdir(G)):
-        if not (f.endswith(f'_{tag}.ncu-rep')):
+        if f.endswith(f'_{tag}.ncu-rep'):
+            if os.path.exists(os.path.join(G, f.replace('.ncu-rep', '.csv'))):
+                continue
+            text = subprocess.run(['ncu', '-i', os.path.join(G, f), '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+        elif f.startswith('prof_') and f.endswith(f'_{tag}.csv'):
+            text = open(os.path.join(G, f)).read()
+        else:
             continue
-        res = subprocess.run(['ncu', '-i', os.path.join(G, f), '--page', 'raw', '--csv'], capture_output=True, text=True)
-        rows = list(csv.reader(io.StringIO(res.stdout)))
+        rows = list(csv.reader(io.StringIO(text)))
         if len(rows) < 3:
             continue
         hdr, units = rows[0], rows[1]
@@ -84,7 +89,7 @@ def reps():
             vals = [r[col[k]] if k in col else '-' for k in METRICS]
             vals = [f'{float(v):.3f}' if re.match(r'^-?\d+\.\d+$', v) else v for v in vals]
             out.append(f'| `{short(r[col["Kernel Name"]])}` | ' + ' | '.join(vals) + ' |')
-        name = f.replace('.ncu-rep', '.md')
+        name = f.replace('.ncu-rep', '.md').replace('.csv', '.md')
         open(os.path.join(P, name), 'w').write('\n'.join(out) + '\n')
         print('\n'.join(out))
 
