@@ -143,6 +143,7 @@ struct TcKernelArgs {
     int batch, cin, cout, b_tiles, n_tiles, kchunks;
     int mode;                   // 0 plain (fused activation), 1 transposed-conv phase (demod only)
     int im2col;                 // A tiles are 128 consecutive pixels of the flattened (b, y, x) output grid (TMA im2col mode)
+    int interleave_units;       // > 0: the 4 transposed-conv phases are interleaved, each padded to this many (pair) tiles
     const float* demod; const float* noise; int64_t noise_bstride; float noise_w; const float* bias;
     float* out_f32; int out_h, out_w;
     const float* s_next; bf16* next_hi; bf16* next_lo;
@@ -167,24 +168,36 @@ template <int BN, int BK, int CG> struct TcCfg {
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
 };
 
-struct TileCoord { int sub, b0, y0, x0, n0; int p0; bool dummy; };
+struct TileCoord { int sub, b0, y0, x0, n0; int p0; bool dummy; bool skip; };
 
 // Tile t of this CTA.  CG = 1: t is a tile index.  CG = 2: t is a PAIR index and `rank` selects the m-tile of the pair
 // (2*mp + rank); an odd m-tile count leaves rank 1 of the last pair with a dummy tile (it recomputes rank 0's tile and
 // stores nothing).
 template <int BN, int TH, int TW, int TB, int CG>
 __device__ __forceinline__ TileCoord decode_tile(const TcKernelArgs& a, int t, int rank) {
-    int p = 0;
+    TileCoord c;
+    c.skip = false;
+    int p = 0, local;
+    if (a.interleave_units) {
+        // transposed conv, im2col mode: the 4 phase sub-GEMMs walk the image together (phase fastest, rotated so a
+        // CTA's static stride does not lock onto one phase), so the input planes are read from DRAM once, not 4 times.
+        // All phases are padded to the same number of units; the surplus tiles are skipped by every role alike.
+        const int per_n = 4 * a.interleave_units;
+        const int r = t % per_n, u = r >> 2;
+        p = (u + (r & 3)) & 3;
+        local = (t / per_n) * a.interleave_units + u;          // n * units + u; decoded below with m_units := interleave_units
+    } else {
 #pragma unroll
-    for (int i = 1; i < 4; ++i)
-        if (i < a.nsub && t >= a.sub[i].tile_begin) p = i;
+        for (int i = 1; i < 4; ++i)
+            if (i < a.nsub && t >= a.sub[i].tile_begin) p = i;
+        local = t - a.sub[p].tile_begin;
+    }
     const TcSubProblem& s = a.sub[p];
-    const int local = t - s.tile_begin;
     const int m_tiles = a.im2col ? s.m_tiles : a.b_tiles * s.tiles_y * s.tiles_x;
-    const int m_units = (m_tiles + CG - 1) / CG;
+    const int m_units = a.interleave_units ? a.interleave_units : (m_tiles + CG - 1) / CG;
     int m = (local % m_units) * CG + rank;
     const int n = local / m_units;
-    TileCoord c;
+    if (a.interleave_units && (local % m_units) * CG >= m_tiles) c.skip = true;
     c.dummy = m >= m_tiles;
     if (c.dummy) m = m_tiles - 1;
     c.sub = p;
@@ -332,6 +345,7 @@ modconv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ T
             int stage = 0; uint32_t phase = 0;
             for (int t = unit0; t < a.total_tiles; t += unit_stride) {
                 const TileCoord c = decode_tile<BN, TH, TW, TB, CG>(a, t, rank);
+                if (c.skip) continue;
                 const TcSubProblem& s = a.sub[c.sub];
                 const int wrow = c.n0 + rank * Cfg::B_ROWS;
                 const CUtensorMap* ma_hi = &maps.a[a.im2col ? c.sub : 0][0];
@@ -367,6 +381,7 @@ modconv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ T
             int acc = 0; uint32_t acc_phase = 0;
             for (int t = unit0; t < a.total_tiles; t += unit_stride) {
                 const TileCoord c = decode_tile<BN, TH, TW, TB, CG>(a, t, 0);
+                if (c.skip) continue;
                 const int kblocks = a.sub[c.sub].ntaps * a.kchunks;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1, a.error, 0x200 + acc);
                 tc_fence_after();
@@ -401,6 +416,7 @@ modconv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ T
         int acc = 0; uint32_t acc_phase = 0;
         for (int t = unit0; t < a.total_tiles; t += unit_stride) {
             const TileCoord c = decode_tile<BN, TH, TW, TB, CG>(a, t, rank);
+            if (c.skip) continue;
             const TcSubProblem& s = a.sub[c.sub];
             int b, yy, xx;
             if (a.im2col) {
@@ -979,6 +995,14 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
                 tiles += units(s);
             }
         a.out_f32 = call.upconv_tmp; a.out_h = 2 * H + 1; a.out_w = 2 * H + 1;
+        static int il_env = -1;
+        if (il_env < 0) il_env = env_int("SIS_TC_INTERLEAVE", 1) != 0;
+        if (im2col && il_env) {
+            int umax = 0;
+            for (int i = 0; i < 4; ++i) umax = std::max(umax, ceil_div(a.sub[i].m_tiles, CG));
+            a.interleave_units = umax;
+            tiles = 4 * umax * a.n_tiles;
+        }
     }
     a.total_tiles = tiles;
 
