@@ -90,91 +90,196 @@ __global__ void __launch_bounds__(256) upfirdn2d_generic_kernel(T* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------ tiled
-// One block = one TH x TW output tile of one plane (minor == 1).  K = padded (template) tap count as in the
-// reference's mode table; taps beyond the real kernel are zero, so the FMA chain has the reference's order.
-template <int UP, int DOWN, int K, int TH, int TW>
-__global__ void __launch_bounds__(TH * TW / 4) upfirdn2d_tiled_kernel(float* __restrict__ out,
-                                                                     const float* __restrict__ in,
-                                                                     const float* __restrict__ kernel,
-                                                                     UpfirdnParams p, int tiles_x, int tiles_y) {
+// One block = one TH x 64 output tile of TWO planes (minor == 1), interleaved in shared memory as float2 so that every
+// shared-memory access is an LDS.64 and every multiply-add is a packed FFMA2 (two planes per instruction).  K = padded
+// (template) tap count as in the reference's mode table; taps beyond the real kernel are zero, so each plane's FMA chain
+// has the reference's order (y outer, x inner, from 0) and results stay bit-identical to the reference kernel.
+// A thread owns 4 consecutive output columns x 2 rows; for UP == 1 the (3*DOWN + K)-wide input span of each needed row
+// is loaded once into registers and shared by the 4 columns and both rows.  All index arithmetic is per thread / per
+// row, none per tap: the first version of this kernel was instruction-bound at 31 % of HBM peak.
+using u64 = unsigned long long;
+__device__ __forceinline__ float2 up_ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<u64&>(d)) : "l"(reinterpret_cast<u64&>(a)), "l"(reinterpret_cast<u64&>(b)), "l"(reinterpret_cast<u64&>(c)));
+    return d;
+}
+
+template <int UP, int DOWN, int K, int TH>
+__global__ void __launch_bounds__(256) upfirdn2d_pair_kernel(float* __restrict__ out, const float* __restrict__ in,
+                                                             const float* __restrict__ kernel, UpfirdnParams p,
+                                                             int tiles_x, int tiles_y) {
+    constexpr int TW = 64, RPT = TH / 16;                    // 16 column groups x 16 row groups, RPT rows per thread
     constexpr int TIN_H = ((TH - 1) * DOWN + K - 1) / UP + 1;
     constexpr int TIN_W = ((TW - 1) * DOWN + K - 1) / UP + 1;
-    constexpr int TIN_WP = TIN_W + 1;
-    constexpr int NT = TH * TW / 4;
+    constexpr int TAPS = K / UP;
+    // Lane t of a half-warp starts its 4 outputs at input column 4*DOWN/UP * t: a 32 B (or 16 / 64 B) lane stride would
+    // serialise the LDS.64 on 4 (2 / 8) banks.  One padding slot every PADG columns makes the stride odd in 8-byte units.
+    constexpr int PADG = 4 * DOWN / UP;
+    constexpr int TIN_WP = TIN_W + TIN_W / PADG + 1;
     __shared__ float sk[K][K];
-    __shared__ float sx[TIN_H][TIN_WP];
+    constexpr int NBUF = (DOWN == 2) ? 1 : 2;               // the decimating tile (35 KB) is single-buffered
+    __shared__ float2 sxbuf[NBUF][TIN_H][TIN_WP];            // double-buffered: tile i+1 is in flight while tile i is computed
+#define SXC(c) ((c) + (c) / PADG)
 
-    for (int t = threadIdx.x; t < K * K; t += NT) {
+    for (int t = threadIdx.x; t < K * K; t += 256) {
         int ky = t / K, kx = t - ky * K;
         float v = 0.0f;
         if (kx < p.kernel_w && ky < p.kernel_h) v = kernel[(p.kernel_h - 1 - ky) * p.kernel_w + (p.kernel_w - 1 - kx)];
         sk[ky][kx] = v;
     }
-    const int64_t tiles_per_plane = (int64_t)tiles_x * tiles_y;
-    const int64_t total_tiles = tiles_per_plane * p.major;
-    const int tx = threadIdx.x % (TW / 4), ty = threadIdx.x / (TW / 4);
+    const int64_t pairs = (p.major + 1) / 2;
+    const int64_t tiles_per_pair = (int64_t)tiles_x * tiles_y;
+    const int64_t total_tiles = tiles_per_pair * pairs;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t in_plane = (int64_t)p.in_h * p.in_w, out_plane = (int64_t)p.out_h * p.out_w;
 
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int64_t plane = tile / tiles_per_plane;
-        const int trem = (int)(tile - plane * tiles_per_plane);
+    // stage one tile: warp w takes rows w, w+8, ...; lanes take consecutive columns (coalesced 4-byte cp.async into the
+    // interleaved float2 slots, fire-and-forget; out-of-range elements are zero-filled with plain stores)
+    auto stage = [&](int64_t tile, int buf) {
+        const int64_t pair = tile / tiles_per_pair;
+        const int trem = (int)(tile - pair * tiles_per_pair);
+        const int tile_out_y = (trem / tiles_x) * TH, tile_out_x = (trem % tiles_x) * TW;
+        const int tile_in_x = floor_div(tile_out_x * DOWN + UP - 1 - p.pad_x0, UP);
+        const int tile_in_y = floor_div(tile_out_y * DOWN + UP - 1 - p.pad_y0, UP);
+        const int64_t plane0 = pair * 2;
+        const float* src0 = in + plane0 * in_plane;
+        const float* src1 = (plane0 + 1 < p.major) ? src0 + in_plane : src0;
+        const uint32_t sx_u32 = (uint32_t)__cvta_generic_to_shared(&sxbuf[buf][0][0]);
+        for (int ry = warp; ry < TIN_H; ry += 8) {
+            const int iy = ry + tile_in_y;
+            const bool rowok = iy >= 0 && iy < p.in_h;
+            const float* r0 = src0 + (int64_t)iy * p.in_w + tile_in_x;
+            const float* r1 = src1 + (int64_t)iy * p.in_w + tile_in_x;
+#pragma unroll
+            for (int rx = lane; rx < TIN_W; rx += 32) {
+                const int ix = rx + tile_in_x;
+                const uint32_t dst = sx_u32 + (uint32_t)(ry * TIN_WP + SXC(rx)) * 8u;
+                if (rowok && ix >= 0 && ix < p.in_w) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(r0 + rx) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst + 4u), "l"(r1 + rx) : "memory");
+                } else {
+                    asm volatile("st.shared.v2.f32 [%0], {%1, %1};" ::"r"(dst), "f"(0.0f) : "memory");
+                }
+            }
+        }
+    };
+
+    int buf = 0;
+    if (NBUF == 2 && (int64_t)blockIdx.x < total_tiles) stage(blockIdx.x, 0);
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, buf ^= (NBUF - 1)) {
+        const int64_t pair = tile / tiles_per_pair;
+        const int trem = (int)(tile - pair * tiles_per_pair);
         const int tile_out_y = (trem / tiles_x) * TH, tile_out_x = (trem % tiles_x) * TW;
         const int tile_mid_x = tile_out_x * DOWN + UP - 1 - p.pad_x0;
         const int tile_mid_y = tile_out_y * DOWN + UP - 1 - p.pad_y0;
         const int tile_in_x = floor_div(tile_mid_x, UP), tile_in_y = floor_div(tile_mid_y, UP);
-        const float* src = in + plane * (int64_t)p.in_h * p.in_w;
-        __syncthreads();
-        for (int i = threadIdx.x; i < TIN_H * TIN_W; i += NT) {
-            int ry = i / TIN_W, rx = i - ry * TIN_W;
-            int ix = rx + tile_in_x, iy = ry + tile_in_y;
-            float v = 0.0f;
-            if (ix >= 0 && iy >= 0 && ix < p.in_w && iy < p.in_h) v = __ldg(src + (int64_t)iy * p.in_w + ix);
-            sx[ry][rx] = v;
+        const int64_t plane0 = pair * 2;
+        const bool has1 = plane0 + 1 < p.major;
+        if (NBUF == 1) {
+            __syncthreads();  // everybody is done computing the previous tile
+            stage(tile, 0);
         }
-        __syncthreads();
-        const int oy = tile_out_y + ty;
-        const int mid_y = tile_mid_y + ty * DOWN;
-        const int in_y = floor_div(mid_y, UP);
-        const int rel_y = in_y - tile_in_y;
-        const int ky0 = (in_y + 1) * UP - mid_y - 1;
-        float res[4];
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();      // this tile's data has landed; everybody is done with the other buffer
+        if (NBUF == 2 && tile + gridDim.x < total_tiles) stage(tile + gridDim.x, buf ^ 1);
+        float2 (*sx)[TIN_WP] = sxbuf[buf];
+
+        float2 acc[RPT][4];
+        if (UP == 1) {
+            // register window: rows [rel_y0, rel_y0 + (RPT-1)*DOWN + K), columns [rel_x0, rel_x0 + 3*DOWN + K)
+            constexpr int SPAN = 3 * DOWN + K, ROWS = (RPT - 1) * DOWN + K;
+            const int rel_x0 = tx * 4 * DOWN, rel_y0 = ty * RPT * DOWN;    // UP == 1: mid == in, kernel phase 0
+            float wreg[K][K];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int rel_ox = tx * 4 + j;
-            const int mid_x = tile_mid_x + rel_ox * DOWN;
-            const int in_x = floor_div(mid_x, UP);
-            const int rel_x = in_x - tile_in_x;
-            const int kx0 = (in_x + 1) * UP - mid_x - 1;
-            float v = 0.0f;
+            for (int ky = 0; ky < K; ++ky)
 #pragma unroll
-            for (int y = 0; y < K / UP; ++y)
+                for (int kx = 0; kx < K; ++kx) wreg[ky][kx] = sk[ky][kx];
 #pragma unroll
-                for (int x = 0; x < K / UP; ++x)
-                    v = __fmaf_rn(sx[rel_y + y][rel_x + x], sk[ky0 + y * UP][kx0 + x * UP], v);
-            res[j] = v;
+            for (int r = 0; r < RPT; ++r)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[r][j] = make_float2(0.0f, 0.0f);
+#pragma unroll
+            for (int wy = 0; wy < ROWS; ++wy) {
+                float2 row[SPAN];
+#pragma unroll
+                for (int c = 0; c < SPAN; ++c) row[c] = sx[rel_y0 + wy][SXC(rel_x0) + SXC(c)];   // rel_x0 % PADG == 0
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) {
+                    const int ky = wy - r * DOWN;              // compile-time after unrolling
+                    if (ky >= 0 && ky < K) {
+#pragma unroll
+                        for (int kx = 0; kx < K; ++kx) {
+                            const float w = wreg[ky][kx];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) acc[r][j] = up_ffma2(row[j * DOWN + kx], make_float2(w, w), acc[r][j]);
+                        }
+                    }
+                }
+            }
+        } else {
+            // UP > 1: TAPS x TAPS taps per output, phase pattern periodic in the output coordinate
+            int rel_x[4], kx0[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int mid_x = tile_mid_x + (tx * 4 + j) * DOWN;
+                const int in_x = floor_div(mid_x, UP);
+                rel_x[j] = in_x - tile_in_x;
+                kx0[j] = (in_x + 1) * UP - mid_x - 1;
+            }
+#pragma unroll
+            for (int r = 0; r < RPT; ++r) {
+                const int mid_y = tile_mid_y + (ty * RPT + r) * DOWN;
+                const int in_y = floor_div(mid_y, UP);
+                const int rel_y = in_y - tile_in_y, ky0 = (in_y + 1) * UP - mid_y - 1;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float2 v = make_float2(0.0f, 0.0f);
+#pragma unroll
+                    for (int y = 0; y < TAPS; ++y)
+#pragma unroll
+                        for (int x = 0; x < TAPS; ++x) {
+                            const float w = sk[ky0 + y * UP][kx0[j] + x * UP];
+                            v = up_ffma2(sx[rel_y + y][SXC(rel_x[j] + x)], make_float2(w, w), v);
+                        }
+                    acc[r][j] = v;
+                }
+            }
         }
-        if (oy < p.out_h) {
-            float* dst = out + (plane * p.out_h + oy) * (int64_t)p.out_w + tile_out_x + tx * 4;
-            const int ox = tile_out_x + tx * 4;
-            if (ox + 3 < p.out_w && ((((uintptr_t)dst) & 15) == 0)) {
-                st_stream_f4((float4*)dst, make_float4(res[0], res[1], res[2], res[3]));
+        // NOTE on ordering: for UP == 1 the accumulation runs over wy (= ky for row r) outer and kx inner, i.e. the
+        // reference's y-outer / x-inner chain per output.
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int oy = tile_out_y + ty * RPT + r, ox = tile_out_x + tx * 4;
+            if (oy >= p.out_h) continue;
+            float* d0 = out + plane0 * out_plane + (int64_t)oy * p.out_w + ox;
+            float* d1 = d0 + out_plane;
+            if (ox + 3 < p.out_w && ((((uintptr_t)d0) & 15) == 0) && ((((uintptr_t)d1) & 15) == 0)) {
+                st_stream_f4((float4*)d0, make_float4(acc[r][0].x, acc[r][1].x, acc[r][2].x, acc[r][3].x));
+                if (has1) st_stream_f4((float4*)d1, make_float4(acc[r][0].y, acc[r][1].y, acc[r][2].y, acc[r][3].y));
             } else {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
-                    if (ox + j < p.out_w) dst[j] = res[j];
+                    if (ox + j < p.out_w) {
+                        d0[j] = acc[r][j].x;
+                        if (has1) d1[j] = acc[r][j].y;
+                    }
             }
         }
     }
 }
 
+#undef SXC
+
 template <int UP, int DOWN, int K>
 static void launch_tiled(float* out, const float* in, const float* kernel, const UpfirdnParams& p,
                          cudaStream_t stream) {
-    constexpr int TH = 16, TW = 64;
+    constexpr int TH = (DOWN == 2) ? 16 : 32, TW = 64;   // DOWN == 2: 2 x 34 x 147 x 8 B = 80 KB would not fit, see below
     int tiles_x = ceil_div(p.out_w, TW), tiles_y = ceil_div(p.out_h, TH);
-    int64_t total = (int64_t)tiles_x * tiles_y * p.major;
-    int64_t cap = (int64_t)kNumSMs * 8;
+    int64_t total = (int64_t)tiles_x * tiles_y * ((p.major + 1) / 2);
+    int64_t cap = (int64_t)kNumSMs * 4;
     int grid = (int)(total < cap ? total : cap);
-    upfirdn2d_tiled_kernel<UP, DOWN, K, TH, TW><<<grid, TH * TW / 4, 0, stream>>>(out, in, kernel, p, tiles_x, tiles_y);
+    upfirdn2d_pair_kernel<UP, DOWN, K, TH><<<grid, 256, 0, stream>>>(out, in, kernel, p, tiles_x, tiles_y);
 }
 
 }  // namespace sis
