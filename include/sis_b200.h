@@ -101,6 +101,16 @@ SIS_API int sis_generator_activation_shape(const sis_generator* g, int idx, int*
 /* style MLP: `Generator.style` / `get_latent`, model.py:383-392,476-477.  z,w: [n, style_dim] fp32 device. */
 SIS_API int sis_generator_style(sis_generator* g, const float* d_z, float* d_w, int64_t n, void* stream);
 
+/* A labelling job executed inside the forward, right after activation `activation_idx` has been produced (same
+ * semantics and outputs as sis_label_assign, mode 0).  When the activation also feeds a ToRGB and the map is large,
+ * labelling and ToRGB run as ONE pass over the activation tensor. */
+typedef struct {
+    int activation_idx;
+    const float* d_centroids; int k;
+    const uint32_t* d_cluster_class_bits; int n_class; int image_size;
+    uint8_t* d_ids_u8; int64_t* d_ids_i64; uint8_t* d_masks; float* d_margin; unsigned long long* d_hist;
+} sis_label_job;
+
 typedef struct {
     int batch;
     /* --- styles (model.py:491-528) ---
@@ -125,6 +135,9 @@ typedef struct {
     float* const* d_activations; /* optional: n_latent pointers, entry idx = [batch, C_idx, H_idx, H_idx] fp32
                                     NCHW or NULL to skip that capture (model.py:530-549) */
     int precision;               /* sis_precision */
+    /* --- optional fused labelling (NULL / 0 = none) --- */
+    int n_label_jobs;
+    const sis_label_job* label_jobs;
 } sis_forward_args;
 
 SIS_API int sis_generator_forward(sis_generator* g, const sis_forward_args* args, void* stream);

@@ -14,6 +14,16 @@ SIS_F32, SIS_F16, SIS_F64 = 0, 1, 2
 PRECISION_FP32, PRECISION_BF16X3 = 0, 1
 
 
+class LabelJob(Structure):
+    """`sis_label_job` (include/sis_b200.h)."""
+    _fields_ = [
+        ('activation_idx', c_int),
+        ('d_centroids', c_void_p), ('k', c_int),
+        ('d_cluster_class_bits', c_void_p), ('n_class', c_int), ('image_size', c_int),
+        ('d_ids_u8', c_void_p), ('d_ids_i64', c_void_p), ('d_masks', c_void_p), ('d_margin', c_void_p), ('d_hist', c_void_p),
+    ]
+
+
 class ForwardArgs(Structure):
     """`sis_forward_args` (include/sis_b200.h)."""
     _fields_ = [
@@ -32,6 +42,8 @@ class ForwardArgs(Structure):
         ('d_latent_out', c_void_p),
         ('d_activations', POINTER(c_void_p)),
         ('precision', c_int),
+        ('n_label_jobs', c_int),
+        ('label_jobs', POINTER(LabelJob)),
     ]
 
 

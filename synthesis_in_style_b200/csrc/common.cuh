@@ -72,6 +72,30 @@ __device__ __forceinline__ float lrelu_scale(float x, float alpha, float scale) 
     return __fmul_rn(y, scale);
 }
 
+// packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2): two IEEE fp32 operations per instruction, per-lane results
+// identical to the scalar instructions
+using u64_t = unsigned long long;
+__device__ __forceinline__ float2 pk_fma(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<u64_t&>(d)) : "l"(reinterpret_cast<u64_t&>(a)), "l"(reinterpret_cast<u64_t&>(b)), "l"(reinterpret_cast<u64_t&>(c)));
+    return d;
+}
+__device__ __forceinline__ float2 pk_add(float2 a, float2 b) {
+    float2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<u64_t&>(d)) : "l"(reinterpret_cast<u64_t&>(a)), "l"(reinterpret_cast<u64_t&>(b)));
+    return d;
+}
+__device__ __forceinline__ float2 pk_sub(float2 a, float2 b) {
+    float2 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<u64_t&>(d)) : "l"(reinterpret_cast<u64_t&>(a)), "l"(reinterpret_cast<u64_t&>(b)));
+    return d;
+}
+__device__ __forceinline__ float2 pk_mul(float2 a, float2 b) {
+    float2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<u64_t&>(d)) : "l"(reinterpret_cast<u64_t&>(a)), "l"(reinterpret_cast<u64_t&>(b)));
+    return d;
+}
+
 // 128-bit streaming accesses: data touched once goes around L1.
 __device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
     float4 r;

@@ -325,6 +325,25 @@ static int ensure_workspace(sis_generator* g, int B) {
     return SIS_OK;
 }
 
+// label jobs attached to activation `idx`; `rgb` = the ToRGB reading the same tensor (fused when possible)
+static int run_label_jobs(const sis_forward_args* a, int idx, const float* act, int batch, int C, int res, const ToRgbArgs* rgb,
+                          bool* rgb_done, cudaStream_t stream) {
+    if (rgb_done) *rgb_done = false;
+    for (int j = 0; j < a->n_label_jobs; ++j) {
+        const sis_label_job& job = a->label_jobs[j];
+        if (job.activation_idx != idx) continue;
+        LabelArgs la;
+        la.act = act; la.batch = batch; la.C = C; la.H = res; la.W = res; la.centroids = job.d_centroids; la.k = job.k;
+        la.class_bits = job.d_cluster_class_bits; la.n_class = job.n_class; la.S = job.image_size;
+        la.ids_u8 = job.d_ids_u8; la.ids_i64 = job.d_ids_i64; la.masks = job.d_masks; la.margin = job.d_margin; la.hist = job.d_hist;
+        bool fused = false;
+        const bool try_fuse = rgb && rgb_done && !*rgb_done;
+        SIS_PROPAGATE(launch_label(la, 0, try_fuse ? rgb : nullptr, &fused, stream));
+        if (fused) *rgb_done = true;
+    }
+    return SIS_OK;
+}
+
 extern "C" int sis_generator_forward(sis_generator* g, const sis_forward_args* a, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SIS_REQUIRE(g && a, "generator_forward: null argument");
@@ -342,6 +361,10 @@ extern "C" int sis_generator_forward(sis_generator* g, const sis_forward_args* a
     SIS_REQUIRE(a->d_image, "generator_forward: image output is null");
     SIS_REQUIRE(a->precision == SIS_PRECISION_FP32 || a->precision == SIS_PRECISION_BF16X3, "generator_forward: unknown precision %d", a->precision);
     for (int l = 0; l < g->num_layers; ++l) SIS_REQUIRE(a->d_noise[l] != nullptr, "generator_forward: noise[%d] is null", l);
+    SIS_REQUIRE(a->n_label_jobs >= 0 && (a->n_label_jobs == 0 || a->label_jobs), "generator_forward: label_jobs is null");
+    for (int j = 0; j < a->n_label_jobs; ++j)
+        SIS_REQUIRE(a->label_jobs[j].activation_idx >= 0 && a->label_jobs[j].activation_idx < g->n_latent,
+                    "generator_forward: label job %d names activation %d", j, a->label_jobs[j].activation_idx);
     SIS_PROPAGATE(ensure_workspace(g, B));
     const int sd = g->style_dim;
     const bool tc = a->precision == SIS_PRECISION_BF16X3;
@@ -382,6 +405,7 @@ extern "C" int sis_generator_forward(sis_generator* g, const sis_forward_args* a
     float* x = act_dst(0, 0);
     SIS_PROPAGATE(launch_const_input(x, g->const_input.as<float>(), (int64_t)g->channels[4] * 16, B, stream));
     if (tc) SIS_PROPAGATE(tc_prescale_split(g->tc_ws, 0, x, g->convs[0].s, B, g->convs[0].cin, 4, 4, stream));
+    SIS_PROPAGATE(run_label_jobs(a, 0, x, B, g->channels[4], 4, nullptr, nullptr, stream));
     int pp = 1;
     const float* skip = nullptr;
     int rgb_i = 0;
@@ -430,10 +454,16 @@ extern "C" int sis_generator_forward(sis_generator* g, const sis_forward_args* a
             ToRgbArgs t;
             t.x = x; t.s = r.s; t.w = r.w_scaled.as<float>(); t.bias = r.bias.as<float>(); t.skip = skip; t.up_k = r.up ? r.up_k.as<float>() : nullptr;
             t.out = out; t.batch = B; t.C = r.cin; t.H = r.res; t.W = r.res;
-            ProfScope prof(PROF_TORGB, stream);
-            SIS_PROPAGATE(launch_torgb(t, stream));
+            bool rgb_done = false;
+            SIS_PROPAGATE(run_label_jobs(a, (int)L + 1, x, B, c.cout, c.res_out, &t, &rgb_done, stream));
+            if (!rgb_done) {
+                ProfScope prof(PROF_TORGB, stream);
+                SIS_PROPAGATE(launch_torgb(t, stream));
+            }
             skip = out;
             ++rgb_i;
+        } else {
+            SIS_PROPAGATE(run_label_jobs(a, (int)L + 1, x, B, c.cout, c.res_out, nullptr, nullptr, stream));
         }
     }
     return SIS_OK;

@@ -43,6 +43,18 @@ struct ToRgbArgs {
     int batch, C, H, W;
 };
 
+struct LabelArgs {
+    const float* act; int batch, C, H, W;
+    const float* centroids; int k;
+    const uint32_t* class_bits; int n_class; int S;
+    uint8_t* ids_u8; int64_t* ids_i64; uint8_t* masks; float* margin; unsigned long long* hist;
+};
+
+// Labelling of one activation map (mode 0 native + nearest resize, mode 1 bilinear-then-assign).  When `fuse_rgb` is
+// given (a ToRGB over the SAME tensor) and the shapes allow the wide kernel, both are done in one pass over the
+// activations and *fused is set; otherwise only the labelling runs and the caller launches ToRGB itself.
+int launch_label(const LabelArgs& a, int mode, const ToRgbArgs* fuse_rgb, bool* fused, cudaStream_t stream);
+
 int launch_pixel_norm(float* out, const float* z, int64_t rows, int dim, cudaStream_t stream);
 // small_m_ok: every job has K % 4 == 0, 16-byte aligned A rows / W rows (then the weight-streaming kernel is used)
 int launch_linear_jobs(const LinearJob* d_jobs, int n_jobs, int max_m, int max_n, int max_k, bool small_m_ok, cudaStream_t stream);

@@ -12,17 +12,13 @@
 // reduced through shared memory in fixed order (deterministic), then argmin (ties -> lowest k, as
 // torch.argmin), class-bit LUT, nearest replication of the masks to SxS, and a warp-aggregated histogram.
 #include "common.cuh"
+#include "kernels.h"
+#include "torgb_common.cuh"
+#include <cstring>
 
 namespace sis {
 
 constexpr int LBL_SLICES = 8;
-
-struct LabelArgs {
-    const float* act; int batch, C, H, W;
-    const float* centroids; int k;
-    const uint32_t* class_bits; int n_class; int S;
-    uint8_t* ids_u8; int64_t* ids_i64; uint8_t* masks; float* margin; unsigned long long* hist;
-};
 
 template <int KMAX, int PPT>
 struct LabelSmem {
@@ -162,48 +158,77 @@ __global__ void __launch_bounds__(32 * LBL_SLICES) label_native_kernel(LabelArgs
 // consecutive pixels x ALL channels.  A block of 256 threads reads 4 KB contiguous per channel plane (DRAM-friendly),
 // keeps 8 independent 128-bit loads in flight per thread, needs no shared-memory reduction and no barrier, and
 // finalises in registers: packed 4-pixel stores for ids and masks (32-bit for rep 1, 128-bit rows for rep 4).
-template <int KMAX>
-__global__ void __launch_bounds__(256) label_wide_kernel(LabelArgs a) {
+// RGB = true: the ToRGB of the same tensor (1x1 modulated conv, bias, upsampled skip; model.py:355-364) rides along in
+// the same pass: the activation map is read once instead of twice.
+// The inner loop is packed fp32x2 (FADD2 / FFMA2 on pixel pairs): the centroid table and the per-sample ToRGB weights
+// sit in shared memory pre-splatted as (m, m) pairs, so a channel costs 1 LDG.128 + 2 LDS.128 + 4k packed ops per
+// 4 pixels (+ 3 LDS.64 + 6 FFMA2 for RGB): the scalar version of the fused kernel was issue-bound at half the speed.
+template <int KMAX, bool RGB>
+__global__ void __launch_bounds__(256) label_wide_kernel(LabelArgs a, ToRgbArgs g) {
     extern __shared__ float smem[];
-    float* sc = smem;                                   // [C][KMAX]
-    unsigned* shist = reinterpret_cast<unsigned*>(smem + (size_t)a.C * KMAX);   // [KMAX]
+    float2* sc2 = reinterpret_cast<float2*>(smem);                              // [C][KMAX] splatted centroids
+    float2* sw2 = sc2 + (size_t)a.C * KMAX;                                     // [C][3] splatted scale*W*s of this sample (RGB)
+    unsigned* shist = reinterpret_cast<unsigned*>(sw2 + (RGB ? 3 * a.C : 0));  // [KMAX]
     const int tid = threadIdx.x;
+    const int64_t hw = (int64_t)a.H * a.W;
+    const int64_t quads_per_sample = hw >> 2;                                   // a multiple of 256 (checked on the host):
+    const int64_t total = quads_per_sample * a.batch;                           // a block never straddles two samples
+    const int64_t q = (int64_t)blockIdx.x * 256 + tid;
+    const int b_blk = (int)(((int64_t)blockIdx.x * 256) / quads_per_sample);
     for (int i = tid; i < a.C * KMAX; i += 256) {
         int c = i / KMAX, kk = i - c * KMAX;
-        sc[i] = kk < a.k ? a.centroids[(int64_t)kk * a.C + c] : 0.0f;
+        const float m = kk < a.k ? a.centroids[(int64_t)kk * a.C + c] : 0.0f;
+        sc2[i] = make_float2(m, m);
+    }
+    if (RGB) {
+        const float* sb = g.s + (int64_t)b_blk * a.C;
+        for (int i = tid; i < 3 * a.C; i += 256) {
+            const int c = i / 3, j = i - c * 3;
+            const float w = __fmul_rn(g.w[j * a.C + c], sb[c]);                 // (scale*W) * s, as the reference orders it
+            sw2[i] = make_float2(w, w);
+        }
     }
     if (tid < KMAX) shist[tid] = 0;
     __syncthreads();
-    const int64_t hw = (int64_t)a.H * a.W;
-    const int64_t quads_per_sample = hw >> 2;
-    const int64_t total = quads_per_sample * a.batch;
-    const int64_t q = (int64_t)blockIdx.x * 256 + tid;
     const bool valid = q < total;
     int ids[4] = {-1, -1, -1, -1};
     if (valid) {
-        const int b = (int)(q / quads_per_sample);
+        const int b = b_blk;
         const int64_t pix = (q - (int64_t)b * quads_per_sample) << 2;
         const float* xb = a.act + ((int64_t)b * a.C) * hw + pix;
-        float acc[KMAX][4];
+        float2 acc2[KMAX][2];
+        float2 rgb2[3][2];
 #pragma unroll
-        for (int kk = 0; kk < KMAX; ++kk)
+        for (int kk = 0; kk < KMAX; ++kk) { acc2[kk][0] = make_float2(0.f, 0.f); acc2[kk][1] = make_float2(0.f, 0.f); }
 #pragma unroll
-            for (int p = 0; p < 4; ++p) acc[kk][p] = 0.0f;
+        for (int j = 0; j < 3; ++j) { rgb2[j][0] = make_float2(0.f, 0.f); rgb2[j][1] = make_float2(0.f, 0.f); }
 #pragma unroll 8
         for (int c = 0; c < a.C; ++c) {
             const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(xb + (int64_t)c * hw));
-            const float xv[4] = {v.x, v.y, v.z, v.w};
-            const float* cc = sc + (size_t)c * KMAX;
+            const float2 x01 = make_float2(v.x, v.y), x23 = make_float2(v.z, v.w);
+            if (RGB) {
 #pragma unroll
-            for (int kk = 0; kk < KMAX; ++kk) {
-                const float m = cc[kk];
-#pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    const float df = __fsub_rn(xv[p], m);
-                    acc[kk][p] = __fmaf_rn(df, df, acc[kk][p]);
+                for (int j = 0; j < 3; ++j) {
+                    const float2 w = sw2[c * 3 + j];
+                    rgb2[j][0] = pk_fma(w, x01, rgb2[j][0]);
+                    rgb2[j][1] = pk_fma(w, x23, rgb2[j][1]);
                 }
             }
+            const float2* cc = sc2 + (size_t)c * KMAX;
+#pragma unroll
+            for (int kk = 0; kk < KMAX; ++kk) {
+                const float2 m = cc[kk];
+                const float2 d0 = pk_sub(x01, m), d1 = pk_sub(x23, m);      // (A - B) ** 2 summed over channels
+                acc2[kk][0] = pk_fma(d0, d0, acc2[kk][0]);
+                acc2[kk][1] = pk_fma(d1, d1, acc2[kk][1]);
+            }
         }
+        float acc[KMAX][4];
+#pragma unroll
+        for (int kk = 0; kk < KMAX; ++kk) { acc[kk][0] = acc2[kk][0].x; acc[kk][1] = acc2[kk][0].y; acc[kk][2] = acc2[kk][1].x; acc[kk][3] = acc2[kk][1].y; }
+        float rgb[3][4];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { rgb[j][0] = rgb2[j][0].x; rgb[j][1] = rgb2[j][0].y; rgb[j][2] = rgb2[j][1].x; rgb[j][3] = rgb2[j][1].y; }
         float best[4], second[4];
 #pragma unroll
         for (int p = 0; p < 4; ++p) { best[p] = INFINITY; second[p] = INFINITY; ids[p] = 0; }
@@ -216,6 +241,20 @@ __global__ void __launch_bounds__(256) label_wide_kernel(LabelArgs a) {
                     if (d < best[p]) { second[p] = best[p]; best[p] = d; ids[p] = kk; }
                     else if (d < second[p]) { second[p] = d; }
                 }
+            }
+        }
+        if (RGB) {
+            const int y = (int)(pix / a.W), x = (int)(pix - (int64_t)y * a.W);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                float o[4];
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    float v = __fadd_rn(rgb[j][p], g.bias[j]);
+                    if (g.skip) v = __fadd_rn(v, torgb_skip_tap(g, g.skip + ((int64_t)b * 3 + j) * (hw >> 2), y, x + p));
+                    o[p] = v;
+                }
+                *reinterpret_cast<float4*>(g.out + ((int64_t)b * 3 + j) * hw + pix) = make_float4(o[0], o[1], o[2], o[3]);
             }
         }
         const int64_t n0 = (int64_t)b * hw + pix;       // flat [B,H,W] index of the first pixel
@@ -383,15 +422,22 @@ static int launch_native(const LabelArgs& a, cudaStream_t stream) {
     return SIS_OK;
 }
 
-template <int KMAX>
-static int launch_wide(const LabelArgs& a, cudaStream_t stream) {
-    size_t smem = ((size_t)a.C * KMAX + KMAX) * sizeof(float);
-    auto kern = label_wide_kernel<KMAX>;
+template <int KMAX, bool RGB>
+static int launch_wide_impl(const LabelArgs& a, const ToRgbArgs& g, cudaStream_t stream) {
+    size_t smem = ((size_t)a.C * KMAX * 2 + (RGB ? 6 * a.C : 0) + KMAX) * sizeof(float);
+    auto kern = label_wide_kernel<KMAX, RGB>;
     if (smem > 48 * 1024) SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t quads = (int64_t)a.H * a.W / 4 * a.batch;
-    kern<<<(unsigned)ceil_div64(quads, 256), 256, smem, stream>>>(a);
+    kern<<<(unsigned)ceil_div64(quads, 256), 256, smem, stream>>>(a, g);
     SIS_CHECK_LAUNCH();
     return SIS_OK;
+}
+template <int KMAX>
+static int launch_wide(const LabelArgs& a, const ToRgbArgs* g, cudaStream_t stream) {
+    if (g) return launch_wide_impl<KMAX, true>(a, *g, stream);
+    ToRgbArgs none;
+    memset(&none, 0, sizeof(none));
+    return launch_wide_impl<KMAX, false>(a, none, stream);
 }
 
 template <int KMAX>
@@ -408,25 +454,22 @@ static int launch_bilinear(const LabelArgs& a, cudaStream_t stream) {
 
 using namespace sis;
 
-extern "C" int sis_label_assign(const float* d_act, int batch, int channels, int h, int w, const float* d_centroids,
-                                int k, const uint32_t* d_cluster_class_bits, int n_class, int image_size, int mode,
-                                uint8_t* d_ids_u8, int64_t* d_ids_i64, uint8_t* d_masks, float* d_margin,
-                                unsigned long long* d_hist, void* stream_) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+namespace sis {
+
+int launch_label(const LabelArgs& a_in, int mode, const ToRgbArgs* fuse_rgb, bool* fused, cudaStream_t stream) {
+    LabelArgs a = a_in;
+    if (fused) *fused = false;
+    const int batch = a.batch, channels = a.C, h = a.H, w = a.W, k = a.k, n_class = a.n_class, image_size = a.S;
     SIS_REQUIRE(batch >= 0 && channels >= 1 && h >= 0 && w >= 0, "label_assign: bad shape");
     SIS_REQUIRE(k >= 1 && k <= 64, "label_assign: k must be in [1, 64] (got %d)", k);
     SIS_REQUIRE(n_class >= 0 && n_class <= 32, "label_assign: n_class must be <= 32");
     SIS_REQUIRE(mode == 0 || mode == 1, "label_assign: mode must be 0 or 1");
-    SIS_REQUIRE(!d_masks || (d_cluster_class_bits && image_size >= h && image_size >= w),
+    SIS_REQUIRE(!a.masks || (a.class_bits && image_size >= h && image_size >= w),
                 "label_assign: masks need class bits and image_size >= map size");
     SIS_REQUIRE((size_t)channels * 64 * 4 <= 200 * 1024 || k <= 32, "label_assign: centroid table does not fit shared memory");
     if ((int64_t)batch * h * w == 0) return SIS_OK;
-    SIS_REQUIRE(d_act && d_centroids, "label_assign: activations / centroids must be CUDA tensors (null pointer)");
+    SIS_REQUIRE(a.act && a.centroids, "label_assign: activations / centroids must be CUDA tensors (null pointer)");
     ProfScope prof(PROF_LABEL, stream);
-    LabelArgs a;
-    a.act = d_act; a.batch = batch; a.C = channels; a.H = h; a.W = w; a.centroids = d_centroids; a.k = k;
-    a.class_bits = d_cluster_class_bits; a.n_class = n_class; a.S = image_size;
-    a.ids_u8 = d_ids_u8; a.ids_i64 = d_ids_i64; a.masks = d_masks; a.margin = d_margin; a.hist = d_hist;
     if (mode == 1) {
         SIS_REQUIRE(image_size >= 1, "label_assign: image_size required for mode 1");
         if (k <= 4) return launch_bilinear<4>(a, stream);
@@ -435,27 +478,29 @@ extern "C" int sis_label_assign(const float* d_act, int batch, int channels, int
         if (k <= 32) return launch_bilinear<32>(a, stream);
         return launch_bilinear<64>(a, stream);
     }
-    const bool vec4 = ((h * w) % 4 == 0) && ((((uintptr_t)d_act) & 15) == 0);
-    const bool int_ratio = d_masks && (image_size % h == 0) && (image_size % w == 0) && (h == w);
-    uint8_t* tmp_ids = nullptr;
-    bool gather = d_masks && !int_ratio;
+    const bool vec4 = ((h * w) % 4 == 0) && ((((uintptr_t)a.act) & 15) == 0);
+    const bool int_ratio = a.masks && (image_size % h == 0) && (image_size % w == 0) && (h == w);
+    uint8_t* d_masks = a.masks;
+    bool gather = a.masks && !int_ratio;
     if (gather) {
         // non-integer ratio: masks are gathered from the ids afterwards
-        SIS_REQUIRE(d_ids_u8 != nullptr, "label_assign: non-integer resize ratio needs d_ids_u8");
-        tmp_ids = d_ids_u8;
+        SIS_REQUIRE(a.ids_u8 != nullptr, "label_assign: non-integer resize ratio needs d_ids_u8");
         a.masks = nullptr;
     }
     int st;
     // wide path: enough pixel quads to fill the GPU without slicing channels, integer (or no) mask replication,
     // rows that are a multiple of 4 pixels, k small enough for 4 x k register accumulators
     const int64_t quads = (int64_t)h * w / 4 * batch;
-    const bool wide_ok = vec4 && k <= 16 && w % 4 == 0 && quads >= (int64_t)kNumSMs * 512 &&
+    const bool wide_ok = vec4 && k <= 16 && w % 4 == 0 && quads >= (int64_t)kNumSMs * 512 && ((int64_t)h * w / 4) % 256 == 0 &&
                          (!a.masks || (int_ratio && ((((uintptr_t)a.masks) & 15) == 0))) &&
                          (!a.ids_u8 || ((((uintptr_t)a.ids_u8) & 3) == 0)) && (!a.margin || ((((uintptr_t)a.margin) & 15) == 0));
     if (wide_ok) {
-        if (k <= 4) st = launch_wide<4>(a, stream);
-        else if (k <= 8) st = launch_wide<8>(a, stream);
-        else st = launch_wide<16>(a, stream);
+        const ToRgbArgs* g = (fuse_rgb && fuse_rgb->x == a.act && fuse_rgb->C == channels && fuse_rgb->H == h && fuse_rgb->W == w &&
+                              fuse_rgb->batch == batch) ? fuse_rgb : nullptr;
+        if (k <= 4) st = launch_wide<4>(a, g, stream);
+        else if (k <= 8) st = launch_wide<8>(a, g, stream);
+        else st = launch_wide<16>(a, g, stream);
+        if (g && fused && st == SIS_OK) *fused = true;
     } else if (vec4) {
         if (k <= 4) st = launch_native<4, 4>(a, stream);
         else if (k <= 8) st = launch_native<8, 4>(a, stream);
@@ -470,10 +515,23 @@ extern "C" int sis_label_assign(const float* d_act, int batch, int channels, int
     SIS_PROPAGATE(st);
     if (gather) {
         masks_gather_kernel<<<flat_grid((int64_t)batch * image_size * image_size), 256, 0, stream>>>(
-            d_masks, tmp_ids, d_cluster_class_bits, n_class, batch, h, w, image_size);
+            d_masks, a.ids_u8, a.class_bits, n_class, batch, h, w, image_size);
         SIS_CHECK_LAUNCH();
     }
     return SIS_OK;
+}
+
+}  // namespace sis
+
+extern "C" int sis_label_assign(const float* d_act, int batch, int channels, int h, int w, const float* d_centroids,
+                                int k, const uint32_t* d_cluster_class_bits, int n_class, int image_size, int mode,
+                                uint8_t* d_ids_u8, int64_t* d_ids_i64, uint8_t* d_masks, float* d_margin,
+                                unsigned long long* d_hist, void* stream_) {
+    LabelArgs a;
+    a.act = d_act; a.batch = batch; a.C = channels; a.H = h; a.W = w; a.centroids = d_centroids; a.k = k;
+    a.class_bits = d_cluster_class_bits; a.n_class = n_class; a.S = image_size;
+    a.ids_u8 = d_ids_u8; a.ids_i64 = d_ids_i64; a.masks = d_masks; a.margin = d_margin; a.hist = d_hist;
+    return launch_label(a, mode, nullptr, nullptr, (cudaStream_t)stream_);
 }
 
 extern "C" int sis_class_masks_from_ids(const int64_t* d_ids, int64_t n, const uint32_t* d_cluster_class_bits, int k,

@@ -58,8 +58,9 @@ def build_latent_and_noise_generator(autoencoder, config: Dict, seed=1) -> Itera
 
 
 def generate_images(batch: Latents, autoencoder, device: str = 'cuda', mean_latent: Optional[torch.Tensor] = None,
-                    capture_layers=None) -> Tuple[Dict[int, torch.Tensor], torch.Tensor]:
-    """(activations, image) exactly as utils/dataset_creation.py:40-58: truncation 0.7 iff mean_latent is given."""
+                    capture_layers=None, label_jobs=None) -> Tuple[Dict[int, torch.Tensor], torch.Tensor]:
+    """(activations, image) exactly as utils/dataset_creation.py:40-58: truncation 0.7 iff mean_latent is given.
+    `capture_layers` / `label_jobs` are forwarded to the generator (extensions, see Generator.forward)."""
     if not isinstance(batch, Latents):
         raise NotImplementedError('the encoder path (dict batches) is outside the hot path (SURVEY.md §2 row 16)')
     latents = batch.to(device)
@@ -67,6 +68,8 @@ def generate_images(batch: Latents, autoencoder, device: str = 'cuda', mean_late
     kwargs = {}
     if capture_layers is not None:
         kwargs['capture_layers'] = capture_layers
+    if label_jobs is not None:
+        kwargs['label_jobs'] = label_jobs
     with torch.no_grad():
         image, activations = decoder(
             [latents.latent], input_is_latent=False, noise=latents.noise, return_intermediate_activations=True,
@@ -113,8 +116,9 @@ class LabelledPairGenerator:
 
     def __init__(self, generator: Generator, segmenter: ClusterSegmenter, config: Dict, seed: int = 1,
                  mean_latent: Optional[torch.Tensor] = None, rank: int = 0, world_size: int = 1,
-                 capture_only_labelled: bool = False):
+                 capture_only_labelled: bool = False, fused_labelling: bool = True):
         self.generator, self.segmenter = generator, segmenter
+        self.fused_labelling = fused_labelling
         self.config, self.seed, self.mean_latent = config, seed, mean_latent
         self.rank, self.world_size = rank, world_size
         # key 0 must always be present: the reference reads the batch size from activations[0]
@@ -125,9 +129,16 @@ class LabelledPairGenerator:
     def __iter__(self) -> Iterator[LabelledBatch]:
         device = self.generator.input.input.device
         for idx, latents in sharded_latent_stream(self.generator, self.config, self.seed, self.rank, self.world_size):
-            acts, image = generate_images(latents, self.generator, device=device, mean_latent=self.mean_latent,
-                                          capture_layers=self.capture_layers)
-            masks = self.segmenter.prepare_image_segmentation(acts)
+            if self.fused_labelling:
+                # labelling runs inside the generator's native call (one pass over each labelled activation)
+                jobs = self.segmenter.make_label_jobs(self.generator, latents.latent.shape[0])
+                acts, image = generate_images(latents, self.generator, device=device, mean_latent=self.mean_latent,
+                                              capture_layers=self.capture_layers, label_jobs=jobs)
+                masks = self.segmenter._as_predicted(self.segmenter.jobs_to_stacked(jobs))
+            else:
+                acts, image = generate_images(latents, self.generator, device=device, mean_latent=self.mean_latent,
+                                              capture_layers=self.capture_layers)
+                masks = self.segmenter.prepare_image_segmentation(acts)
             masks = self.segmenter.merge_sub_images(masks)
             self.stats['pairs'] += image.shape[0]
             self.stats['batches'] += 1
@@ -158,8 +169,14 @@ class LabelledPairGenerator:
             slot = slots[n % (depth + 1)]
             slot['z'].copy_(latents.latent)
             lat = Latents(slot['z'].to(device, non_blocking=True), latents.noise)
-            acts, image = generate_images(lat, g, device=device, mean_latent=self.mean_latent, capture_layers=self.capture_layers)
-            stacked = seg.label_layers_stacked(acts)
+            if self.fused_labelling:
+                jobs = seg.make_label_jobs(g, B)
+                acts, image = generate_images(lat, g, device=device, mean_latent=self.mean_latent, capture_layers=self.capture_layers,
+                                              label_jobs=jobs)
+                stacked = seg.jobs_to_stacked(jobs)
+            else:
+                acts, image = generate_images(lat, g, device=device, mean_latent=self.mean_latent, capture_layers=self.capture_layers)
+                stacked = seg.label_layers_stacked(acts)
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream(device))
             with torch.cuda.stream(copy_stream):

@@ -94,6 +94,30 @@ def label_assign(act: torch.Tensor, centroids: torch.Tensor, class_bits: Optiona
     return ids64, {'masks': masks, 'margin': margin, 'ids_u8': ids8}
 
 
+class LabelJobSpec:
+    """One labelling job to run INSIDE `Generator.forward` (see `sis_label_job`): the activation is labelled right after
+    it is produced, and shares its single HBM read with the ToRGB of the same tensor where shapes allow."""
+
+    def __init__(self, activation_idx: int, centroids: torch.Tensor, class_bits: Optional[torch.Tensor] = None, n_class: int = 0,
+                 image_size: int = 0, masks: Optional[torch.Tensor] = None, ids_u8: Optional[torch.Tensor] = None,
+                 ids_i64: Optional[torch.Tensor] = None, margin: Optional[torch.Tensor] = None, hist: Optional[torch.Tensor] = None,
+                 names: Optional[List[str]] = None):
+        self.activation_idx, self.centroids, self.class_bits, self.n_class = activation_idx, centroids, class_bits, n_class
+        self.image_size, self.masks, self.ids_u8, self.ids_i64, self.margin, self.hist = image_size, masks, ids_u8, ids_i64, margin, hist
+        self.names = names
+
+    def fill(self, c_job):
+        c_job.activation_idx = int(self.activation_idx)
+        c_job.d_centroids = self.centroids.data_ptr()
+        c_job.k = int(self.centroids.shape[0])
+        c_job.d_cluster_class_bits = self.class_bits.data_ptr() if self.class_bits is not None else None
+        c_job.n_class = int(self.n_class)
+        c_job.image_size = int(self.image_size)
+        for name in ('ids_u8', 'ids_i64', 'masks', 'margin', 'hist'):
+            t = getattr(self, name)
+            setattr(c_job, 'd_' + name, t.data_ptr() if t is not None else None)
+
+
 def extract_centroids_from_pickle(path) -> Dict[str, numpy.ndarray]:
     """Read a reference catalog pickle (`catalogs/{k}.pkl`: {str(layer): FactorCatalog, 'id_to_size_map': ...},
     scf/create_semantic_segmentation.py:123-137) WITHOUT importing sklearn or the reference: every unknown class is
@@ -290,6 +314,32 @@ class ClusterSegmenter(BaseDatasetSegmenter):
             size = a.shape[-1] if (native or a.shape[-1] >= self.image_size) else self.image_size
             out[layer_id] = self._label_layer(layer_id, a, class_label_map, size)
         return out
+
+    def make_label_jobs(self, generator, batch: int, class_label_map=None) -> List[LabelJobSpec]:
+        """Jobs for `Generator.forward(..., label_jobs=...)`: one per catalog layer, masks written at image size.
+        Read the results with `jobs_to_stacked(jobs)` / `_as_predicted(...)` after the forward."""
+        class_label_map = class_label_map if class_label_map is not None else self.class_label_map
+        device = generator.input.input.device
+        jobs = []
+        for layer_id in self.catalog:
+            cat = self.catalog[layer_id]
+            c, res = generator.activation_shape(int(layer_id))
+            names, bits = self._class_bits(layer_id, class_label_map, device)
+            size = self.image_size if res < self.image_size else res
+            hist = self.cluster_pixel_counts.get(layer_id)
+            if hist is None or hist.device != device:
+                hist = torch.zeros(cat.k, dtype=torch.int64, device=device)
+                self.cluster_pixel_counts[layer_id] = hist
+            masks = torch.empty((len(names), batch, size, size), dtype=torch.uint8, device=device)
+            need_u8 = size % res != 0
+            ids8 = torch.empty((batch, res, res), dtype=torch.uint8, device=device) if need_u8 else None
+            jobs.append(LabelJobSpec(int(layer_id), cat.centroids_on(device), bits, len(names), size, masks=masks, ids_u8=ids8,
+                                     hist=hist, names=names))
+        return jobs
+
+    @staticmethod
+    def jobs_to_stacked(jobs: List[LabelJobSpec]):
+        return {str(j.activation_idx): (j.names, j.masks) for j in jobs}
 
     @staticmethod
     def _as_predicted(stacked) -> PredictedClusters:

@@ -267,9 +267,11 @@ class Generator(nn.Module):
     # ------------------------------------------------------------------ forward
     def forward(self, styles, return_latents=False, inject_index=None, truncation=1, truncation_latent=None,
                 input_is_latent=False, noise=None, randomize_noise=True, return_intermediate_activations=False,
-                capture_layers=None):
-        """Same arguments / returns as the reference (model.py:479-561).  `capture_layers` (optional, not in the
-        reference) restricts which activation indices are materialised when `return_intermediate_activations`."""
+                capture_layers=None, label_jobs=None):
+        """Same arguments / returns as the reference (model.py:479-561).  Two optional extensions (not in the reference):
+        `capture_layers` restricts which activation indices are materialised when `return_intermediate_activations`;
+        `label_jobs` (a list of `labelling.LabelJobSpec`) labels activations inside the same native call, fused with
+        the ToRGB pass where both read the same tensor."""
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             # The fused plan is inference-only.  Running silently without a graph would be a wrong gradient.
             raise RuntimeError('Generator.forward of synthesis_in_style_b200 is inference-only: call it under '
@@ -360,6 +362,16 @@ class Generator(nn.Module):
             args.d_activations = ctypes.cast(act_ptrs, ctypes.POINTER(ctypes.c_void_p))
         else:
             args.d_activations = None
+        c_jobs = None
+        if label_jobs:
+            c_jobs = (_lib.LabelJob * len(label_jobs))()
+            for cj, spec in zip(c_jobs, label_jobs):
+                spec.fill(cj)
+            args.n_label_jobs = len(label_jobs)
+            args.label_jobs = ctypes.cast(c_jobs, ctypes.POINTER(_lib.LabelJob))
+        else:
+            args.n_label_jobs = 0
+            args.label_jobs = None
         if self.precision not in PRECISIONS:
             raise RuntimeError(f'unknown precision {self.precision!r} (use one of {sorted(PRECISIONS)})')
         args.precision = PRECISIONS[self.precision]

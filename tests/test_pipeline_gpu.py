@@ -125,3 +125,21 @@ def test_iter_host_equals_device_iteration(cuda_device):
             assert hb.class_names[layer] == list(NAMES)
             for j, cn in enumerate(hb.class_names[layer]):
                 assert torch.equal(hb.masks[layer][j].bool(), ref[i].masks[layer][cn].cpu())
+
+
+def test_in_forward_labelling_equals_separate_calls(cuda_device):
+    """label_jobs inside Generator.forward (fused ToRGB + labelling pass on the large maps) gives the same image, masks,
+    ids and histograms as the separate sis_label_assign launches."""
+    layers = ['8', '9', '12', '13']
+    spec, sd, g, seg, cents = make_setup(256, layers, cuda_device)
+    cfg = {'batch_size': 4, 'latent_size': 512}
+    a = next(iter(dc.LabelledPairGenerator(g, seg, cfg, seed=3, fused_labelling=False)))
+    counts_a = {k: v.clone() for k, v in seg.cluster_pixel_counts.items()}
+    for v in seg.cluster_pixel_counts.values():
+        v.zero_()
+    b = next(iter(dc.LabelledPairGenerator(g, seg, cfg, seed=3, fused_labelling=True)))
+    assert torch.equal(a.image, b.image)
+    for layer in layers:
+        for cn in NAMES:
+            assert torch.equal(a.masks[layer][cn], b.masks[layer][cn]), (layer, cn)
+        assert torch.equal(counts_a[layer], seg.cluster_pixel_counts[layer])
