@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(256) upfirdn2d_pair_kernel(float* __restrict__
     constexpr int TIN_WP = TIN_W + TIN_W / PADG + 1;
     __shared__ float sk[K][K];
     constexpr int NBUF = (DOWN == 2) ? 1 : 2;               // the decimating tile (35 KB) is single-buffered
-    __shared__ float2 sxbuf[NBUF][TIN_H][TIN_WP];            // double-buffered: tile i+1 is in flight while tile i is computed
+    extern __shared__ __align__(16) float2 sx_dyn[];         // [NBUF][TIN_H][TIN_WP], double-buffered: tile i+1 is in flight
+    float2 (*sxbuf)[TIN_H][TIN_WP] = reinterpret_cast<float2 (*)[TIN_H][TIN_WP]>(sx_dyn);   // while tile i is computed
 #define SXC(c) ((c) + (c) / PADG)
 
     for (int t = threadIdx.x; t < K * K; t += 256) {
@@ -274,12 +275,23 @@ __global__ void __launch_bounds__(256) upfirdn2d_pair_kernel(float* __restrict__
 template <int UP, int DOWN, int K>
 static void launch_tiled(float* out, const float* in, const float* kernel, const UpfirdnParams& p,
                          cudaStream_t stream) {
-    constexpr int TH = (DOWN == 2) ? 16 : 32, TW = 64;   // DOWN == 2: 2 x 34 x 147 x 8 B = 80 KB would not fit, see below
+    // tall tiles for the up == down == 1 FIR (4 rows per thread: the per-tile overheads and the window loads are
+    // amortised over 32 outputs per thread); 32 rows for the interpolating modes, 16 for the decimating one
+    constexpr int TH = (DOWN == 2) ? 16 : (UP == 1 ? 64 : 32), TW = 64;
+    constexpr int TIN_H = ((TH - 1) * DOWN + K - 1) / UP + 1, TIN_W = ((TW - 1) * DOWN + K - 1) / UP + 1;
+    constexpr int PADG = 4 * DOWN / UP, TIN_WP = TIN_W + TIN_W / PADG + 1, NBUF = (DOWN == 2) ? 1 : 2;
+    constexpr int SMEM = NBUF * TIN_H * TIN_WP * 8;
+    auto kern = upfirdn2d_pair_kernel<UP, DOWN, K, TH>;
+    static int blocks_per_sm = 0;
+    if (!blocks_per_sm) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, 256, SMEM) != cudaSuccess || blocks_per_sm < 1) blocks_per_sm = 1;
+    }
     int tiles_x = ceil_div(p.out_w, TW), tiles_y = ceil_div(p.out_h, TH);
     int64_t total = (int64_t)tiles_x * tiles_y * ((p.major + 1) / 2);
-    int64_t cap = (int64_t)kNumSMs * 4;
+    int64_t cap = (int64_t)kNumSMs * blocks_per_sm;      // exactly one resident wave of persistent blocks
     int grid = (int)(total < cap ? total : cap);
-    upfirdn2d_pair_kernel<UP, DOWN, K, TH><<<grid, 256, 0, stream>>>(out, in, kernel, p, tiles_x, tiles_y);
+    kern<<<grid, 256, SMEM, stream>>>(out, in, kernel, p, tiles_x, tiles_y);
 }
 
 }  // namespace sis
