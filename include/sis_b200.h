@@ -143,6 +143,33 @@ typedef struct {
 SIS_API int sis_generator_forward(sis_generator* g, const sis_forward_args* args, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
+ * Stand-alone layers — the reference's module-level forwards outside the fused plan (same kernels, one layer per call,
+ * weights repacked per call; NOT re-entrant, like the reference's single-threaded use).  All tensors fp32 on device.
+ *   sis_modulated_conv2d   ModulatedConv2d.forward (model.py:237-278, 3x3 only) and, with noise / act_bias /
+ *                          activate, StyledConv.forward (model.py:336-342).  x [B,Cin,res,res]; weight [1,Cout,Cin,3,3];
+ *                          mod_weight [Cin,style_dim]; style [B,style_dim]; upsample needs blur_kernel [4,4] and
+ *                          writes [B,Cout,2res,2res]; noise [1 or B,1,R,R] (stride 0 or R*R) with its scalar weight.
+ *   sis_to_rgb             ToRGB.forward (model.py:355-364): 1x1 modulated conv (no demod) + bias [3] + upsampled skip
+ *                          [B,3,res/2,res/2] (up_kernel [4,4]) -> [B,3,res,res].
+ *   sis_equal_linear       EqualLinear.forward (model.py:152-162), optional fused leaky ReLU.
+ *   sis_pixel_norm         PixelNorm.forward (model.py:19-20) over rows of `dim`.
+ *   sis_noise_injection    NoiseInjection.forward (model.py:287-292): x + weight * noise.
+ * ------------------------------------------------------------------------------------------------------- */
+SIS_API int sis_modulated_conv2d(const float* d_x, int batch, int cin, int res, const float* d_weight, int cout,
+                                 const float* d_mod_weight, const float* d_mod_bias, int style_dim, const float* d_style,
+                                 int demodulate, int upsample, const float* d_blur_kernel, const float* d_noise,
+                                 int64_t noise_batch_stride, const float* d_noise_weight, const float* d_act_bias, int activate,
+                                 float* d_out, int precision, void* stream);
+SIS_API int sis_to_rgb(const float* d_x, int batch, int cin, int res, const float* d_weight, const float* d_mod_weight,
+                       const float* d_mod_bias, int style_dim, const float* d_style, const float* d_bias, const float* d_skip,
+                       const float* d_up_kernel, float* d_out, void* stream);
+SIS_API int sis_equal_linear(const float* d_x, int64_t rows, int in_dim, const float* d_weight, const float* d_bias, int out_dim,
+                             float lr_mul, int fused_lrelu, float* d_out, void* stream);
+SIS_API int sis_pixel_norm(const float* d_x, float* d_out, int64_t rows, int dim, void* stream);
+SIS_API int sis_noise_injection(const float* d_x, const float* d_noise, int64_t noise_batch_stride, const float* d_weight, int batch,
+                                int channels, int h, int w, float* d_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
  * Labelling — replaces, on the device and in one pass per layer,
  *   FactorCatalog.predict / pairwise_distance  scf/segmentation/gan_local_edit/factor_catalog.py:47-75
  *   predict_clusters                           scf/segmentation/base_cluster_based_dataset_segmenter.py:119-138

@@ -66,6 +66,13 @@ _SIGNATURES = {
     'sis_generator_activation_shape': (c_int, [c_void_p, c_int, POINTER(c_int), POINTER(c_int)]),
     'sis_generator_style': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     'sis_generator_forward': (c_int, [c_void_p, POINTER(ForwardArgs), c_void_p]),
+    'sis_modulated_conv2d': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
+                                     c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    'sis_to_rgb': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_void_p, c_void_p]),
+    'sis_equal_linear': (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p]),
+    'sis_pixel_norm': (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    'sis_noise_injection': (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'sis_label_assign': (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_int, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'sis_class_masks_from_ids': (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p]),

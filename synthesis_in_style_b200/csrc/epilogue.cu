@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(256) blur_noise_act_kernel(BlurActArgs a) {
         if (oy < a.OH) {
             const int b = (int)(plane / a.C), c = (int)(plane % a.C);
             const float bias = a.bias ? a.bias[c] : 0.0f;
-            const float* nz = a.noise + (int64_t)b * a.noise_bstride + (int64_t)oy * a.OW;
+            const float* nz = a.noise ? a.noise + (int64_t)b * a.noise_bstride + (int64_t)oy * a.OW : nullptr;
             float res[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(256) blur_noise_act_kernel(BlurActArgs a) {
 #pragma unroll
                     for (int kx = 0; kx < 4; ++kx) v = __fmaf_rn(sx[ty + ky][rx + kx], sk[ky][kx], v);
                 const int ox = x0 + rx;
-                if (ox < a.OW) {
-                    v = __fadd_rn(v, __fmul_rn(a.noise_w, nz[ox]));
+                if (ox < a.OW && a.act) {
+                    if (nz) v = __fadd_rn(v, __fmul_rn(a.noise_w, nz[ox]));
                     v = __fadd_rn(v, bias);
                     v = lrelu_scale(v, 0.2f, 1.41421356237309504880f);
                 }

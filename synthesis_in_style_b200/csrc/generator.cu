@@ -441,7 +441,7 @@ extern "C" int sis_generator_forward(sis_generator* g, const sis_forward_args* a
                 BlurActArgs bl;
                 bl.in = g->upconv_tmp.as<float>(); bl.out = y; bl.planes = (int64_t)B * c.cout; bl.C = c.cout; bl.IH = th; bl.IW = th;
                 bl.OH = c.res_out; bl.OW = c.res_out; bl.blur_k = c.blur_k.as<float>(); bl.noise = noise; bl.noise_bstride = nstride;
-                bl.noise_w = c.noise_w; bl.bias = c.act_bias.as<float>();
+                bl.noise_w = c.noise_w; bl.bias = c.act_bias.as<float>(); bl.act = 1;
                 ProfScope prof(PROF_BLUR_SIMT, stream);
                 SIS_PROPAGATE(launch_blur_noise_act(bl, stream));
             }

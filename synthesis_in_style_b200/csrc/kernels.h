@@ -30,6 +30,7 @@ struct ModConvSimtArgs {
 struct BlurActArgs {
     const float* in; float* out; int64_t planes; int C, IH, IW, OH, OW;
     const float* blur_k; const float* noise; int64_t noise_bstride; float noise_w; const float* bias;
+    int act;   // 1: + noise + bias, lrelu*sqrt2 (StyledConv); 0: blur only
 };
 
 struct ToRgbArgs {

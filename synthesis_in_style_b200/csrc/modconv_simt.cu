@@ -109,8 +109,7 @@ __global__ void __launch_bounds__(256) modconv3x3_simt_kernel(ModConvSimtArgs a)
             float v = __fmul_rn(acc[c][p], d);
             if (a.fuse_act) {
                 // NoiseInjection (model.py:292) then FusedLeakyReLU (fused_bias_act_kernel.cu:26-47)
-                const float nz = a.noise[(int64_t)b * a.noise_bstride + (int64_t)oy * a.OW + ox];
-                v = __fadd_rn(v, __fmul_rn(a.noise_w, nz));
+                if (a.noise) v = __fadd_rn(v, __fmul_rn(a.noise_w, a.noise[(int64_t)b * a.noise_bstride + (int64_t)oy * a.OW + ox]));
                 v = __fadd_rn(v, bias);
                 v = lrelu_scale(v, 0.2f, 1.41421356237309504880f);
             }

@@ -141,7 +141,8 @@ struct TcKernelArgs {
     TcSubProblem sub[4];
     int nsub, total_tiles;
     int batch, cin, cout, b_tiles, n_tiles, kchunks;
-    int mode;                   // 0 plain (fused activation), 1 transposed-conv phase (demod only)
+    int mode;                   // 0 plain (fused noise + bias [+ activation]), 1 transposed-conv phase (demod only)
+    int act;                    // mode 0: apply lrelu(0.2)*sqrt2 (StyledConv) or not (bare ModulatedConv2d)
     int im2col;                 // A tiles are 128 consecutive pixels of the flattened (b, y, x) output grid (TMA im2col mode)
     int interleave_units;       // > 0: the 4 transposed-conv phases are interleaved, each padded to this many (pair) tiles
     const float* demod; const float* noise; int64_t noise_bstride; float noise_w; const float* bias;
@@ -432,7 +433,7 @@ modconv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ T
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
             const float* dm = a.demod + (int64_t)(valid ? b : 0) * a.cout + c.n0;
             float nz = 0.0f;
-            if (a.mode == 0 && valid) nz = __fmul_rn(a.noise_w, a.noise[(int64_t)b * a.noise_bstride + (int64_t)oy * a.out_w + ox]);
+            if (a.mode == 0 && valid && a.noise) nz = __fmul_rn(a.noise_w, a.noise[(int64_t)b * a.noise_bstride + (int64_t)oy * a.out_w + ox]);
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 uint32_t r[32];
@@ -449,8 +450,8 @@ modconv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ T
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             float x = __fadd_rn(v[j], nz);
-                            x = __fadd_rn(x, __ldg(a.bias + c.n0 + c0 + j));
-                            x = lrelu_scale(x, 0.2f, 1.41421356237309504880f);
+                            if (a.bias) x = __fadd_rn(x, __ldg(a.bias + c.n0 + c0 + j));
+                            if (a.act) x = lrelu_scale(x, 0.2f, 1.41421356237309504880f);
                             v[j] = x;
                             dst[(int64_t)j * plane] = x;       // lanes = consecutive x: coalesced per channel
                         }
@@ -514,6 +515,7 @@ struct BlurSplitArgs {
     float* out_f32; int OH, OW, C, batch; // [B][C][OH][OW]
     const float* blur_k; const float* noise; int64_t noise_bstride; float noise_w; const float* bias;
     const float* s_next; bf16* next_hi; bf16* next_lo;   // [B][OH][OW][C]
+    int act;                              // apply lrelu(0.2)*sqrt2 (StyledConv) or blur only (bare ModulatedConv2d)
 };
 constexpr int BS_TH = 8, BS_TW = 16, BS_C = 64;
 constexpr int BS_IH = BS_TH + 3, BS_IW = BS_TW + 3;
@@ -591,7 +593,7 @@ __global__ void __launch_bounds__(256, 3) blur_act_split_kernel(BlurSplitArgs a)
             }
             if (tid < BS_TH * BS_TW) {
                 const int oy = y0 + (tid >> 4), ox = x0 + (tid & 15);
-                snz[tid] = (oy < a.OH && ox < a.OW) ? a.noise_w * __ldg(a.noise + (int64_t)b * a.noise_bstride + (int64_t)oy * a.OW + ox) : 0.0f;
+                snz[tid] = (a.noise && oy < a.OH && ox < a.OW) ? a.noise_w * __ldg(a.noise + (int64_t)b * a.noise_bstride + (int64_t)oy * a.OW + ox) : 0.0f;
             }
         }
         cp_async_wait_all();
@@ -602,7 +604,7 @@ __global__ void __launch_bounds__(256, 3) blur_act_split_kernel(BlurSplitArgs a)
         {
             const int px = warp * 2;
             const bool chok = c0 + 2 * lane < a.C;
-            const float2 bias = chok ? *reinterpret_cast<const float2*>(a.bias + c0 + 2 * lane) : make_float2(0.f, 0.f);
+            const float2 bias = (chok && a.bias) ? *reinterpret_cast<const float2*>(a.bias + c0 + 2 * lane) : make_float2(0.f, 0.f);
             const float2 sn = (a.s_next && chok) ? *reinterpret_cast<const float2*>(a.s_next + (int64_t)b * a.C + c0 + 2 * lane) : make_float2(0.f, 0.f);
             const bool colok0 = chok && x0 + px < a.OW, colok1 = chok && x0 + px + 1 < a.OW;
             // NHWC element offset of (b, y0, x0+px, c0+2*lane); advances by OW*C per row, C per column
@@ -647,8 +649,10 @@ __global__ void __launch_bounds__(256, 3) blur_act_split_kernel(BlurSplitArgs a)
                         }
                         v = fadd2(fadd2(v, splat2(snz[py * BS_TW + px + cx])), bias);
                         // lrelu(x)*sqrt2 = max(x*sqrt2, x*0.2*sqrt2)
-                        const float2 p = fmul2(v, splat2(1.41421356237309504880f)), q = fmul2(v, splat2(0.2f * 1.41421356237309504880f));
-                        v = make_float2(fmaxf(p.x, q.x), fmaxf(p.y, q.y));
+                        if (a.act) {
+                            const float2 p = fmul2(v, splat2(1.41421356237309504880f)), q = fmul2(v, splat2(0.2f * 1.41421356237309504880f));
+                            v = make_float2(fmaxf(p.x, q.x), fmaxf(p.y, q.y));
+                        }
                         res[cx][py] = v;
                         if (a.s_next && rowok && (cx ? colok1 : colok0)) {
                             const float2 xs = fmul2(v, sn);
@@ -956,6 +960,7 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
     a.b_tiles = b_tiles; a.n_tiles = n_tiles;
     a.demod = call.demod; a.noise = call.noise; a.noise_bstride = call.noise_bstride; a.noise_w = call.noise_w; a.bias = call.bias;
     a.error = ws.d_error;
+    a.act = call.act ? 1 : 0;
     a.im2col = im2col ? 1 : 0;
     int tiles = 0;   // tiles (CG = 1) or pair tiles (CG = 2)
     auto units = [&](TcSubProblem& s) {
@@ -1042,6 +1047,7 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
         bs.out_f32 = call.out_f32; bs.OH = call.res_out; bs.OW = call.res_out; bs.C = call.cout; bs.batch = B;
         bs.blur_k = call.blur_k; bs.noise = call.noise; bs.noise_bstride = call.noise_bstride; bs.noise_w = call.noise_w; bs.bias = call.bias;
         bs.s_next = call.s_next; bs.next_hi = (bf16*)ws.a_hi[call.out_slot]; bs.next_lo = (bf16*)ws.a_lo[call.out_slot];
+        bs.act = call.act ? 1 : 0;
         SIS_REQUIRE(bs.C % 32 == 0, "tc_modconv: the blur pass needs Cout %% 32 == 0 (got %d)", bs.C);
         static int blocks_per_sm[2] = {0, 0};
         const int sep = call.blur_separable ? 1 : 0;

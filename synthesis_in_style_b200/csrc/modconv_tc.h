@@ -29,8 +29,9 @@ struct TcWorkspace {
 struct TcConvCall {
     int batch, cin, cout, res_in, res_out; bool up;
     const float* demod;        // [B, cout]
-    const float* noise; int64_t noise_bstride; float noise_w;
-    const float* bias;         // [cout]
+    const float* noise; int64_t noise_bstride; float noise_w;   // noise may be null (= no noise)
+    const float* bias;         // [cout] or null
+    bool act = true;           // lrelu(0.2)*sqrt2 after noise + bias (StyledConv); false = bare ModulatedConv2d
     const float* blur_k;       // [4,4] (up only)
     bool blur_separable;       // blur_k is an outer product (checked on the host at prepare time)
     float* out_f32;            // [B, cout, res_out, res_out] NCHW (the captured activation)

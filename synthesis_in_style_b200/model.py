@@ -58,16 +58,41 @@ def make_kernel(k):
     return k
 
 
+def _stream(t):
+    return _lib.current_stream_ptr(t.device)
+
+
+def _f32c(t, name):
+    _lib.require_cuda(t, name)
+    return t.contiguous().float()
+
+
 class PixelNorm(nn.Module):
-    """Placeholder for index 0 of `style` (model.py:15-20); evaluated inside the fused style-MLP launch."""
+    """model.py:15-20.  Inside `Generator.forward` it is part of the fused style-MLP launch; stand-alone it runs
+    `sis_pixel_norm` (normalisation over dim 1 of a [N, D] input, the only way the generator uses it)."""
+
+    def forward(self, input):
+        x = _f32c(input, 'input')
+        if x.dim() != 2:
+            raise NotImplementedError('PixelNorm is implemented for [N, D] inputs (the style MLP)')
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().sis_pixel_norm(_lib.ptr(x), _lib.ptr(out), x.shape[0], x.shape[1], _stream(x)))
+        return out
 
 
 class _FirBuffer(nn.Module):
-    """Holds a `kernel` buffer under the reference's name (`blur.kernel`, `upsample.kernel`)."""
+    """Holds a `kernel` buffer under the reference's name (`blur.kernel`, `upsample.kernel`) and applies it like the
+    reference's `Blur` (pad given) / `Upsample` (factor 2) modules when called (model.py:34-52, 76-92)."""
 
-    def __init__(self, taps, gain):
+    def __init__(self, taps, gain, up=1, pad=(0, 0)):
         super().__init__()
         self.register_buffer('kernel', make_kernel(taps) * gain)
+        self.up, self.pad = up, pad
+
+    def forward(self, input):
+        from .op import upfirdn2d
+        return upfirdn2d(input, self.kernel, up=self.up, down=1, pad=self.pad)
 
 
 class EqualLinear(nn.Module):
@@ -81,6 +106,18 @@ class EqualLinear(nn.Module):
         self.scale = (1 / math.sqrt(in_dim)) * lr_mul
         self.lr_mul = lr_mul
 
+    def forward(self, input):
+        """model.py:152-162 through `sis_equal_linear` (fused bias + leaky ReLU when `activation` is set)."""
+        x = _f32c(input, 'input')
+        x2 = x.reshape(-1, x.shape[-1])
+        out = torch.empty(x2.shape[0], self.weight.shape[0], device=x.device)
+        w = _f32c(self.weight.detach(), 'weight')
+        b = _f32c(self.bias.detach(), 'bias') if self.bias is not None else None
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().sis_equal_linear(_lib.ptr(x2), x2.shape[0], x2.shape[1], _lib.ptr(w), _lib.ptr(b), w.shape[0],
+                                                    float(self.lr_mul), int(bool(self.activation)), _lib.ptr(out), _stream(x)))
+        return out.reshape(*x.shape[:-1], w.shape[0])
+
 
 class ModulatedConv2d(nn.Module):
     """Parameters of model.py:182-229."""
@@ -92,11 +129,48 @@ class ModulatedConv2d(nn.Module):
         self.kernel_size, self.in_channel, self.out_channel = kernel_size, in_channel, out_channel
         self.upsample, self.demodulate = upsample, demodulate
         if upsample:
-            self.blur = _FirBuffer(blur_kernel, 4)   # Blur(..., upsample_factor=2): kernel * factor**2
+            # Blur(kernel, pad=(pad0, pad1), upsample_factor=2), model.py:201-207: p = (4 - 2) - (3 - 1) = 0 -> pad (1, 1)
+            p = (len(blur_kernel) - 2) - (kernel_size - 1)
+            self.blur = _FirBuffer(blur_kernel, 4, up=1, pad=((p + 1) // 2 + 1, p // 2 + 1))
         self.scale = 1 / math.sqrt(in_channel * kernel_size ** 2)
         self.padding = kernel_size // 2
         self.weight = nn.Parameter(torch.randn(1, out_channel, in_channel, kernel_size, kernel_size))
         self.modulation = EqualLinear(style_dim, in_channel, bias_init=1)
+        self.precision = 'bf16x3'
+
+    def _run(self, input, style, noise=None, noise_weight=None, act_bias=None, activate=False):
+        """One `sis_modulated_conv2d` call (model.py:237-278; with noise / bias / activation: StyledConv, :336-342)."""
+        if self.kernel_size != 3:
+            raise NotImplementedError('stand-alone ModulatedConv2d runs 3x3 kernels; the 1x1 case is ToRGB.forward')
+        x, st = _f32c(input, 'input'), _f32c(style, 'style')
+        b, cin, h, w_ = x.shape
+        if h != w_ or cin != self.in_channel:
+            raise RuntimeError(f'expected a square [B, {self.in_channel}, H, H] input')
+        res_out = 2 * h if self.upsample else h
+        out = torch.empty(b, self.out_channel, res_out, res_out, device=x.device)
+        nz, nstride = None, 0
+        if noise is not None:
+            nz = _f32c(noise, 'noise')
+            if nz.numel() == res_out * res_out:
+                nstride = 0
+            elif nz.numel() == b * res_out * res_out:
+                nstride = res_out * res_out
+            else:
+                raise RuntimeError(f'noise must be [1,1,{res_out},{res_out}] or [{b},1,{res_out},{res_out}]')
+        wt = _f32c(self.weight.detach(), 'weight')
+        mw, mb = _f32c(self.modulation.weight.detach(), 'modulation.weight'), _f32c(self.modulation.bias.detach(), 'modulation.bias')
+        blur = _f32c(self.blur.kernel, 'blur.kernel') if self.upsample else None
+        nw = _f32c(noise_weight.detach(), 'noise.weight') if noise_weight is not None else None
+        ab = _f32c(act_bias.detach(), 'activate.bias') if act_bias is not None else None
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().sis_modulated_conv2d(
+                _lib.ptr(x), b, cin, h, _lib.ptr(wt), self.out_channel, _lib.ptr(mw), _lib.ptr(mb), mw.shape[1], _lib.ptr(st),
+                int(self.demodulate), int(self.upsample), _lib.ptr(blur), _lib.ptr(nz), nstride, _lib.ptr(nw), _lib.ptr(ab),
+                int(activate), _lib.ptr(out), PRECISIONS[self.precision], _stream(x)))
+        return out
+
+    def forward(self, input, style):
+        return self._run(input, style)
 
 
 class NoiseInjection(nn.Module):
@@ -104,11 +178,30 @@ class NoiseInjection(nn.Module):
         super().__init__()
         self.weight = nn.Parameter(torch.zeros(1))
 
+    def forward(self, image, noise=None):
+        """model.py:287-292: image + weight * noise (fresh per-sample noise when none is given)."""
+        x = _f32c(image, 'image')
+        b, c, h, w = x.shape
+        if noise is None:
+            noise = x.new_empty(b, 1, h, w).normal_()
+        nz = _f32c(noise, 'noise')
+        if nz.numel() not in (h * w, b * h * w):
+            raise RuntimeError(f'noise must be [1,1,{h},{w}] or [{b},1,{h},{w}]')
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().sis_noise_injection(_lib.ptr(x), _lib.ptr(nz), 0 if nz.numel() == h * w else h * w,
+                                                       _lib.ptr(_f32c(self.weight.detach(), 'weight')), b, c, h, w, _lib.ptr(out), _stream(x)))
+        return out
+
 
 class ConstantInput(nn.Module):
     def __init__(self, channel, size=4):
         super().__init__()
         self.input = nn.Parameter(torch.randn(1, channel, size, size))
+
+    def forward(self, input):
+        """model.py:301-305: the learned constant repeated over the batch of `input`."""
+        return self.input.repeat(input.shape[0], 1, 1, 1)
 
 
 class StyledConv(nn.Module):
@@ -122,6 +215,14 @@ class StyledConv(nn.Module):
         self.noise = NoiseInjection()
         self.activate = FusedLeakyReLU(out_channel)
 
+    def forward(self, input, style, noise=None):
+        """model.py:336-342: conv -> noise -> bias + leaky ReLU, one native call with the fused epilogue."""
+        if noise is None:
+            b, _, h, _ = input.shape
+            r = 2 * h if self.conv.upsample else h
+            noise = torch.empty(b, 1, r, r, device=input.device).normal_()
+        return self.conv._run(input, style, noise=noise, noise_weight=self.noise.weight, act_bias=self.activate.bias, activate=True)
+
 
 class ToRGB(nn.Module):
     """Parameters of model.py:345-353."""
@@ -129,9 +230,27 @@ class ToRGB(nn.Module):
     def __init__(self, in_channel, style_dim, upsample=True, blur_kernel=(1, 3, 3, 1)):
         super().__init__()
         if upsample:
-            self.upsample = _FirBuffer(blur_kernel, 4)   # Upsample(kernel, factor=2): kernel * factor**2
+            # Upsample(kernel, factor=2), model.py:34-52: kernel * factor**2, pad = ((p + 1) // 2 + 1, p // 2), p = 4 - 2
+            p = len(blur_kernel) - 2
+            self.upsample = _FirBuffer(blur_kernel, 4, up=2, pad=((p + 1) // 2 + 1, p // 2))
         self.conv = ModulatedConv2d(in_channel, 3, 1, style_dim, demodulate=False)
         self.bias = nn.Parameter(torch.zeros(1, 3, 1, 1))
+
+    def forward(self, input, style, skip=None):
+        """model.py:355-364 through `sis_to_rgb`: 1x1 modulated conv + bias + upsampled skip in one pass."""
+        x, st = _f32c(input, 'input'), _f32c(style, 'style')
+        b, cin, h, _ = x.shape
+        out = torch.empty(b, 3, h, h, device=x.device)
+        sk = _f32c(skip, 'skip') if skip is not None else None
+        if sk is not None and (not hasattr(self, 'upsample') or tuple(sk.shape) != (b, 3, h // 2, h // 2)):
+            raise RuntimeError('skip must be [B, 3, H/2, H/2] and the layer must have been built with upsample=True')
+        upk = _f32c(self.upsample.kernel, 'upsample.kernel') if hasattr(self, 'upsample') else None
+        mw, mb = _f32c(self.conv.modulation.weight.detach(), 'weight'), _f32c(self.conv.modulation.bias.detach(), 'bias')
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().sis_to_rgb(_lib.ptr(x), b, cin, h, _lib.ptr(_f32c(self.conv.weight.detach(), 'weight')), _lib.ptr(mw),
+                                              _lib.ptr(mb), mw.shape[1], _lib.ptr(st), _lib.ptr(_f32c(self.bias.detach(), 'bias')),
+                                              _lib.ptr(sk), _lib.ptr(upk), _lib.ptr(out), _stream(x)))
+        return out
 
 
 class _StyleMLP(nn.Module):
@@ -183,6 +302,9 @@ class Generator(nn.Module):
             self.to_rgbs.append(ToRGB(out_channel, style_dim))
             in_channel = out_channel
         self.n_latent = self.log_size * 2 - 2
+        for m in self.modules():
+            if isinstance(m, ModulatedConv2d):
+                m.precision = precision      # stand-alone layer calls follow the generator's precision
         self._plan = _Plan()
 
     # ------------------------------------------------------------------ reference helpers
