@@ -163,12 +163,18 @@ __global__ void __launch_bounds__(32 * LBL_SLICES) label_native_kernel(LabelArgs
 // The inner loop is packed fp32x2 (FADD2 / FFMA2 on pixel pairs): the centroid table and the per-sample ToRGB weights
 // sit in shared memory pre-splatted as (m, m) pairs, so a channel costs 1 LDG.128 + 2 LDS.128 + 4k packed ops per
 // 4 pixels (+ 3 LDS.64 + 6 FFMA2 for RGB): the scalar version of the fused kernel was issue-bound at half the speed.
+// KMAX > 8 switches to the expanded form d_k = |c_k|^2 - 2 x.c_k (+ |x|^2, common to all k and therefore dropped: ids and
+// margins are unchanged): k packed FMAs per pixel pair per channel instead of 2k.  At k ~ 20 the direct form needs more
+// fp32 FMA throughput than the SM has per HBM byte; SURVEY.md §7 measured <= 1 flip per 131 k pixels (never at margin
+// > 1e-3) between the two forms.  k <= 8 keeps the reference's (A - B)^2 form, which is memory-bound anyway.
 template <int KMAX, bool RGB>
-__global__ void __launch_bounds__(256) label_wide_kernel(LabelArgs a, ToRgbArgs g) {
+__global__ void __launch_bounds__(256, (KMAX > 8 ? 2 : 3)) label_wide_kernel(LabelArgs a, ToRgbArgs g) {
+    constexpr bool EXPANDED = KMAX > 8;
     extern __shared__ float smem[];
     float2* sc2 = reinterpret_cast<float2*>(smem);                              // [C][KMAX] splatted centroids
     float2* sw2 = sc2 + (size_t)a.C * KMAX;                                     // [C][3] splatted scale*W*s of this sample (RGB)
     unsigned* shist = reinterpret_cast<unsigned*>(sw2 + (RGB ? 3 * a.C : 0));  // [KMAX]
+    float* scn = reinterpret_cast<float*>(shist + KMAX);                        // [KMAX] |c_k|^2 (expanded form)
     const int tid = threadIdx.x;
     const int64_t hw = (int64_t)a.H * a.W;
     const int64_t quads_per_sample = hw >> 2;                                   // a multiple of 256 (checked on the host):
@@ -178,7 +184,8 @@ __global__ void __launch_bounds__(256) label_wide_kernel(LabelArgs a, ToRgbArgs 
     for (int i = tid; i < a.C * KMAX; i += 256) {
         int c = i / KMAX, kk = i - c * KMAX;
         const float m = kk < a.k ? a.centroids[(int64_t)kk * a.C + c] : 0.0f;
-        sc2[i] = make_float2(m, m);
+        if (EXPANDED) reinterpret_cast<float*>(sc2)[i] = m;     // [C][KMAX] floats: FFMA2 operands are (m_k, m_k+1) pairs
+        else sc2[i] = make_float2(m, m);                          // [C][KMAX] pixel-pair splats
     }
     if (RGB) {
         const float* sb = g.s + (int64_t)b_blk * a.C;
@@ -188,7 +195,13 @@ __global__ void __launch_bounds__(256) label_wide_kernel(LabelArgs a, ToRgbArgs 
             sw2[i] = make_float2(w, w);
         }
     }
-    if (tid < KMAX) shist[tid] = 0;
+    if (tid < KMAX) {
+        shist[tid] = 0;
+        float cn = 0.0f;
+        if (EXPANDED && tid < a.k)
+            for (int c = 0; c < a.C; ++c) { const float m = a.centroids[(int64_t)tid * a.C + c]; cn = fmaf(m, m, cn); }
+        scn[tid] = cn;
+    }
     __syncthreads();
     const bool valid = q < total;
     int ids[4] = {-1, -1, -1, -1};
@@ -196,10 +209,16 @@ __global__ void __launch_bounds__(256) label_wide_kernel(LabelArgs a, ToRgbArgs 
         const int b = b_blk;
         const int64_t pix = (q - (int64_t)b * quads_per_sample) << 2;
         const float* xb = a.act + ((int64_t)b * a.C) * hw + pix;
-        float2 acc2[KMAX][2];
+        // direct form: acc2[k][pixel pair];  expanded form: accK[k pair][pixel]
+        float2 acc2[EXPANDED ? 1 : KMAX][2];
+        float2 accK[EXPANDED ? KMAX / 2 : 1][4];
         float2 rgb2[3][2];
 #pragma unroll
-        for (int kk = 0; kk < KMAX; ++kk) { acc2[kk][0] = make_float2(0.f, 0.f); acc2[kk][1] = make_float2(0.f, 0.f); }
+        for (int kk = 0; kk < (EXPANDED ? 1 : KMAX); ++kk) { acc2[kk][0] = make_float2(0.f, 0.f); acc2[kk][1] = make_float2(0.f, 0.f); }
+#pragma unroll
+        for (int kk = 0; kk < (EXPANDED ? KMAX / 2 : 1); ++kk)
+#pragma unroll
+            for (int p = 0; p < 4; ++p) accK[kk][p] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < 3; ++j) { rgb2[j][0] = make_float2(0.f, 0.f); rgb2[j][1] = make_float2(0.f, 0.f); }
 #pragma unroll 8
@@ -214,18 +233,41 @@ __global__ void __launch_bounds__(256) label_wide_kernel(LabelArgs a, ToRgbArgs 
                     rgb2[j][1] = pk_fma(w, x23, rgb2[j][1]);
                 }
             }
-            const float2* cc = sc2 + (size_t)c * KMAX;
+            if (EXPANDED) {
+                const float2* cc = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(sc2) + (size_t)c * KMAX);
+                const float2 xs[4] = {make_float2(v.x, v.x), make_float2(v.y, v.y), make_float2(v.z, v.z), make_float2(v.w, v.w)};
 #pragma unroll
-            for (int kk = 0; kk < KMAX; ++kk) {
-                const float2 m = cc[kk];
-                const float2 d0 = pk_sub(x01, m), d1 = pk_sub(x23, m);      // (A - B) ** 2 summed over channels
-                acc2[kk][0] = pk_fma(d0, d0, acc2[kk][0]);
-                acc2[kk][1] = pk_fma(d1, d1, acc2[kk][1]);
+                for (int kk = 0; kk < KMAX / 2; ++kk) {
+                    const float2 m = cc[kk];                                     // (c_2kk, c_2kk+1)
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) accK[kk][p] = pk_fma(xs[p], m, accK[kk][p]);   // x . c_k
+                }
+            } else {
+                const float2* cc = sc2 + (size_t)c * KMAX;
+#pragma unroll
+                for (int kk = 0; kk < KMAX; ++kk) {
+                    const float2 m = cc[kk];
+                    const float2 d0 = pk_sub(x01, m), d1 = pk_sub(x23, m);      // (A - B) ** 2 summed over channels
+                    acc2[kk][0] = pk_fma(d0, d0, acc2[kk][0]);
+                    acc2[kk][1] = pk_fma(d1, d1, acc2[kk][1]);
+                }
             }
         }
         float acc[KMAX][4];
+        if (EXPANDED) {
 #pragma unroll
-        for (int kk = 0; kk < KMAX; ++kk) { acc[kk][0] = acc2[kk][0].x; acc[kk][1] = acc2[kk][0].y; acc[kk][2] = acc2[kk][1].x; acc[kk][3] = acc2[kk][1].y; }
+            for (int kk = 0; kk < KMAX; ++kk) {
+                const float cn = scn[kk];                                        // |c_k|^2
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const float dot = (kk & 1) ? accK[kk / 2][p].y : accK[kk / 2][p].x;
+                    acc[kk][p] = fmaf(-2.0f, dot, cn);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int kk = 0; kk < KMAX; ++kk) { acc[kk][0] = acc2[kk][0].x; acc[kk][1] = acc2[kk][0].y; acc[kk][2] = acc2[kk][1].x; acc[kk][3] = acc2[kk][1].y; }
+        }
         float rgb[3][4];
 #pragma unroll
         for (int j = 0; j < 3; ++j) { rgb[j][0] = rgb2[j][0].x; rgb[j][1] = rgb2[j][0].y; rgb[j][2] = rgb2[j][1].x; rgb[j][3] = rgb2[j][1].y; }
@@ -424,7 +466,7 @@ static int launch_native(const LabelArgs& a, cudaStream_t stream) {
 
 template <int KMAX, bool RGB>
 static int launch_wide_impl(const LabelArgs& a, const ToRgbArgs& g, cudaStream_t stream) {
-    size_t smem = ((size_t)a.C * KMAX * 2 + (RGB ? 6 * a.C : 0) + KMAX) * sizeof(float);
+    size_t smem = ((size_t)a.C * KMAX * 2 + (RGB ? 6 * a.C : 0) + 2 * KMAX) * sizeof(float);   // (expanded form uses half the table)
     auto kern = label_wide_kernel<KMAX, RGB>;
     if (smem > 48 * 1024) SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t quads = (int64_t)a.H * a.W / 4 * a.batch;
@@ -491,7 +533,7 @@ int launch_label(const LabelArgs& a_in, int mode, const ToRgbArgs* fuse_rgb, boo
     // wide path: enough pixel quads to fill the GPU without slicing channels, integer (or no) mask replication,
     // rows that are a multiple of 4 pixels, k small enough for 4 x k register accumulators
     const int64_t quads = (int64_t)h * w / 4 * batch;
-    const bool wide_ok = vec4 && k <= 16 && w % 4 == 0 && quads >= (int64_t)kNumSMs * 512 && ((int64_t)h * w / 4) % 256 == 0 &&
+    const bool wide_ok = vec4 && k <= 24 && (size_t)channels * 24 * 8 <= 160 * 1024 && w % 4 == 0 && quads >= (int64_t)kNumSMs * 512 && ((int64_t)h * w / 4) % 256 == 0 &&
                          (!a.masks || (int_ratio && ((((uintptr_t)a.masks) & 15) == 0))) &&
                          (!a.ids_u8 || ((((uintptr_t)a.ids_u8) & 3) == 0)) && (!a.margin || ((((uintptr_t)a.margin) & 15) == 0));
     if (wide_ok) {
@@ -499,7 +541,8 @@ int launch_label(const LabelArgs& a_in, int mode, const ToRgbArgs* fuse_rgb, boo
                               fuse_rgb->batch == batch) ? fuse_rgb : nullptr;
         if (k <= 4) st = launch_wide<4>(a, g, stream);
         else if (k <= 8) st = launch_wide<8>(a, g, stream);
-        else st = launch_wide<16>(a, g, stream);
+        else if (k <= 16) st = launch_wide<16>(a, g, stream);
+        else st = launch_wide<24>(a, g, stream);
         if (g && fused && st == SIS_OK) *fused = true;
     } else if (vec4) {
         if (k <= 4) st = launch_native<4, 4>(a, stream);

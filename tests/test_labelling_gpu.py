@@ -22,7 +22,8 @@ def check_ids(got, want, margin, frac=0.999):
     assert float((got == want).float().mean()) >= frac
 
 
-@pytest.mark.parametrize('cfg', [(2, 128, 64, 4), (1, 512, 16, 20), (3, 64, 8, 3), (2, 32, 32, 24), (1, 17, 6, 33), (2, 128, 10, 7)])
+@pytest.mark.parametrize('cfg', [(2, 128, 64, 4), (1, 512, 16, 20), (3, 64, 8, 3), (2, 32, 32, 24), (1, 17, 6, 33), (2, 128, 10, 7),
+                                 (32, 64, 128, 20), (20, 32, 128, 12), (24, 16, 128, 7)])   # the last three take the wide kernels
 def test_label_assign_against_oracle(cuda_device, cfg):
     b, c, h, k = cfg
     g = torch.Generator().manual_seed(sum(cfg))
