@@ -90,6 +90,80 @@ def time_oracle(steps, warmup, batch):
     return steps * batch / dt, dt / steps * 1e3
 
 
+def load_ref_kernels():
+    """The reference's own two CUDA ops compiled by oracle/build_ref.py (None when oracle/_ref is absent)."""
+    import importlib.util
+    mods = {}
+    for name in ('ref_fused', 'ref_upfirdn2d'):
+        path = os.path.join(ROOT, 'oracle', '_ref', f'{name}.so')
+        if not os.path.exists(path):
+            return None
+        spec = importlib.util.spec_from_file_location(name, path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mods[name] = mod
+    return mods
+
+
+def time_reference_gpu(dev, steps, warmup, batch):
+    """SURVEY.md §8(d) "GPU reference path": the reference's graph on THIS GPU, as the reference runs it -- cuDNN/cuBLAS
+    fp32 convs (TF32 off), its own fused_bias_act / upfirdn2d kernels (oracle/_ref), ~150 launches per forward, then
+    FactorCatalog.predict with its CPU round trip (factor_catalog.py:47-62: A.cpu(), distances + argmin on the host,
+    ids .cuda()), class merge and nearest resize on the GPU.  A reported baseline (bench leg), never the product path."""
+    from oracle import labelling_oracle as lo
+    from oracle import stylegan2_oracle as so
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec, sd = oracle_state()
+    sd = {k: v.to(dev) for k, v in sd.items()}
+    catalog = synthetic_catalog()
+    inv = lo.invert_class_label_map({layer: CLASS_MAP for layer in LABEL_LAYERS})
+    ref = load_ref_kernels()
+    saved = (so.fused_bias_act, so.upfirdn2d_op, lo.predict)
+
+    def predict_round_trip(x, centroids):
+        b, _, h, w = x.shape
+        flat = lo.partial_flat(x).cpu()
+        ids = torch.argmin(lo.pairwise_distances(flat, centroids.cpu()), dim=1)
+        return ids.to(x.device).reshape(b, h, w)
+
+    def step():
+        z = torch.randn(batch, STYLE_DIM).to(dev)
+        noise = [n.to(dev) for n in so.make_noise(spec)]
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            img, acts = so.generator_forward(sd, spec, [z], noise=noise, return_intermediate_activations=True)
+            torch.cuda.synchronize(dev)
+            t1 = time.perf_counter()
+            masks = lo.prepare_image_segmentation(acts, catalog, inv, SIZE)
+        torch.cuda.synchronize(dev)
+        return t1 - t0, time.perf_counter() - t0
+
+    try:
+        if ref is not None:
+            so.fused_bias_act = ref['ref_fused'].fused_bias_act
+            so.upfirdn2d_op = ref['ref_upfirdn2d'].upfirdn2d
+        lo.predict = predict_round_trip
+        torch.manual_seed(1)
+        for _ in range(warmup):
+            step()
+        fwd = tot = 0.0
+        for _ in range(steps):
+            a, b = step()
+            fwd += a
+            tot += b
+    finally:
+        so.fused_bias_act, so.upfirdn2d_op, lo.predict = saved
+    return {'value': steps * batch / tot, 'unit': UNIT, 'forward_only_images_per_s': steps * batch / fwd,
+            'ms_per_step': tot / steps * 1e3, 'forward_ms_per_step': fwd / steps * 1e3,
+            'kind': 'reference graph on this GPU: cuDNN/cuBLAS fp32 (TF32 off) + '
+                    + ("the reference's compiled fused_bias_act/upfirdn2d kernels" if ref is not None else 'torch restatement of its two ops')
+                    + ', labelling through its CPU round trip (factor_catalog.py:47-62)',
+            'cores': torch.get_num_threads(), 'sample': f'{steps} timed + {warmup} warm-up steps of {batch} images, wall clock around synchronize'}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
     Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,' \
@@ -336,6 +410,10 @@ def main():
         cpu = {'value': v, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
                'sample': '3 timed + 1 warm-up steps of 1 image (256^2 generator + labelling of layers 8,9,12,13), oracle fp32'}
 
+    gpu_ref = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        gpu_ref = time_reference_gpu(dev, 2, 1, B)
+
     if rank == 0:
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
                 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -344,7 +422,7 @@ def main():
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                         'ms_per_step': float(ms2.item()) / args.steps},
                 'gpu_launches': launches, 'clocks': clocks, 'roofline': roofline, 'kernels': kernels, 'cpu_baseline': cpu,
-                'stats_allreduce_sum': int(stats.sum().item())}
+                'gpu_reference': gpu_ref, 'stats_allreduce_sum': int(stats.sum().item())}
         print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.barrier()

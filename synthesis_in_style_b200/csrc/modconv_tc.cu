@@ -152,7 +152,7 @@ struct TcKernelArgs {
 };
 
 constexpr int BM = 128, UMMA_K = 16;
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;          // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue (two per TMEM lane quarter)
 
 // BK = K elements per pipeline stage = one swizzle row (64 -> 128 B rows, 32 -> 64 B rows; measured: the 64 B rows
 // are slower, the L2 -> SM path is request-bound).  CG = tcgen05 cta_group: with CG = 2 a CTA pair computes a
@@ -233,7 +233,10 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    // default semantics (.release.cta), as CUTLASS' ClusterBarrier::arrive(cta_id): a cluster-scope release would make the
+    // epilogue wait for its global stores to be acknowledged by L2 before every accumulator hand-back; the accumulator
+    // reads themselves are ordered by tcgen05.wait::ld + tcgen05.fence::before_thread_sync
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-pair bit of a shared::cluster address -> even CTA
 
@@ -296,6 +299,100 @@ __device__ __forceinline__ void umma_commit_cg(uint64_t* bar) {
     }
 }
 
+// Epilogue warps (2..9): TMEM accumulator -> demodulate [-> noise + bias + lrelu] -> fp32 capture (+ the next conv's
+// pre-scaled bf16 hi/lo planes), shared by the per-tap and the halo kernels.
+template <int BN, int TH, int TW, int TB, int CG>
+__device__ __forceinline__ void tc_epilogue(const TcKernelArgs& a, uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base,
+                                            int rank, int warp, int lane, int unit0, int unit_stride) {
+        // ============================== epilogue (warps 2..9) ==============================
+        const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
+        const int chalf = (warp - 2) >> 2;              // the two warps of a quarter take alternate 32-column chunks
+        const int row = quarter * 32 + lane;            // GEMM row = pixel of the tile box
+        const int tw = row % TW, th = (row / TW) % TH, tb = row / (TW * TH);
+        const uint32_t tempty_leader = (CG == 2) ? map_to_cta(smem_u32(&tempty_bar[0]), 0) : 0u;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = unit0; t < a.total_tiles; t += unit_stride) {
+            const TileCoord c = decode_tile<BN, TH, TW, TB, CG>(a, t, rank);
+            if (c.skip) continue;
+            const TcSubProblem& s = a.sub[c.sub];
+            int b, yy, xx;
+            if (a.im2col) {
+                const int p = c.p0 + row;
+                xx = p % s.ow; yy = (p / s.ow) % s.oh; b = p / (s.ow * s.oh);
+            } else {
+                b = c.b0 + tb; yy = c.y0 + th; xx = c.x0 + tw;
+            }
+            const bool valid = !c.dummy && b < a.batch && yy < s.oh && xx < s.ow;
+            const int oy = yy * s.ostride + s.ooff_y, ox = xx * s.ostride + s.ooff_x;
+            mbar_wait(&tfull_bar[acc], acc_phase, a.error, 0x400 + acc);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+            const float* dm = a.demod + (int64_t)(valid ? b : 0) * a.cout + c.n0;
+            float nz = 0.0f;
+            if (a.mode == 0 && valid && a.noise) nz = __fmul_rn(a.noise_w, a.noise[(int64_t)b * a.noise_bstride + (int64_t)oy * a.out_w + ox]);
+            const int cstep = (blockDim.x / 32 - 2) * 8;      // 4 epilogue warps: 32, 8: 64
+#pragma unroll 1
+            for (int c0 = chalf * 32; c0 < BN; c0 += cstep) {
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + (uint32_t)c0, r);
+                tmem_ld_wait();
+                if (valid) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = __fmul_rn(__uint_as_float(r[j]), __ldg(dm + c0 + j));
+                    if (a.mode == 0) {
+                        // NoiseInjection + FusedLeakyReLU (model.py:292, fused_bias_act_kernel.cu:26-47)
+                        const int64_t plane = (int64_t)a.out_h * a.out_w;
+                        float* dst = a.out_f32 + ((int64_t)b * a.cout + c.n0 + c0) * plane + (int64_t)oy * a.out_w + ox;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            float x = __fadd_rn(v[j], nz);
+                            if (a.bias) x = __fadd_rn(x, __ldg(a.bias + c.n0 + c0 + j));
+                            if (a.act) x = lrelu_scale(x, 0.2f, 1.41421356237309504880f);
+                            v[j] = x;
+                            dst[(int64_t)j * plane] = x;       // lanes = consecutive x: coalesced per channel
+                        }
+                        if (a.s_next) {
+                            const float* sn = a.s_next + (int64_t)b * a.cout + c.n0 + c0;
+                            const int64_t off = (((int64_t)b * a.out_h + oy) * a.out_w + ox) * a.cout + c.n0 + c0;
+                            uint4* ph = reinterpret_cast<uint4*>(a.next_hi + off);
+                            uint4* pl = reinterpret_cast<uint4*>(a.next_lo + off);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                uint32_t wh[4], wl[4];
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const int j = q * 8 + e * 2;
+                                    const float x0 = __fmul_rn(v[j], __ldg(sn + j)), x1 = __fmul_rn(v[j + 1], __ldg(sn + j + 1));
+                                    const bf16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                                    const bf16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+                                    const bf16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                                    wh[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                                    wl[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                                }
+                                ph[q] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                                pl[q] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+                            }
+                        }
+                    } else {
+                        // transposed-conv phase: demodulated fp32, NHWC scratch [B][out_h][out_w][cout]
+                        float4* dst = reinterpret_cast<float4*>(
+                            a.out_f32 + (((int64_t)b * a.out_h + oy) * a.out_w + ox) * a.cout + c.n0 + c0);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (CG == 1) mbar_arrive(&tempty_bar[acc]);
+                else mbar_arrive_cluster(tempty_leader + (uint32_t)(acc * 8));   // the even CTA's MMA thread waits on it
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
 template <int BN, int TH, int TW, int TB, int BK, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 modconv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcKernelArgs a) {
@@ -323,7 +420,7 @@ modconv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ T
         for (int i = 0; i < a.nsub; ++i) { tma_prefetch_desc(&maps.a[i][0]); tma_prefetch_desc(&maps.a[i][1]); }
         tma_prefetch_desc(&maps.w[0]); tma_prefetch_desc(&maps.w[1]);
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4 * CG); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], (blockDim.x / 32 - 2) * CG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -409,94 +506,171 @@ modconv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ T
             }
         }
     } else {
-        // ============================== epilogue (warps 2..5) ==============================
-        const int quarter = warp & 3;                   // TMEM lane quarter this warp may access
-        const int row = quarter * 32 + lane;            // GEMM row = pixel of the tile box
-        const int tw = row % TW, th = (row / TW) % TH, tb = row / (TW * TH);
-        const uint32_t tempty_leader = (CG == 2) ? map_to_cta(smem_u32(&tempty_bar[0]), 0) : 0u;
-        int acc = 0; uint32_t acc_phase = 0;
-        for (int t = unit0; t < a.total_tiles; t += unit_stride) {
-            const TileCoord c = decode_tile<BN, TH, TW, TB, CG>(a, t, rank);
-            if (c.skip) continue;
-            const TcSubProblem& s = a.sub[c.sub];
-            int b, yy, xx;
-            if (a.im2col) {
-                const int p = c.p0 + row;
-                xx = p % s.ow; yy = (p / s.ow) % s.oh; b = p / (s.ow * s.oh);
-            } else {
-                b = c.b0 + tb; yy = c.y0 + th; xx = c.x0 + tw;
-            }
-            const bool valid = !c.dummy && b < a.batch && yy < s.oh && xx < s.ow;
-            const int oy = yy * s.ostride + s.ooff_y, ox = xx * s.ostride + s.ooff_x;
-            mbar_wait(&tfull_bar[acc], acc_phase, a.error, 0x400 + acc);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-            const float* dm = a.demod + (int64_t)(valid ? b : 0) * a.cout + c.n0;
-            float nz = 0.0f;
-            if (a.mode == 0 && valid && a.noise) nz = __fmul_rn(a.noise_w, a.noise[(int64_t)b * a.noise_bstride + (int64_t)oy * a.out_w + ox]);
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                uint32_t r[32];
-                tmem_ld_32x32(taddr + (uint32_t)c0, r);
-                tmem_ld_wait();
-                if (valid) {
-                    float v[32];
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __fmul_rn(__uint_as_float(r[j]), __ldg(dm + c0 + j));
-                    if (a.mode == 0) {
-                        // NoiseInjection + FusedLeakyReLU (model.py:292, fused_bias_act_kernel.cu:26-47)
-                        const int64_t plane = (int64_t)a.out_h * a.out_w;
-                        float* dst = a.out_f32 + ((int64_t)b * a.cout + c.n0 + c0) * plane + (int64_t)oy * a.out_w + ox;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float x = __fadd_rn(v[j], nz);
-                            if (a.bias) x = __fadd_rn(x, __ldg(a.bias + c.n0 + c0 + j));
-                            if (a.act) x = lrelu_scale(x, 0.2f, 1.41421356237309504880f);
-                            v[j] = x;
-                            dst[(int64_t)j * plane] = x;       // lanes = consecutive x: coalesced per channel
-                        }
-                        if (a.s_next) {
-                            const float* sn = a.s_next + (int64_t)b * a.cout + c.n0 + c0;
-                            const int64_t off = (((int64_t)b * a.out_h + oy) * a.out_w + ox) * a.cout + c.n0 + c0;
-                            uint4* ph = reinterpret_cast<uint4*>(a.next_hi + off);
-                            uint4* pl = reinterpret_cast<uint4*>(a.next_lo + off);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint32_t wh[4], wl[4];
-#pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const int j = q * 8 + e * 2;
-                                    const float x0 = __fmul_rn(v[j], __ldg(sn + j)), x1 = __fmul_rn(v[j + 1], __ldg(sn + j + 1));
-                                    const bf16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-                                    const bf16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-                                    const bf16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-                                    wh[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                                    wl[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-                                }
-                                ph[q] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
-                                pl[q] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
-                            }
-                        }
-                    } else {
-                        // transposed-conv phase: demodulated fp32, NHWC scratch [B][out_h][out_w][cout]
-                        float4* dst = reinterpret_cast<float4*>(
-                            a.out_f32 + (((int64_t)b * a.out_h + oy) * a.out_w + ox) * a.cout + c.n0 + c0);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-                    }
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (CG == 1) mbar_arrive(&tempty_bar[acc]);
-                else mbar_arrive_cluster(tempty_leader + (uint32_t)(acc * 8));   // the even CTA's MMA thread waits on it
-            }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        }
+        tc_epilogue<BN, TH, TW, TB, CG>(a, tfull_bar, tempty_bar, tmem_base, rank, warp, lane, unit0, unit_stride);
     }
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();   // CG = 2: the peer may still read this CTA's smem / TMEM
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        if (CG == 1)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------- halo-reuse variant
+// Plain 3x3 layers with H >= 16: instead of one A tile per (tap, K chunk), the producer loads ONE 18 x 10 pixel halo of
+// the 16 x 8 output tile per K chunk and the 9 taps read it through shifted operand descriptors: tap (dy, dx) starts
+// at halo pixel (dy+1)*10 + (dx+1) and its sixteen 8-pixel row groups are one halo row (10 pixels = 1280 B) apart.
+// SWIZZLE_128B is a function of the absolute shared-memory address (bits 4-6 ^= bits 7-9), so any 128 B-aligned start
+// inside a 1024 B-aligned TMA-written buffer reads back consistently with base_offset 0 (scripts/exp_halo_desc.cu
+// verifies this on the B200).  A traffic drops from 9 x 32 KB to 45 KB per K chunk; the weights stream per tap through
+// their own ring.  With Cout = 128 that takes the L2 -> SM fill from ~62 to ~27 B/clk/SM, i.e. back under the tensor pipe.
+constexpr int HALO_TH = 16, HALO_TW = 8, HALO_W = HALO_TW + 2, HALO_H = HALO_TH + 2;
+template <int BN, int CG> struct TcHaloCfg {
+    static constexpr int BK = 64;
+    static constexpr int A_BYTES = HALO_H * HALO_W * BK * 2;                 // 23040: bytes one halo load delivers
+    static constexpr int A_PAD = (A_BYTES + 1023) / 1024 * 1024;             // 23552: hi / lo planes stay 1024 B aligned
+    static constexpr int A_STAGE = 2 * A_PAD;
+    static constexpr int NA = 2;
+    static constexpr int B_ROWS = BN / CG;
+    static constexpr int B_TILE_BYTES = B_ROWS * BK * 2;
+    static constexpr int B_STAGE = 2 * B_TILE_BYTES;
+    static constexpr int BUDGET = 227 * 1024 - 1024 - 512;
+    static constexpr int NB_RAW = (BUDGET - NA * A_STAGE) / B_STAGE;
+    static constexpr int NB = NB_RAW > 8 ? 8 : NB_RAW;
+    static constexpr int SMEM_BYTES = NA * A_STAGE + NB * B_STAGE + 1024 /*align*/ + 512 /*barriers*/;
+    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    static_assert(NB >= 2, "weight ring too shallow");
+};
+
+__device__ __forceinline__ uint64_t make_halo_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((HALO_W * 128) >> 4) << 32;         // 8-pixel row groups are one halo row apart
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B, base_offset 0
+    return d;
+}
+
+template <int BN, int CG>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+modconv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcKernelArgs a) {
+    using Cfg = TcHaloCfg<BN, CG>;
+    constexpr int NA = Cfg::NA, NB = Cfg::NB, BK = Cfg::BK;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_b = smem + NA * Cfg::A_STAGE;
+    uint64_t* bars = (uint64_t*)(smem_b + NB * Cfg::B_STAGE);
+    uint64_t* full_bar = bars;                       // [NB] weights   (CG = 2: only the even CTA's full barriers are used)
+    uint64_t* empty_bar = bars + NB;                 // [NB]
+    uint64_t* afull_bar = bars + 2 * NB;             // [NA] halo tiles
+    uint64_t* aempty_bar = bars + 2 * NB + NA;       // [NA]
+    uint64_t* tfull_bar = bars + 2 * NB + 2 * NA;    // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;            // [2]
+    uint32_t* tmem_ptr_smem = (uint32_t*)(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
+    const bool leader = rank == 0;
+    const int unit0 = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int unit_stride = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&maps.a[0][0]); tma_prefetch_desc(&maps.a[0][1]);
+        tma_prefetch_desc(&maps.w[0]); tma_prefetch_desc(&maps.w[1]);
+        for (int i = 0; i < NB; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < NA; ++i) { mbar_init(&afull_bar[i], 1); mbar_init(&aempty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], (blockDim.x / 32 - 2) * CG); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        if (CG == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
+    }
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const TcSubProblem& s = a.sub[0];
+
+    if (warp == 0) {
+        // ============================== TMA producer (both CTAs of a pair) ==============================
+        if (lane == 0) {
+            int as = 0; uint32_t aphase = 0;
+            int bs = 0; uint32_t bphase = 0;
+            for (int t = unit0; t < a.total_tiles; t += unit_stride) {
+                const TileCoord c = decode_tile<BN, HALO_TH, HALO_TW, 1, CG>(a, t, rank);
+                const int wrow = c.n0 + rank * Cfg::B_ROWS;
+                for (int kc = 0; kc < a.kchunks; ++kc) {
+                    mbar_wait(&aempty_bar[as], aphase ^ 1, a.error, 0x500 + as);
+                    uint8_t* sa = smem + as * Cfg::A_STAGE;
+                    if (leader) mbar_expect_tx(&afull_bar[as], CG * 2 * Cfg::A_BYTES);
+                    tma_load_4d_cg<CG>(&maps.a[0][0], &afull_bar[as], sa, kc * BK, c.x0 - 1, c.y0 - 1, c.b0);
+                    tma_load_4d_cg<CG>(&maps.a[0][1], &afull_bar[as], sa + Cfg::A_PAD, kc * BK, c.x0 - 1, c.y0 - 1, c.b0);
+                    if (++as == NA) { as = 0; aphase ^= 1; }
+                    for (int tap = 0; tap < s.ntaps; ++tap) {
+                        mbar_wait(&empty_bar[bs], bphase ^ 1, a.error, 0x100 + bs);
+                        uint8_t* sb = smem_b + bs * Cfg::B_STAGE;
+                        if (leader) mbar_expect_tx(&full_bar[bs], CG * Cfg::B_STAGE);
+                        tma_load_3d_cg<CG>(&maps.w[0], &full_bar[bs], sb, kc * BK, wrow, s.widx[tap]);
+                        tma_load_3d_cg<CG>(&maps.w[1], &full_bar[bs], sb + Cfg::B_TILE_BYTES, kc * BK, wrow, s.widx[tap]);
+                        if (++bs == NB) { bs = 0; bphase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer (even CTA of a pair only) ==============================
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
+            int as = 0; uint32_t aphase = 0;
+            int bs = 0; uint32_t bphase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int t = unit0; t < a.total_tiles; t += unit_stride) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1, a.error, 0x200 + acc);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kc = 0; kc < a.kchunks; ++kc) {
+                    mbar_wait(&afull_bar[as], aphase, a.error, 0x600 + as);
+                    const uint32_t sa = smem_u32(smem + as * Cfg::A_STAGE);
+                    for (int tap = 0; tap < s.ntaps; ++tap) {
+                        mbar_wait(&full_bar[bs], bphase, a.error, 0x300 + bs);
+                        tc_fence_after();
+                        const uint32_t aoff = (uint32_t)(((s.dy[tap] + 1) * HALO_W + (s.dx[tap] + 1)) * (BK * 2));
+                        const uint64_t d_ah = make_halo_desc(sa + aoff), d_al = make_halo_desc(sa + Cfg::A_PAD + aoff);
+                        const uint32_t sb = smem_u32(smem_b + bs * Cfg::B_STAGE);
+                        const uint64_t d_bh = make_smem_desc<BK * 2>(sb), d_bl = make_smem_desc<BK * 2>(sb + Cfg::B_TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+                            umma_bf16_cg<CG>(d_tmem, d_ah + koff, d_bh + koff, idesc, (kc | tap | k) ? 1u : 0u);
+                            umma_bf16_cg<CG>(d_tmem, d_ah + koff, d_bl + koff, idesc, 1u);
+                            umma_bf16_cg<CG>(d_tmem, d_al + koff, d_bh + koff, idesc, 1u);
+                        }
+                        umma_commit_cg<CG>(&empty_bar[bs]);
+                        if (++bs == NB) { bs = 0; bphase ^= 1; }
+                    }
+                    umma_commit_cg<CG>(&aempty_bar[as]);            // halo stage free (in both CTAs) once its 9 taps retire
+                    if (++as == NA) { as = 0; aphase ^= 1; }
+                }
+                umma_commit_cg<CG>(&tfull_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        tc_epilogue<BN, HALO_TH, HALO_TW, 1, CG>(a, tfull_bar, tempty_bar, tmem_base, rank, warp, lane, unit0, unit_stride);
+    }
+    tc_fence_before();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
@@ -796,6 +970,17 @@ static int make_im2col_map(CUtensorMap* map, void* base, int C, int W, int H, in
 
 struct TcTensorMapCacheEntry { CUtensorMap m; };
 
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+// SIS_TC_EPIWARPS (8 default | 4): epilogue warps per CTA; the kernels size their barriers from blockDim
+static int tc_threads() {
+    static int t = 0;
+    if (!t) t = env_int("SIS_TC_EPIWARPS", 8) == 4 ? 192 : TC_THREADS;
+    return t;
+}
+
 int tc_pack_weights(TcConvWeights& w, const float* d_weight, int cin, int cout, bool up, float scale, cudaStream_t stream) {
     (void)up;
     const size_t bytes = (size_t)9 * cin * cout * sizeof(bf16);
@@ -887,7 +1072,7 @@ static int launch_tc(const TcMaps& maps, const TcKernelArgs& a, cudaStream_t str
     int grid = a.total_tiles * CG < kNumSMs ? a.total_tiles * CG : kNumSMs;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc_threads()); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -895,6 +1080,36 @@ static int launch_tc(const TcMaps& maps, const TcKernelArgs& a, cudaStream_t str
     SIS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, a));
     SIS_CHECK_LAUNCH();
     return SIS_OK;
+}
+
+template <int BN, int CG>
+static int launch_tc_halo(const TcMaps& maps, const TcKernelArgs& a, cudaStream_t stream) {
+    using Cfg = TcHaloCfg<BN, CG>;
+    auto kern = modconv_tc_halo_kernel<BN, CG>;
+    static bool configured = false;
+    if (!configured) {
+        SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    int grid = a.total_tiles * CG < kNumSMs ? a.total_tiles * CG : kNumSMs;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc_threads()); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    SIS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, maps, a));
+    SIS_CHECK_LAUNCH();
+    return SIS_OK;
+}
+
+template <int CG>
+static int launch_tc_halo_any(int BN, const TcMaps& maps, const TcKernelArgs& a, cudaStream_t stream) {
+    if (BN == 256) return launch_tc_halo<256, CG>(maps, a, stream);
+    if (BN == 128) return launch_tc_halo<128, CG>(maps, a, stream);
+    if (BN == 64) return launch_tc_halo<64, CG>(maps, a, stream);
+    return launch_tc_halo<32, CG>(maps, a, stream);
 }
 
 template <int BN, int BK, int CG>
@@ -914,21 +1129,20 @@ static int launch_tc_any(int BN, int th, int tw, int tb, const TcMaps& maps, con
     return launch_tc_bn<32, BK, CG>(th, tw, tb, maps, a, stream);
 }
 
-static int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-
 int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, cudaStream_t stream) {
     // Tunables for A/B runs: SIS_TC_BK (64 default | 32: stage depth along K), SIS_TC_CG (2 default | 1: CTA pairs)
     //                       SIS_TC_IM2COL (1 default | 0: spatial-box A tiles instead of flattened 128-pixel runs)
-    static int bk_env = 0, cg_env = 0, im2col_env = 1;
+    //                       SIS_TC_HALO (1 default | 0: per-tap A tiles on the plain layers too)
+    static int bk_env = 0, cg_env = 0, im2col_env = 1, halo_env = 1;
     if (!bk_env) {
         bk_env = env_int("SIS_TC_BK", 64) == 32 ? 32 : 64; cg_env = env_int("SIS_TC_CG", 2) == 1 ? 1 : 2;
         im2col_env = env_int("SIS_TC_IM2COL", 1) != 0;
+        halo_env = env_int("SIS_TC_HALO", 1) != 0;
     }
-    const bool im2col = im2col_env != 0;
-    const int BK = (call.cin % 64 == 0) ? bk_env : 32;
+    // halo reuse: plain 3x3 layers whose image holds whole 16 x 8 tiles and whose K chunks are 64 wide
+    const bool halo = halo_env && !call.up && call.res_in >= HALO_TH && call.res_in % HALO_TH == 0 && call.cin % 64 == 0;
+    const bool im2col = im2col_env != 0 && !halo;
+    const int BK = halo ? 64 : (call.cin % 64 == 0) ? bk_env : 32;
     SIS_REQUIRE(call.cin % BK == 0, "tc_modconv: Cin must be a multiple of 32 (got %d)", call.cin);
     SIS_REQUIRE(call.cout % 32 == 0, "tc_modconv: Cout must be a multiple of 32 (got %d)", call.cout);
     SIS_REQUIRE(w.hi && w.cin == call.cin && w.cout == call.cout, "tc_modconv: weights not packed for this layer");
@@ -936,7 +1150,8 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
     // tile box by the GEMM grid extent (plain: H; transposed phases: up to H+1)
     const int ext = call.up ? H + 1 : H;
     int th, tw, tb;
-    if (im2col || ext > 8) { th = 8; tw = 16; tb = 1; }      // im2col mode ignores the box (one kernel variant)
+    if (halo) { th = HALO_TH; tw = HALO_TW; tb = 1; }
+    else if (im2col || ext > 8) { th = 8; tw = 16; tb = 1; }      // im2col mode ignores the box (one kernel variant)
     else if (ext <= 4) { th = 4; tw = 4; tb = 8; }
     else { th = 8; tw = 8; tb = 2; }
     const int b_tiles = ceil_div(B, tb);
@@ -1024,7 +1239,7 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
             }
         } else {
             const uint64_t adims[4] = {(uint64_t)call.cin, (uint64_t)H, (uint64_t)H, (uint64_t)B};
-            const uint32_t abox[4] = {(uint32_t)BK, (uint32_t)tw, (uint32_t)th, (uint32_t)tb};
+            const uint32_t abox[4] = {(uint32_t)BK, (uint32_t)(halo ? HALO_W : tw), (uint32_t)(halo ? HALO_H : th), (uint32_t)tb};
             SIS_PROPAGATE(make_map(&maps.a[0][0], ws.a_hi[call.in_slot], 4, adims, abox, BK * 2));
             SIS_PROPAGATE(make_map(&maps.a[0][1], ws.a_lo[call.in_slot], 4, adims, abox, BK * 2));
         }
@@ -1036,7 +1251,8 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
     int st;
     {
         ProfScope prof(PROF_CONV_TC, stream);
-        if (CG == 2) st = (BK == 64) ? launch_tc_any<64, 2>(BN, th, tw, tb, maps, a, stream) : launch_tc_any<32, 2>(BN, th, tw, tb, maps, a, stream);
+        if (halo) st = (CG == 2) ? launch_tc_halo_any<2>(BN, maps, a, stream) : launch_tc_halo_any<1>(BN, maps, a, stream);
+        else if (CG == 2) st = (BK == 64) ? launch_tc_any<64, 2>(BN, th, tw, tb, maps, a, stream) : launch_tc_any<32, 2>(BN, th, tw, tb, maps, a, stream);
         else st = (BK == 64) ? launch_tc_any<64, 1>(BN, th, tw, tb, maps, a, stream) : launch_tc_any<32, 1>(BN, th, tw, tb, maps, a, stream);
     }
     SIS_PROPAGATE(st);
