@@ -106,9 +106,23 @@ class LabelledBatch:
 @dataclass
 class HostBatch:
     batch_index: int
-    image: torch.Tensor                      # pinned host [B, 3, S, S] fp32
+    image: torch.Tensor                      # pinned host [B, 3, S, S] fp32, or uint8 [B, S, S, 3] (image_u8=True)
     masks: Dict[str, torch.Tensor]           # pinned host {layer: uint8 [n_class, B, S, S]}
     class_names: Dict[str, List[str]]        # {layer: class name of each mask plane}
+
+
+@dataclass
+class SegmentedBatch:
+    """One batch after the host-side contour stage (create_dataset_for_segmentation.py:132-140)."""
+    batch_index: int
+    images: 'numpy.ndarray'                  # uint8 [B, S, S, 3]   make_image(generated_images)
+    label_images: 'numpy.ndarray'            # uint8 [B, S, S, 3]   colour label images
+    image_ids_to_drop: List[int]
+
+    def kept(self):
+        """(images, label_images) with the dropped rows removed (numpy.delete, as the reference does)."""
+        import numpy
+        return numpy.delete(self.images, self.image_ids_to_drop, axis=0), numpy.delete(self.label_images, self.image_ids_to_drop, axis=0)
 
 
 class LabelledPairGenerator:
@@ -144,7 +158,7 @@ class LabelledPairGenerator:
             self.stats['batches'] += 1
             yield LabelledBatch(idx, image, masks, acts)
 
-    def iter_host(self, depth: int = 2) -> Iterator['HostBatch']:
+    def iter_host(self, depth: int = 2, image_u8: bool = False) -> Iterator['HostBatch']:
         """The same loop with HOST buffers on both sides, as `build_dataset` needs them (its next steps are CPU code):
         latents are staged in pinned memory and copied in, the fp32 image and the per-layer uint8 mask stacks are
         copied out to pinned memory on a side stream, with `depth` batches in flight so the copies overlap the next
@@ -155,7 +169,8 @@ class LabelledPairGenerator:
         g, seg = self.generator, self.segmenter
         B, S = self.config['batch_size'], g.size
         copy_stream = torch.cuda.Stream(device=device)
-        slots = [{'z': torch.empty(B, self.config['latent_size']).pin_memory(), 'image': torch.empty(B, 3, S, S).pin_memory(),
+        slots = [{'z': torch.empty(B, self.config['latent_size']).pin_memory(),
+                  'image': (torch.empty(B, S, S, 3, dtype=torch.uint8) if image_u8 else torch.empty(B, 3, S, S)).pin_memory(),
                   'masks': {}} for _ in range(depth + 1)]
         in_flight = []
 
@@ -177,6 +192,8 @@ class LabelledPairGenerator:
             else:
                 acts, image = generate_images(lat, g, device=device, mean_latent=self.mean_latent, capture_layers=self.capture_layers)
                 stacked = seg.label_layers_stacked(acts)
+            if image_u8:
+                image = make_image(image)              # uint8 NHWC on the device: a quarter of the fp32 copy
             ready = torch.cuda.Event()
             ready.record(torch.cuda.current_stream(device))
             with torch.cuda.stream(copy_stream):
@@ -197,6 +214,38 @@ class LabelledPairGenerator:
             n += 1
             if len(in_flight) >= depth:
                 yield finish(in_flight.pop(0))
+
+    def iter_segmented(self, depth: int = 2, pool=None, lag: int = 1) -> Iterator[SegmentedBatch]:
+        """generate -> label (GPU) -> contour post-processing (host), pipelined: the per-image contour tasks of a batch
+        run on `pool` (a concurrent.futures executor; None = inline) while the GPU produces the next `lag` batches.
+        Yields what the reference's loop has after create_segmentation_image + make_image."""
+        import collections
+
+        import numpy
+
+        from . import contours
+        cfg = self.segmenter.contour_config()
+        keys = set(cfg.keys_for_class_determination) | set(cfg.keys_for_finegrained_segmentation)
+        pending = collections.deque()
+
+        def collect(entry):
+            index, images, tasks = entry
+            results = [t.result() if hasattr(t, 'result') else t for t in tasks]
+            return SegmentedBatch(index, images, numpy.stack([r[0] for r in results], axis=0),
+                                  [b for b, r in enumerate(results) if r[1]])
+
+        for hb in self.iter_host(depth, image_u8=True):
+            B = hb.image.shape[0]
+            tasks = []
+            for b in range(B):
+                # the pinned slot is reused depth+1 batches later: every task gets its own copy of its image's masks
+                per_image = {layer: {name: hb.masks[layer][j, b:b + 1].numpy().copy() for j, name in enumerate(hb.class_names[layer])}
+                             for layer in hb.masks if layer in keys}
+                tasks.append(pool.submit(contours._segment_one, (per_image, cfg)) if pool is not None
+                             else contours._segment_one((per_image, cfg)))
+            pending.append((hb.batch_index, hb.image.numpy().copy(), tasks))
+            if len(pending) > lag:
+                yield collect(pending.popleft())
 
     def stats_vector(self) -> torch.Tensor:
         """int64 [sum_k cluster pixel counts per labelled layer | pairs | batches] on the generator's device."""

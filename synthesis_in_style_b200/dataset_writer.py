@@ -1,0 +1,180 @@
+"""On-disk output of the dataset-creation loop: side-by-side PNGs, directory sharding,
+running ids, train / val JSON.
+
+Mirrors scf/create_dataset_for_segmentation.py
+  :84-90    save_image                 <base>/<id // 100000>/<id // 1000>/<name_format>
+  :93-99    save_generated_images      image || label concatenated along the width, id = batch_id + row
+  :109-148  build_dataset loop         drop, running id = number of images kept so far, stop once >= num_images
+  :151-206  create_dataset_json_data, main: shuffle under random.seed(config['seed']), 90 / 10 split, train.json / val.json
+and scf/segmentation/evaluation/coco_gt.py:35-65 (`determine_classes_in_image`: a class is present when its colour has
+an external contour with at least 3 points in the right half of the PNG).
+Not here: coco_gt.json (coco_gt.py:67-134) needs pycocotools' polygon-to-RLE coder, which is neither in this image nor
+under /root/reference -- nothing to pin it against.
+
+PNG encoding is CPU-bound zlib work; `DatasetWriter` hands the rows of a batch to a thread pool (PIL releases the GIL
+while it compresses), so files are written while the GPU and the contour workers produce the next batch.
+Multi-GPU runs assign the reference's GLOBAL running ids: ranks exchange the kept count of their batch once per round
+(`exchange_kept_counts`, an all-gather of one int64) and `assign_round_ids` replays the reference's sequential loop.
+"""
+import json
+import random
+from pathlib import Path
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import cv2
+import numpy
+from PIL import Image
+
+from .labelling import BaseDatasetSegmenter
+
+
+def image_file_name(image_id: int, base_dir: Path, name_format: str = '{id}.png') -> Path:
+    """save_image's path rule (:85-87)."""
+    return Path(base_dir) / str(image_id // 100000) / str(image_id // 1000) / name_format.format(id=image_id)
+
+
+def name_format_for(num_images: int) -> str:
+    """save_generated_images' name format (:99): zero-padded to max(4, digits of num_images)."""
+    return f'{{id:0{max(4, len(str(num_images)))}d}}.png'
+
+
+def save_image(image: numpy.ndarray, image_id: int, base_dir: Path, name_format: str = '{id}.png') -> Path:
+    dest = image_file_name(image_id, base_dir, name_format)
+    dest.parent.mkdir(exist_ok=True, parents=True)
+    Image.fromarray(image).save(str(dest))
+    return dest
+
+
+def save_generated_images(generated_images: numpy.ndarray, semantic_segmentation_images: numpy.ndarray, batch_id: int,
+                          base_dir: Path, num_images: int, pool=None) -> List:
+    """:93-99.  With `pool` (a concurrent.futures executor) returns the futures of the per-file writes."""
+    images = numpy.concatenate([generated_images, semantic_segmentation_images], axis=2)
+    fmt = name_format_for(num_images)
+    if pool is None:
+        return [save_image(image, batch_id + idx, base_dir, fmt) for idx, image in enumerate(images)]
+    return [pool.submit(save_image, image, batch_id + idx, base_dir, fmt) for idx, image in enumerate(images)]
+
+
+# --------------------------------------------------------------------------- running ids across ranks
+
+def assign_round_ids(kept_counts: Sequence[int], n_before: int, num_images: int) -> Tuple[List[Optional[int]], int, bool]:
+    """Replay the reference's sequential loop over one round of batches (round t holds batch t*W + r of rank r, in rank
+    order).  Returns (first image id of every batch, or None for a batch the reference would never have generated
+    because the target was already reached; the new running count; whether the run is finished)."""
+    starts: List[Optional[int]] = []
+    n = n_before
+    for kept in kept_counts:
+        if n >= num_images:              # `while pbar.n < args.num_images` (:128)
+            starts.append(None)
+            continue
+        starts.append(n)
+        n += int(kept)
+    return starts, n, n >= num_images
+
+
+def exchange_kept_counts(kept: int, device=None) -> List[int]:
+    """All-gather of this rank's kept count (one int64 per rank and round); [kept] without a process group."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [int(kept)]
+    mine = torch.tensor([int(kept)], dtype=torch.int64, device=device)
+    gathered = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+    dist.all_gather(gathered, mine)
+    return [int(g.item()) for g in gathered]
+
+
+class DatasetWriter:
+    """The tail of build_dataset's loop for one rank: drop, assign ids, write the PNGs."""
+
+    def __init__(self, base_dir, num_images: int, rank: int = 0, world_size: int = 1, pool=None, device=None):
+        self.base_dir, self.num_images = Path(base_dir), num_images
+        self.rank, self.world_size, self.pool, self.device = rank, world_size, pool, device
+        self.n = 0                       # the reference's pbar.n: images kept so far, over all ranks
+        self.finished = False
+        self._futures = []
+        self.files_written = 0
+
+    def add(self, generated_images: numpy.ndarray, label_images: numpy.ndarray, image_ids_to_drop: Sequence[int]) -> int:
+        """One batch of this rank (one round): returns how many files it queued."""
+        drop = list(image_ids_to_drop)
+        generated_images = numpy.delete(generated_images, drop, axis=0)
+        label_images = numpy.delete(label_images, drop, axis=0)
+        counts = exchange_kept_counts(len(label_images), self.device)
+        starts, self.n, self.finished = assign_round_ids(counts, self.n, self.num_images)
+        start = starts[self.rank if len(starts) > 1 else 0]
+        if start is None or len(label_images) == 0:
+            return 0
+        out = save_generated_images(generated_images, label_images, start, self.base_dir, self.num_images, self.pool)
+        if self.pool is not None:
+            self._futures.extend(out)
+        self.files_written += len(out)
+        return len(out)
+
+    def flush(self):
+        for f in self._futures:
+            f.result()
+        self._futures = []
+
+
+# --------------------------------------------------------------------------- train / val JSON
+
+def iter_through_images_in(image_root: Path, extension: str = 'png') -> Iterable[Path]:
+    """coco_gt.py:137-140 (glob order, unsorted, as the reference)."""
+    yield from Path(image_root).glob(f'**/*.{extension}')
+
+
+def determine_classes_in_image(image, class_to_color_map: Dict) -> Dict[str, bool]:
+    """coco_gt.py:51-65 on a PIL image or an [S, 2S, 3] array: has_<class> for every non-background class."""
+    data = numpy.array(image)
+    _, label_image = numpy.split(data, 2, axis=1)
+    colors = BaseDatasetSegmenter.load_class_to_color_map(class_to_color_map)
+    present = {}
+    for class_name, color in colors.items():
+        if class_name == 'background':
+            continue
+        class_mask = numpy.multiply.reduce(label_image[:, :] == color, axis=2)
+        contours, _ = cv2.findContours(class_mask.astype('uint8'), cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+        present[f'has_{class_name}'] = any(c.size >= 6 for c in contours)      # extract_rle keeps contours with >= 3 points
+    return present
+
+
+def create_dataset_json_data(image_paths: Sequence[Path], image_root: Path, class_to_color_map: Dict) -> List[dict]:
+    """:151-167."""
+    out = []
+    for path in image_paths:
+        with Image.open(str(path)) as im:
+            entry = {'file_name': str(Path(path).relative_to(image_root))}
+            entry.update(determine_classes_in_image(im, class_to_color_map))
+        out.append(entry)
+    return out
+
+
+def write_train_val_split(image_root, class_to_color_map: Dict, seed: int) -> Tuple[Path, Path]:
+    """main, :181-202: shuffle the PNG list under random.seed(seed), first 90 % -> train.json, rest -> val.json."""
+    image_root = Path(image_root)
+    images = list(iter_through_images_in(image_root))
+    random.seed(seed)
+    random.shuffle(images)
+    split = int(len(images) * 0.9)
+    names = []
+    for name, part in (('train.json', images[:split]), ('val.json', images[split:])):
+        with (image_root / name).open('w') as f:
+            json.dump(create_dataset_json_data(part, image_root, class_to_color_map), f)
+        names.append(image_root / name)
+    return names[0], names[1]
+
+
+def build_dataset(pair_generator, base_dir, num_images: int, contour_pool=None, writer_pool=None, depth: int = 2) -> Dict:
+    """build_dataset's loop (:109-148) on the pipelined B200 path: `pair_generator` is a LabelledPairGenerator; contour
+    tasks run on `contour_pool`, PNG writes on `writer_pool`.  Returns counters."""
+    writer = DatasetWriter(base_dir, num_images, pair_generator.rank, pair_generator.world_size, writer_pool,
+                           device=pair_generator.generator.input.input.device if pair_generator.world_size > 1 else None)
+    batches = 0
+    for sb in pair_generator.iter_segmented(depth=depth, pool=contour_pool):
+        writer.add(sb.images, sb.label_images, sb.image_ids_to_drop)
+        batches += 1
+        if writer.finished:
+            break
+    writer.flush()
+    return {'images_kept_all_ranks': writer.n, 'files_written_this_rank': writer.files_written, 'batches_this_rank': batches}

@@ -207,8 +207,13 @@ class BaseDatasetSegmenter:
             resized[key] = out
         return resized
 
+    @staticmethod
+    def dilate_image(image, kernel=None, kernel_size: int = 3):
+        from . import contours
+        return contours.dilate_image(image, kernel, kernel_size)
+
     def create_segmentation_image(self, activations):
-        raise NotImplementedError('CPU contour post-processing is a SURVEY.md §8f "next" row')
+        raise NotImplementedError
 
 
 class ClusterSegmenter(BaseDatasetSegmenter):
@@ -368,6 +373,90 @@ class ClusterSegmenter(BaseDatasetSegmenter):
                 merged[class_name] = acc
             predicted_clusters[dst_key] = merged
         return predicted_clusters
+
+
+    # -- host-side contour stage (contours.py; base_cluster_based…:148-450, black_white…:42-99) ------------------
+    def contour_config(self):
+        from . import contours
+        return contours.ContourConfig(self.image_size, self.class_to_color_map, self.keys_for_class_determination,
+                                      self.keys_for_finegrained_segmentation, self.only_keep_overlapping,
+                                      self.min_class_contour_area)
+
+    def cluster_image_to_contours(self, cluster_arrays):
+        from . import contours
+        return contours.cluster_image_to_contours(cluster_arrays)
+
+    def contour_overlap(self, contour1, contour2) -> int:
+        from . import contours
+        return contours.contour_overlap(contour1, contour2)
+
+    def merge_two_contours_if_overlapping(self, contour1, contour2):
+        from . import contours
+        return contours.merge_two_contours_if_overlapping(contour1, contour2)
+
+    def merge_contours(self, contours_, only_keep_overlapping: bool = False):
+        from . import contours
+        return contours.merge_contours(contours_, only_keep_overlapping)
+
+    def merge_contours_of_same_class_from_different_images(self, class_contours_for_sub_images, batch_size: int,
+                                                           only_keep_overlapping: bool = False, class_names_to_merge=(),
+                                                           drop_if_size_of_contours_zero: bool = False):
+        from . import contours
+        return contours.merge_contours_of_same_class_from_different_images(
+            class_contours_for_sub_images, batch_size, only_keep_overlapping, class_names_to_merge, drop_if_size_of_contours_zero)
+
+    def merge_contours_of_same_class_from_same_image(self, class_contours):
+        from . import contours
+        return contours.merge_contours_of_same_class_from_same_image(class_contours)
+
+    def extract_contours(self, predicted_clusters: PredictedClusters, image_ids_to_extract: List[str]):
+        from . import contours
+        return contours.extract_contours(predicted_clusters, image_ids_to_extract)
+
+    def extract_text_regions(self, predicted_clusters: PredictedClusters, batch_size: int):
+        """black_white…:42-59."""
+        merged = self.merge_contours_of_same_class_from_different_images(
+            self.extract_contours(predicted_clusters, self.keys_for_class_determination), batch_size,
+            only_keep_overlapping=self.only_keep_overlapping, drop_if_size_of_contours_zero=True)
+        return self.drop_too_small_contours(merged)
+
+    def merge_finegrained_segmentation(self, predicted_clusters: PredictedClusters, batch_size: int):
+        """base_cluster_based…:334-349."""
+        return self.merge_contours_of_same_class_from_different_images(
+            self.extract_contours(predicted_clusters, self.keys_for_finegrained_segmentation), batch_size,
+            only_keep_overlapping=True, drop_if_size_of_contours_zero=True)
+
+    def classify_fine_grained_contours(self, text_regions_per_class, fine_grained_contours_per_class,
+                                       fine_grained_class_name: str = 'printed_text'):
+        from . import contours
+        return contours.classify_fine_grained_contours(text_regions_per_class, fine_grained_contours_per_class,
+                                                       self.class_id_map, fine_grained_class_name)
+
+    def drop_too_small_contours(self, class_contours):
+        from . import contours
+        return contours.drop_too_small_contours(class_contours, self.min_class_contour_area)
+
+    def determine_images_to_drop(self, fine_grained_contours_per_image) -> List[int]:
+        from . import contours
+        return contours.determine_images_to_drop(fine_grained_contours_per_image, self.image_size)
+
+    def render_segmentation_image(self, fine_grained_prediction, classified_contours, batch_size: int,
+                                  cluster_class_name: str = 'printed_text'):
+        from . import contours
+        return contours.render_segmentation_image(fine_grained_prediction, classified_contours, batch_size, self.image_size,
+                                                  self.class_to_color_map, cluster_class_name)
+
+    def segment_predicted_clusters(self, predicted_clusters: PredictedClusters, batch_size: int, pool=None):
+        """The host half of create_segmentation_image on masks that are already merged and resized (device tensors or
+        host arrays); `pool` = a concurrent.futures executor to fan the images out over."""
+        from . import contours
+        return contours.segment_masks_parallel(predicted_clusters, batch_size, self.contour_config(), pool)
+
+    def create_segmentation_image(self, activations: Dict[int, torch.Tensor], pool=None):
+        """black_white…:77-99: (uint8 [B,S,S,3] colour label images, ids of images to drop).  The batch size is read
+        from the constant-input capture `activations[0]`, as the reference does (:79)."""
+        predicted_clusters = self.merge_sub_images(self.prepare_image_segmentation(activations, self.class_label_map))
+        return self.segment_predicted_clusters(predicted_clusters, len(activations[0]), pool)
 
 
 def make_image(images: torch.Tensor) -> torch.Tensor:

@@ -143,3 +143,54 @@ def test_in_forward_labelling_equals_separate_calls(cuda_device):
         for cn in NAMES:
             assert torch.equal(a.masks[layer][cn], b.masks[layer][cn]), (layer, cn)
         assert torch.equal(counts_a[layer], seg.cluster_pixel_counts[layer])
+
+
+def test_create_segmentation_image_equals_oracle_contour_stage(cuda_device):
+    """§8(f) row 1 on the device pipeline: masks from the B200 labeller, contour stage vs the oracle restatement of the
+    reference's create_segmentation_image on the same masks (colour label images and drop list identical)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import contour_oracle as co
+    layers = ['4', '5', '6', '7']
+    spec, sd, g, seg, cents = make_setup(32, layers, cuda_device)
+    seg.min_class_contour_area = 2
+    cfg = {'batch_size': 4, 'latent_size': 512}
+    lat = next(iter(dc.build_latent_and_noise_generator(g, cfg, seed=1)))
+    acts, image = dc.generate_images(lat, g, device=cuda_device)
+    label_images, drop = seg.create_segmentation_image(acts)
+    assert label_images.shape == (4, 32, 32, 3) and label_images.dtype.name == 'uint8'
+    masks = seg.merge_sub_images(seg.prepare_image_segmentation(acts))
+    host = {k: {n: m.cpu().numpy() for n, m in v.items()} for k, v in masks.items()}
+    want_images, want_drop = co.create_segmentation_image(host, 4, 32, seg.class_to_color_map, layers[:2], layers[2:],
+                                                          seg.only_keep_overlapping, seg.min_class_contour_area)
+    assert (label_images == want_images).all() and sorted(drop) == sorted(want_drop)
+    with ThreadPoolExecutor(2) as pool:
+        par_images, par_drop = seg.create_segmentation_image(acts, pool=pool)
+    assert (par_images == label_images).all() and sorted(par_drop) == sorted(drop)
+
+
+def test_build_dataset_writes_the_reference_layout(cuda_device, tmp_path):
+    """§8(f) rows 1+2 end to end: pipelined generate -> label -> contours -> PNG tree; every file is make_image || label
+    image of a kept sample, ids are the running count of kept images."""
+    import numpy
+    from concurrent.futures import ThreadPoolExecutor
+    from PIL import Image
+
+    from synthesis_in_style_b200 import dataset_writer as dw
+    layers = ['4', '5', '6', '7']
+    spec, sd, g, seg, cents = make_setup(32, layers, cuda_device)
+    cfg = {'batch_size': 4, 'latent_size': 512}
+    with ThreadPoolExecutor(2) as cpool, ThreadPoolExecutor(2) as wpool:
+        stats = dw.build_dataset(dc.LabelledPairGenerator(g, seg, cfg, seed=1), tmp_path, 10, cpool, wpool)
+    files = sorted(tmp_path.glob('**/*.png'))
+    assert stats['images_kept_all_ranks'] >= 10 and len(files) == stats['files_written_this_rank'] == stats['images_kept_all_ranks']
+    # replay the stream without the pipeline
+    expect = []
+    for b, batch in zip(range(stats['batches_this_rank']), dc.LabelledPairGenerator(g, seg, cfg, seed=1)):
+        labels, drop = seg.segment_predicted_clusters(batch.masks, 4)
+        imgs = labelling.make_image(batch.image).cpu().numpy()
+        expect += [numpy.concatenate([imgs[i], labels[i]], axis=1) for i in range(4) if i not in drop]
+    assert len(expect) == len(files)
+    for i, f in enumerate(files):
+        assert f.relative_to(tmp_path).as_posix() == f'0/0/{i:04d}.png'
+        assert numpy.array_equal(numpy.array(Image.open(f)), expect[i])
