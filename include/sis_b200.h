@@ -206,6 +206,31 @@ SIS_API int sis_or_u8(uint8_t* d_dst, const uint8_t* d_src, int64_t n, void* str
  * [batch,3,S,S] fp32 -> [batch,S,S,3] uint8, clamp(-1,1), (x+1)/2*255 truncated. */
 SIS_API int sis_make_image_u8(const float* d_image, int batch, int size, uint8_t* d_out, void* stream);
 
+/* -----------------------------------------------------------------------------------------------------------
+ * DatasetGAN labeller (the other `segmenter_type`): every capture -> ensemble of per-pixel MLP classifiers -> labels.
+ * Replaces DatasetGANSegmenter.create_segmentation_image's device work
+ *   scf/segmentation/dataset_gan_segmenter.py:34-60  (predict_labels, label_images_to_color_images)
+ *   scf/data/dataset_gan_dataset.py:12-34            (scale_activations: bilinear upsample to S x S + concat)
+ *   scf/networks/pixel_classifier/model.py:40-121    (PixelClassifier n_class < 32: Linear F->128, ReLU, BatchNorm1d,
+ *                                                     Linear 128->32, ReLU, BatchNorm1d, Linear 32->n; ensemble mode vote)
+ * Networks are in eval mode.  Parameters are set per network under the reference's state-dict keys
+ * ("layers.0.weight" [128,F], "layers.0.bias", "layers.2.{weight,bias,running_mean,running_var}", "layers.3.*",
+ * "layers.5.*", "layers.6.weight" [n,32], "layers.6.bias") from HOST memory, then `prepare` uploads them.
+ * `label`: captures in the generator's dict order (their channels must sum to feature_size), fp32 NCHW on the device;
+ *   d_labels [batch,S,S] uint8 (required), d_votes [batch,S,S,n_models] uint8 (optional),
+ *   host_colors [n_class*3] uint8 in HOST memory + d_color_image [batch,S,S,3] uint8 (optional, both or neither).
+ * Asynchronous on `stream`; `check` synchronises it and reports a fired GEMM watchdog.
+ * ----------------------------------------------------------------------------------------------------------- */
+typedef struct sis_pixel_ensemble sis_pixel_ensemble;
+SIS_API int sis_pixel_ensemble_create(sis_pixel_ensemble** out, int n_models, int feature_size, int n_class);
+SIS_API void sis_pixel_ensemble_destroy(sis_pixel_ensemble* e);
+SIS_API int sis_pixel_ensemble_set_param(sis_pixel_ensemble* e, int model, const char* name, const float* host_data, int64_t numel);
+SIS_API int sis_pixel_ensemble_prepare(sis_pixel_ensemble* e, void* stream);
+SIS_API int sis_pixel_ensemble_label(sis_pixel_ensemble* e, int n_layers, const float* const* d_activations, const int* channels,
+                             const int* resolutions, int batch, int image_size, uint8_t* d_labels, uint8_t* d_votes,
+                             const uint8_t* host_colors, uint8_t* d_color_image, void* stream);
+SIS_API int sis_pixel_ensemble_check(sis_pixel_ensemble* e, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

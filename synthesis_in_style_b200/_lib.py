@@ -79,6 +79,13 @@ _SIGNATURES = {
     'sis_nearest_resize_u8': (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'sis_or_u8': (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     'sis_make_image_u8': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    'sis_pixel_ensemble_create': (c_int, [POINTER(c_void_p), c_int, c_int, c_int]),
+    'sis_pixel_ensemble_destroy': (None, [c_void_p]),
+    'sis_pixel_ensemble_set_param': (c_int, [c_void_p, c_int, c_char_p, c_void_p, c_int64]),
+    'sis_pixel_ensemble_prepare': (c_int, [c_void_p, c_void_p]),
+    'sis_pixel_ensemble_label': (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_int), POINTER(c_int), c_int, c_int, c_void_p, c_void_p,
+                                         c_void_p, c_void_p, c_void_p]),
+    'sis_pixel_ensemble_check': (c_int, [c_void_p, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

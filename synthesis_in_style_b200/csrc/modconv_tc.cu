@@ -889,6 +889,49 @@ __global__ void __launch_bounds__(256) prescale_split_kernel(bf16* __restrict__ 
     }
 }
 
+// NCHW fp32 plane set -> a channel slice [c_off, c_off + C) of an NHWC bf16 hi/lo plane pair with c_total channels
+// (unscaled).  64 channels x 32 pixels per block through shared memory: reads are 128 B runs along the pixels, writes
+// 128 B runs along the channels.  Used by the DatasetGAN labeller to stack the captures of one resolution along K.
+__global__ void __launch_bounds__(256) nchw_to_nhwc_split_kernel(bf16* __restrict__ hi, bf16* __restrict__ lo, const float* __restrict__ x,
+                                                                 int C, int64_t hw, int c_total, int c_off) {
+    __shared__ float tile[64][33];
+    const int b = blockIdx.z, c0 = blockIdx.y * 64;
+    const int64_t p0 = (int64_t)blockIdx.x * 32;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int cc = w; cc < 64; cc += 8) {
+        const int c = c0 + cc;
+        float v = 0.0f;
+        if (c < C && p0 + lane < hw) v = __ldg(x + ((int64_t)b * C + c) * hw + p0 + lane);
+        tile[cc][lane] = v;
+    }
+    __syncthreads();
+    for (int pp = w; pp < 32; pp += 8) {
+        const int64_t p = p0 + pp;
+        const int c = c0 + 2 * lane;
+        if (p >= hw || c >= C) continue;
+        const float v0 = tile[2 * lane][pp], v1 = tile[2 * lane + 1][pp];
+        const bf16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+        const bf16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+        const int64_t o = ((int64_t)b * hw + p) * c_total + c_off + c;
+        *reinterpret_cast<uint32_t*>(hi + o) = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        *reinterpret_cast<uint32_t*>(lo + o) = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+}
+
+// W [N][k_total] fp32 (row-major), columns [k_off, k_off + K) -> columns [out_off, out_off + K) of hi/lo [N][out_total] bf16
+__global__ void __launch_bounds__(256) pack_matrix_split_kernel(bf16* __restrict__ hi, bf16* __restrict__ lo, const float* __restrict__ w,
+                                                                int N, int K, int k_total, int k_off, int out_total, int out_off) {
+    const int64_t total = (int64_t)N * K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int n = (int)(i / K), k = (int)(i - (int64_t)n * K);
+        const float v = w[(int64_t)n * k_total + k_off + k];
+        const bf16 h = __float2bfloat16_rn(v);
+        const int64_t o = (int64_t)n * out_total + out_off + k;
+        hi[o] = h;
+        lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
 // scale*W [Cout][Cin][9] fp32 -> hi/lo [9][Cout][Cin] bf16
 __global__ void __launch_bounds__(256) pack_weights_kernel(bf16* __restrict__ hi, bf16* __restrict__ lo, const float* __restrict__ w,
                                                            float scale, int cout, int cin) {
@@ -1295,6 +1338,64 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
         SIS_CHECK_LAUNCH();
     }
     return SIS_OK;
+}
+
+// ------------------------------------------------------------------------------- 1x1 GEMM (DatasetGAN labeller)
+int tc_nchw_to_nhwc_split(void* hi, void* lo, const float* x, int batch, int c, int64_t hw, int c_total, int c_off, cudaStream_t stream) {
+    SIS_REQUIRE(c % 2 == 0 && c_off % 2 == 0 && c_total % 2 == 0, "nchw_to_nhwc_split: channel counts must be even");
+    dim3 grid((unsigned)ceil_div64(hw, 32), (unsigned)ceil_div(c, 64), (unsigned)batch);
+    ProfScope prof(PROF_OTHER, stream);
+    nchw_to_nhwc_split_kernel<<<grid, 256, 0, stream>>>((bf16*)hi, (bf16*)lo, x, c, hw, c_total, c_off);
+    SIS_CHECK_LAUNCH();
+    return SIS_OK;
+}
+
+int tc_pack_matrix_split(void* hi, void* lo, const float* w, int n, int k, int k_total, int k_off, int out_total, int out_off, cudaStream_t stream) {
+    const int64_t total = (int64_t)n * k;
+    int grid = (int)std::min<int64_t>(ceil_div64(total, 256), (int64_t)kNumSMs * 8);
+    pack_matrix_split_kernel<<<grid, 256, 0, stream>>>((bf16*)hi, (bf16*)lo, w, n, k, k_total, k_off, out_total, out_off);
+    SIS_CHECK_LAUNCH();
+    return SIS_OK;
+}
+
+// out[b, n, y, x] = sum_k W[n, k] * A[b, y, x, k]: the conv GEMM with a single tap and the plain epilogue without
+// noise / bias / activation (`ones` [B, cout] stands in for the demodulation factors).
+int tc_conv1x1(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, int batch, int res, int cin, int cout,
+               const float* ones, float* out_nchw, unsigned int* d_error, cudaStream_t stream) {
+    SIS_REQUIRE(cin % 32 == 0, "tc_conv1x1: K must be a multiple of 32 (got %d)", cin);
+    SIS_REQUIRE(cout % 32 == 0, "tc_conv1x1: N must be a multiple of 32 (got %d)", cout);
+    const int BK = (cin % 64 == 0) ? 64 : 32;
+    const int64_t m_tiles = ceil_div64((int64_t)batch * res * res, BM);
+    int BN = 32;
+    for (int cand = 256; cand >= 32; cand /= 2) {
+        if (cout % cand) continue;
+        if (m_tiles * (cout / cand) >= kNumSMs || cand == 32) { BN = cand; break; }
+    }
+    const int n_tiles = cout / BN;
+    const int CG = (BN >= 64 && m_tiles * n_tiles >= 2 * kNumSMs) ? 2 : 1;
+    TcKernelArgs a;
+    memset(&a, 0, sizeof(a));
+    a.batch = batch; a.cin = cin; a.cout = cout; a.kchunks = cin / BK;
+    a.b_tiles = batch; a.n_tiles = n_tiles;
+    a.demod = ones; a.error = d_error; a.act = 0; a.im2col = 1; a.mode = 0; a.nsub = 1;
+    TcSubProblem& s = a.sub[0];
+    s.ntaps = 1; s.dy[0] = 0; s.dx[0] = 0; s.widx[0] = 0;
+    s.oh = res; s.ow = res; s.ostride = 1; s.ooff_y = 0; s.ooff_x = 0;
+    s.tiles_y = ceil_div(res, 8); s.tiles_x = ceil_div(res, 16); s.tile_begin = 0;
+    s.m_tiles = (int)m_tiles; s.base_dy = 0; s.base_dx = 0;
+    a.total_tiles = ceil_div((int)m_tiles, CG) * n_tiles;
+    a.out_f32 = out_nchw; a.out_h = res; a.out_w = res;
+    TcMaps maps;
+    memset(&maps, 0, sizeof(maps));
+    SIS_PROPAGATE(make_im2col_map(&maps.a[0][0], const_cast<void*>(a_hi), cin, res, res, batch, 0, 0, 0, 0, BK, BK * 2));
+    SIS_PROPAGATE(make_im2col_map(&maps.a[0][1], const_cast<void*>(a_lo), cin, res, res, batch, 0, 0, 0, 0, BK, BK * 2));
+    const uint64_t wdims[3] = {(uint64_t)cin, (uint64_t)cout, 1};
+    const uint32_t wbox[3] = {(uint32_t)BK, (uint32_t)(BN / CG), 1};
+    SIS_PROPAGATE(make_map(&maps.w[0], const_cast<void*>(w_hi), 3, wdims, wbox, BK * 2));
+    SIS_PROPAGATE(make_map(&maps.w[1], const_cast<void*>(w_lo), 3, wdims, wbox, BK * 2));
+    ProfScope prof(PROF_CONV_TC, stream);
+    if (CG == 2) return (BK == 64) ? launch_tc_any<64, 2>(BN, 8, 16, 1, maps, a, stream) : launch_tc_any<32, 2>(BN, 8, 16, 1, maps, a, stream);
+    return (BK == 64) ? launch_tc_any<64, 1>(BN, 8, 16, 1, maps, a, stream) : launch_tc_any<32, 1>(BN, 8, 16, 1, maps, a, stream);
 }
 
 }  // namespace sis
