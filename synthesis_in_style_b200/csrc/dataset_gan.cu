@@ -27,8 +27,9 @@ namespace sis {
 constexpr int GAN_H1 = 128, GAN_H2 = 32, GAN_MAX_GROUPS = 8, GAN_MAX_MODELS = 8;
 
 struct GanTailArgs {
-    const float* y[GAN_MAX_GROUPS];     // [B][M*128][r][r] fp32, first-layer products per resolution
-    int res[GAN_MAX_GROUPS];
+    const float* y[GAN_MAX_GROUPS];     // first-layer products per resolution: fp32 [B][M*128][r][r] (NCHW) or, when
+    int res[GAN_MAX_GROUPS];            // nhwc[g], [B][r][r][M*128]
+    int nhwc[GAN_MAX_GROUPS];
     int n_groups;
     int batch, S, n_models, n_class;
     const float* b1;                    // [M][128]
@@ -136,6 +137,135 @@ __global__ void __launch_bounds__(128) dataset_gan_tail_kernel(GanTailArgs a) {
         for (int q = 0; q < a.n_models; ++q) count += (vote[q] == vote[m]);
         if (count > best_count || (count == best_count && vote[m] < label)) { best_count = count; label = vote[m]; }
     }
+    a.labels[p] = (uint8_t)label;
+    if (a.votes)
+        for (int m = 0; m < a.n_models; ++m) a.votes[p * a.n_models + m] = (uint8_t)vote[m];
+    if (a.color_image && a.colors) {
+        a.color_image[p * 3 + 0] = a.colors[label * 3 + 0];
+        a.color_image[p * 3 + 1] = a.colors[label * 3 + 1];
+        a.color_image[p * 3 + 2] = a.colors[label * 3 + 2];
+    }
+}
+
+// Tiled variant (S a multiple of 16): a block is a 16 x 8 pixel tile.  The low-resolution products are NHWC; per network
+// and resolution the tile's source footprint (at most 6 x 10 pixels x 128 channels) is staged in shared memory with
+// 512 B coalesced rows and every thread accumulates its four taps from there; the full-resolution product is NCHW and is
+// read directly (consecutive lanes = consecutive pixels).
+constexpr int GAN_TX = 16, GAN_TY = 8, GAN_SRC_STRIDE = GAN_H1 + 4, GAN_SRC_PIX = 60;
+constexpr int GAN_TILED_SMEM = (GAN_SRC_PIX * GAN_SRC_STRIDE + GAN_H1 * GAN_H2 + GAN_H1 + GAN_H2 + 31 * GAN_H2 + 32) * 4;
+
+__device__ __forceinline__ void gan_src_range(int o0, int n, int r, int S, int& lo, int& hi) {
+    const float sc = (float)r / (float)S;
+    lo = (int)fmaxf(((float)o0 + 0.5f) * sc - 0.5f, 0.0f);
+    hi = min((int)fmaxf(((float)(o0 + n - 1) + 0.5f) * sc - 0.5f, 0.0f) + 1, r - 1);
+}
+
+__global__ void __launch_bounds__(128) dataset_gan_tail_tiled_kernel(GanTailArgs a) {
+    extern __shared__ __align__(16) float gsm[];
+    float* s_src = gsm;
+    float* s_w2t = s_src + GAN_SRC_PIX * GAN_SRC_STRIDE;
+    float* s_b1 = s_w2t + GAN_H1 * GAN_H2;
+    float* s_b2 = s_b1 + GAN_H1;
+    float* s_w3 = s_b2 + GAN_H2;
+    float* s_b3 = s_w3 + 31 * GAN_H2;
+    const int tid = threadIdx.x;
+    const int tiles_x = a.S / GAN_TX, tiles_y = a.S / GAN_TY;
+    const int tile = blockIdx.x;
+    const int b = tile / (tiles_x * tiles_y);
+    const int trem = tile - b * tiles_x * tiles_y;
+    const int oy0 = (trem / tiles_x) * GAN_TY, ox0 = (trem % tiles_x) * GAN_TX;
+    const int oy = oy0 + tid / GAN_TX, ox = ox0 + tid % GAN_TX;
+    const int N = a.n_models * GAN_H1;
+    int vote[GAN_MAX_MODELS];
+
+    for (int m = 0; m < a.n_models; ++m) {
+        __syncthreads();
+        for (int i = tid; i < GAN_H1 * GAN_H2; i += 128) s_w2t[i] = a.w2t[(int64_t)m * GAN_H1 * GAN_H2 + i];
+        s_b1[tid] = a.b1[m * GAN_H1 + tid];
+        if (tid < GAN_H2) s_b2[tid] = a.b2[m * GAN_H2 + tid];
+        for (int i = tid; i < a.n_class * GAN_H2; i += 128) s_w3[i] = a.w3[(int64_t)m * a.n_class * GAN_H2 + i];
+        if (tid < a.n_class) s_b3[tid] = a.b3[m * a.n_class + tid];
+        __syncthreads();
+
+        float z[GAN_H1];
+#pragma unroll
+        for (int i = 0; i < GAN_H1; ++i) z[i] = s_b1[i];
+        for (int g = 0; g < a.n_groups; ++g) {
+            const int r = a.res[g];
+            if (!a.nhwc[g]) {
+                const int64_t plane = (int64_t)r * r;
+                const float* q = a.y[g] + ((int64_t)b * a.n_models + m) * GAN_H1 * plane + (int64_t)oy * r + ox;
+#pragma unroll
+                for (int i = 0; i < GAN_H1; ++i) z[i] += __ldg(q + (int64_t)i * plane);
+                continue;
+            }
+            int fy0, fy1, fx0, fx1;
+            gan_src_range(oy0, GAN_TY, r, a.S, fy0, fy1);
+            gan_src_range(ox0, GAN_TX, r, a.S, fx0, fx1);
+            const int fw = fx1 - fx0 + 1, fh = fy1 - fy0 + 1;
+            __syncthreads();                                     // the previous group's taps are consumed
+            for (int q = tid; q < fh * fw * (GAN_H1 / 4); q += 128) {
+                const int px = q / (GAN_H1 / 4), c4 = q - px * (GAN_H1 / 4);
+                const int py = px / fw, pxx = px - py * fw;
+                const float4 v = __ldg(reinterpret_cast<const float4*>(
+                    a.y[g] + (((int64_t)b * r + fy0 + py) * r + fx0 + pxx) * N + m * GAN_H1) + c4);
+                *reinterpret_cast<float4*>(s_src + px * GAN_SRC_STRIDE + c4 * 4) = v;
+            }
+            __syncthreads();
+            const float sc = (float)r / (float)a.S;
+            const float fy = fmaxf(((float)oy + 0.5f) * sc - 0.5f, 0.0f), fx = fmaxf(((float)ox + 0.5f) * sc - 0.5f, 0.0f);
+            const int y0 = (int)fy, x0 = (int)fx;
+            const int y1 = min(y0 + 1, r - 1), x1 = min(x0 + 1, r - 1);
+            const float ly = fy - (float)y0, lx = fx - (float)x0;
+            const float w00 = (1.0f - ly) * (1.0f - lx), w01 = (1.0f - ly) * lx, w10 = ly * (1.0f - lx), w11 = ly * lx;
+            const float4* q00 = reinterpret_cast<const float4*>(s_src + ((y0 - fy0) * fw + x0 - fx0) * GAN_SRC_STRIDE);
+            const float4* q01 = reinterpret_cast<const float4*>(s_src + ((y0 - fy0) * fw + x1 - fx0) * GAN_SRC_STRIDE);
+            const float4* q10 = reinterpret_cast<const float4*>(s_src + ((y1 - fy0) * fw + x0 - fx0) * GAN_SRC_STRIDE);
+            const float4* q11 = reinterpret_cast<const float4*>(s_src + ((y1 - fy0) * fw + x1 - fx0) * GAN_SRC_STRIDE);
+#pragma unroll
+            for (int i4 = 0; i4 < GAN_H1 / 4; ++i4) {
+                const float4 v00 = q00[i4], v01 = q01[i4], v10 = q10[i4], v11 = q11[i4];
+                z[4 * i4 + 0] += fmaf(w11, v11.x, fmaf(w10, v10.x, fmaf(w01, v01.x, w00 * v00.x)));
+                z[4 * i4 + 1] += fmaf(w11, v11.y, fmaf(w10, v10.y, fmaf(w01, v01.y, w00 * v00.y)));
+                z[4 * i4 + 2] += fmaf(w11, v11.z, fmaf(w10, v10.z, fmaf(w01, v01.z, w00 * v00.z)));
+                z[4 * i4 + 3] += fmaf(w11, v11.w, fmaf(w10, v10.w, fmaf(w01, v01.w, w00 * v00.w)));
+            }
+        }
+        float2 u2[GAN_H2 / 2];
+#pragma unroll
+        for (int j = 0; j < GAN_H2 / 2; ++j) u2[j] = make_float2(s_b2[2 * j], s_b2[2 * j + 1]);
+#pragma unroll
+        for (int i = 0; i < GAN_H1; ++i) {
+            const float h = fmaxf(z[i], 0.0f);
+            const float2 hh = make_float2(h, h);
+            const float4* wrow = reinterpret_cast<const float4*>(s_w2t + i * GAN_H2);
+#pragma unroll
+            for (int q = 0; q < GAN_H2 / 4; ++q) {
+                const float4 w = wrow[q];
+                u2[2 * q] = pk_fma(hh, make_float2(w.x, w.y), u2[2 * q]);
+                u2[2 * q + 1] = pk_fma(hh, make_float2(w.z, w.w), u2[2 * q + 1]);
+            }
+        }
+        float u[GAN_H2];
+#pragma unroll
+        for (int j = 0; j < GAN_H2 / 2; ++j) { u[2 * j] = fmaxf(u2[j].x, 0.0f); u[2 * j + 1] = fmaxf(u2[j].y, 0.0f); }
+        float best = -INFINITY;
+        int arg = 0;
+        for (int c = 0; c < a.n_class; ++c) {
+            float acc = s_b3[c];
+#pragma unroll
+            for (int j = 0; j < GAN_H2; ++j) acc = fmaf(s_w3[c * GAN_H2 + j], u[j], acc);
+            if (acc > best) { best = acc; arg = c; }
+        }
+        vote[m] = arg;
+    }
+    int label = 0, best_count = 0;
+    for (int m = 0; m < a.n_models; ++m) {
+        int count = 0;
+        for (int q = 0; q < a.n_models; ++q) count += (vote[q] == vote[m]);
+        if (count > best_count || (count == best_count && vote[m] < label)) { best_count = count; label = vote[m]; }
+    }
+    const int64_t p = ((int64_t)b * a.S + oy) * a.S + ox;
     a.labels[p] = (uint8_t)label;
     if (a.votes)
         for (int m = 0; m < a.n_models; ++m) a.votes[p * a.n_models + m] = (uint8_t)vote[m];
@@ -337,6 +467,9 @@ extern "C" int sis_pixel_ensemble_label(sis_pixel_ensemble* e, int n_layers, con
     }
     GanTailArgs t;
     memset(&t, 0, sizeof(t));
+    // tiled tail: 16 x 8 pixel tiles, power-of-two integer scale factors (footprints of at most 6 x 10 source pixels)
+    bool tiled = image_size % GAN_TX == 0 && image_size % GAN_TY == 0;
+    for (auto& g : e->groups) tiled = tiled && image_size % g.res == 0 && (g.res == image_size || image_size / g.res >= 2);
     int gi = 0;
     for (auto& g : e->groups) {
         int koff = 0;
@@ -344,8 +477,9 @@ extern "C" int sis_pixel_ensemble_label(sis_pixel_ensemble* e, int n_layers, con
             SIS_PROPAGATE(tc_nchw_to_nhwc_split(g.a_hi, g.a_lo, d_activations[g.layers[i]], batch, g.chan[i], (int64_t)g.res * g.res, g.k, koff, stream));
             koff += g.chan[i];
         }
-        SIS_PROPAGATE(tc_conv1x1(g.a_hi, g.a_lo, g.w_hi, g.w_lo, batch, g.res, g.k, N, e->d_ones, g.y, e->d_error, stream));
-        t.y[gi] = g.y; t.res[gi] = g.res; ++gi;
+        const bool nhwc = tiled && g.res < image_size;
+        SIS_PROPAGATE(tc_conv1x1(g.a_hi, g.a_lo, g.w_hi, g.w_lo, batch, g.res, g.k, N, e->d_ones, g.y, nhwc, e->d_error, stream));
+        t.y[gi] = g.y; t.res[gi] = g.res; t.nhwc[gi] = nhwc ? 1 : 0; ++gi;
     }
     t.n_groups = gi; t.batch = batch; t.S = image_size; t.n_models = M; t.n_class = e->n_class;
     t.b1 = e->d_b1; t.w2t = e->d_w2t; t.b2 = e->d_b2; t.w3 = e->d_w3; t.b3 = e->d_b3;
@@ -353,7 +487,17 @@ extern "C" int sis_pixel_ensemble_label(sis_pixel_ensemble* e, int n_layers, con
     const int64_t total = (int64_t)batch * image_size * image_size;
     {
         ProfScope prof(PROF_LABEL, stream);
-        dataset_gan_tail_kernel<<<(unsigned)ceil_div64(total, 128), 128, 0, stream>>>(t);
+        if (tiled) {
+            static bool configured = false;
+            if (!configured) {
+                SIS_CHECK_CUDA(cudaFuncSetAttribute(dataset_gan_tail_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GAN_TILED_SMEM));
+                configured = true;
+            }
+            const unsigned tiles = (unsigned)((int64_t)batch * (image_size / GAN_TX) * (image_size / GAN_TY));
+            dataset_gan_tail_tiled_kernel<<<tiles, 128, GAN_TILED_SMEM, stream>>>(t);
+        } else {
+            dataset_gan_tail_kernel<<<(unsigned)ceil_div64(total, 128), 128, 0, stream>>>(t);
+        }
         SIS_CHECK_LAUNCH();
     }
     return SIS_OK;

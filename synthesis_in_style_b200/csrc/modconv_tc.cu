@@ -1359,9 +1359,10 @@ int tc_pack_matrix_split(void* hi, void* lo, const float* w, int n, int k, int k
 }
 
 // out[b, n, y, x] = sum_k W[n, k] * A[b, y, x, k]: the conv GEMM with a single tap and the plain epilogue without
-// noise / bias / activation (`ones` [B, cout] stands in for the demodulation factors).
+// noise / bias / activation (`ones` [B, cout] stands in for the demodulation factors); fp32 NCHW out, or NHWC
+// [B][res][res][cout] with `out_nhwc`.
 int tc_conv1x1(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, int batch, int res, int cin, int cout,
-               const float* ones, float* out_nchw, unsigned int* d_error, cudaStream_t stream) {
+               const float* ones, float* out, bool out_nhwc, unsigned int* d_error, cudaStream_t stream) {
     SIS_REQUIRE(cin % 32 == 0, "tc_conv1x1: K must be a multiple of 32 (got %d)", cin);
     SIS_REQUIRE(cout % 32 == 0, "tc_conv1x1: N must be a multiple of 32 (got %d)", cout);
     const int BK = (cin % 64 == 0) ? 64 : 32;
@@ -1377,14 +1378,14 @@ int tc_conv1x1(const void* a_hi, const void* a_lo, const void* w_hi, const void*
     memset(&a, 0, sizeof(a));
     a.batch = batch; a.cin = cin; a.cout = cout; a.kchunks = cin / BK;
     a.b_tiles = batch; a.n_tiles = n_tiles;
-    a.demod = ones; a.error = d_error; a.act = 0; a.im2col = 1; a.mode = 0; a.nsub = 1;
+    a.demod = ones; a.error = d_error; a.act = 0; a.im2col = 1; a.mode = out_nhwc ? 1 : 0; a.nsub = 1;
     TcSubProblem& s = a.sub[0];
     s.ntaps = 1; s.dy[0] = 0; s.dx[0] = 0; s.widx[0] = 0;
     s.oh = res; s.ow = res; s.ostride = 1; s.ooff_y = 0; s.ooff_x = 0;
     s.tiles_y = ceil_div(res, 8); s.tiles_x = ceil_div(res, 16); s.tile_begin = 0;
     s.m_tiles = (int)m_tiles; s.base_dy = 0; s.base_dx = 0;
     a.total_tiles = ceil_div((int)m_tiles, CG) * n_tiles;
-    a.out_f32 = out_nchw; a.out_h = res; a.out_w = res;
+    a.out_f32 = out; a.out_h = res; a.out_w = res;
     TcMaps maps;
     memset(&maps, 0, sizeof(maps));
     SIS_PROPAGATE(make_im2col_map(&maps.a[0][0], const_cast<void*>(a_hi), cin, res, res, batch, 0, 0, 0, 0, BK, BK * 2));

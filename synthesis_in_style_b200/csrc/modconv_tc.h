@@ -51,10 +51,10 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
 int tc_check_error(TcWorkspace& ws, cudaStream_t stream);
 
 // DatasetGAN labeller building blocks: capture -> channel slice of an NHWC bf16 hi/lo pair, weight matrix slice -> hi/lo,
-// and the single-tap GEMM out[b,n,y,x] = sum_k W[n,k] A[b,y,x,k] (fp32 NCHW out).
+// and the single-tap GEMM out[b,n,y,x] = sum_k W[n,k] A[b,y,x,k] (fp32 NCHW, or NHWC, out).
 int tc_nchw_to_nhwc_split(void* hi, void* lo, const float* x, int batch, int c, int64_t hw, int c_total, int c_off, cudaStream_t stream);
 int tc_pack_matrix_split(void* hi, void* lo, const float* w, int n, int k, int k_total, int k_off, int out_total, int out_off, cudaStream_t stream);
 int tc_conv1x1(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, int batch, int res, int cin, int cout,
-               const float* ones, float* out_nchw, unsigned int* d_error, cudaStream_t stream);
+               const float* ones, float* out, bool out_nhwc, unsigned int* d_error, cudaStream_t stream);
 
 }  // namespace sis
