@@ -1207,18 +1207,19 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
         if (call.cout % cand) continue;
         if (m_tiles_all * (call.cout / cand) >= kNumSMs || cand == 32) { BN = cand; break; }
     }
-    if (m_tiles_all * (call.cout / BN) < 4 * kNumSMs) {
-        // few tiles (4^2 .. 16^2 layers): the rule above can land on 1.x waves of narrow tiles.  Pick the N tile by a
-        // small cost model instead: waves x per-K-block time, the latter the larger of the MMA time (3 passes x 4 K
-        // steps x BN/2 clk) and the L2 -> SM fill of the stage (A 32 KB, or 5 KB per tap with halo reuse, + B BN x 256 B at
-        // ~60 B/clk/SM).
+    if (!call.up && !halo && m_tiles_all * (call.cout / BN) < 4 * kNumSMs) {
+        // the 4^2 / 8^2 plain layers have a handful of pixel tiles, and the rule above can land on 1.x waves of narrow
+        // tiles.  Pick the N tile by a small cost model instead: waves x per-K-block time, the latter the larger of the
+        // MMA time (12 instructions of max(BN/2, (128 + BN)/4) clk: math, or operand fetch from shared memory at
+        // 128 B/clk) and the L2 -> SM fill of the stage (A 32 KB + B BN x 256 B at ~60 B/clk/SM).  Measured: 8^2 layer
+        // 89 -> 51 us.  (Applied to the plain per-tap kernel only; it mispredicts the halo and the 4-phase layers.)
         double best = 1e30;
         for (int cand = 256; cand >= 32; cand /= 2) {
             if (call.cout % cand) continue;
             const int64_t tiles_c = m_tiles_all * (call.cout / cand);
             const double waves = (double)((tiles_c + kNumSMs - 1) / kNumSMs);
-            const double kblock = std::max(6.0 * cand, ((halo ? 5120.0 : 32768.0) + 256.0 * cand) / 60.0);
-            const double cost = waves * (kblock + 40.0 * cand / std::max(1, 9 * call.cin / 64));   // + epilogue share per K block
+            const double mma = 12.0 * std::max(cand / 2.0, (128.0 + cand) / 4.0);
+            const double cost = waves * std::max(mma, (32768.0 + 256.0 * cand) / 60.0);
             if (cost < best) { best = cost; BN = cand; }
         }
     }
