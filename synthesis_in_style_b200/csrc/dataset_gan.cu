@@ -147,12 +147,13 @@ __global__ void __launch_bounds__(128) dataset_gan_tail_kernel(GanTailArgs a) {
     }
 }
 
-// Tiled variant (S a multiple of 16): a block is a 16 x 8 pixel tile.  The low-resolution products are NHWC; per network
-// and resolution the tile's source footprint (at most 6 x 10 pixels x 128 channels) is staged in shared memory with
-// 512 B coalesced rows and every thread accumulates its four taps from there; the full-resolution product is NCHW and is
-// read directly (consecutive lanes = consecutive pixels).
-constexpr int GAN_TX = 16, GAN_TY = 8, GAN_SRC_STRIDE = GAN_H1 + 4, GAN_SRC_PIX = 60;
-constexpr int GAN_TILED_SMEM = (GAN_SRC_PIX * GAN_SRC_STRIDE + GAN_H1 * GAN_H2 + GAN_H1 + GAN_H2 + 31 * GAN_H2 + 32) * 4;
+// Tiled variant (S a multiple of 16): a block is a 16 x 8 pixel tile.  The low-resolution products are NHWC; per network,
+// 32-channel chunk and resolution the tile's source footprint (at most 6 x 10 pixels) is staged in shared memory with
+// 128 B coalesced rows and every thread accumulates its four taps from there; the full-resolution product is NCHW and
+// is read directly (consecutive lanes = consecutive pixels).  Working in 32-channel chunks keeps a thread at 32
+// activations + 32 second-layer accumulators (the chunk is folded into Linear2 as soon as it is complete), so four
+// blocks fit on an SM.
+constexpr int GAN_TX = 16, GAN_TY = 8, GAN_CH = 32, GAN_SRC_STRIDE = GAN_CH + 4, GAN_SRC_PIX = 60;
 
 __device__ __forceinline__ void gan_src_range(int o0, int n, int r, int S, int& lo, int& hi) {
     const float sc = (float)r / (float)S;
@@ -160,14 +161,10 @@ __device__ __forceinline__ void gan_src_range(int o0, int n, int r, int S, int& 
     hi = min((int)fmaxf(((float)(o0 + n - 1) + 0.5f) * sc - 0.5f, 0.0f) + 1, r - 1);
 }
 
-__global__ void __launch_bounds__(128) dataset_gan_tail_tiled_kernel(GanTailArgs a) {
-    extern __shared__ __align__(16) float gsm[];
-    float* s_src = gsm;
-    float* s_w2t = s_src + GAN_SRC_PIX * GAN_SRC_STRIDE;
-    float* s_b1 = s_w2t + GAN_H1 * GAN_H2;
-    float* s_b2 = s_b1 + GAN_H1;
-    float* s_w3 = s_b2 + GAN_H2;
-    float* s_b3 = s_w3 + 31 * GAN_H2;
+__global__ void __launch_bounds__(128, 4) dataset_gan_tail_tiled_kernel(GanTailArgs a) {
+    __shared__ __align__(16) float s_src[GAN_SRC_PIX * GAN_SRC_STRIDE];
+    __shared__ __align__(16) float s_w2t[GAN_H1 * GAN_H2];
+    __shared__ float s_b1[GAN_H1], s_b2[GAN_H2], s_w3[31 * GAN_H2], s_b3[32];
     const int tid = threadIdx.x;
     const int tiles_x = a.S / GAN_TX, tiles_y = a.S / GAN_TY;
     const int tile = blockIdx.x;
@@ -187,63 +184,70 @@ __global__ void __launch_bounds__(128) dataset_gan_tail_tiled_kernel(GanTailArgs
         if (tid < a.n_class) s_b3[tid] = a.b3[m * a.n_class + tid];
         __syncthreads();
 
-        float z[GAN_H1];
-#pragma unroll
-        for (int i = 0; i < GAN_H1; ++i) z[i] = s_b1[i];
-        for (int g = 0; g < a.n_groups; ++g) {
-            const int r = a.res[g];
-            if (!a.nhwc[g]) {
-                const int64_t plane = (int64_t)r * r;
-                const float* q = a.y[g] + ((int64_t)b * a.n_models + m) * GAN_H1 * plane + (int64_t)oy * r + ox;
-#pragma unroll
-                for (int i = 0; i < GAN_H1; ++i) z[i] += __ldg(q + (int64_t)i * plane);
-                continue;
-            }
-            int fy0, fy1, fx0, fx1;
-            gan_src_range(oy0, GAN_TY, r, a.S, fy0, fy1);
-            gan_src_range(ox0, GAN_TX, r, a.S, fx0, fx1);
-            const int fw = fx1 - fx0 + 1, fh = fy1 - fy0 + 1;
-            __syncthreads();                                     // the previous group's taps are consumed
-            for (int q = tid; q < fh * fw * (GAN_H1 / 4); q += 128) {
-                const int px = q / (GAN_H1 / 4), c4 = q - px * (GAN_H1 / 4);
-                const int py = px / fw, pxx = px - py * fw;
-                const float4 v = __ldg(reinterpret_cast<const float4*>(
-                    a.y[g] + (((int64_t)b * r + fy0 + py) * r + fx0 + pxx) * N + m * GAN_H1) + c4);
-                *reinterpret_cast<float4*>(s_src + px * GAN_SRC_STRIDE + c4 * 4) = v;
-            }
-            __syncthreads();
-            const float sc = (float)r / (float)a.S;
-            const float fy = fmaxf(((float)oy + 0.5f) * sc - 0.5f, 0.0f), fx = fmaxf(((float)ox + 0.5f) * sc - 0.5f, 0.0f);
-            const int y0 = (int)fy, x0 = (int)fx;
-            const int y1 = min(y0 + 1, r - 1), x1 = min(x0 + 1, r - 1);
-            const float ly = fy - (float)y0, lx = fx - (float)x0;
-            const float w00 = (1.0f - ly) * (1.0f - lx), w01 = (1.0f - ly) * lx, w10 = ly * (1.0f - lx), w11 = ly * lx;
-            const float4* q00 = reinterpret_cast<const float4*>(s_src + ((y0 - fy0) * fw + x0 - fx0) * GAN_SRC_STRIDE);
-            const float4* q01 = reinterpret_cast<const float4*>(s_src + ((y0 - fy0) * fw + x1 - fx0) * GAN_SRC_STRIDE);
-            const float4* q10 = reinterpret_cast<const float4*>(s_src + ((y1 - fy0) * fw + x0 - fx0) * GAN_SRC_STRIDE);
-            const float4* q11 = reinterpret_cast<const float4*>(s_src + ((y1 - fy0) * fw + x1 - fx0) * GAN_SRC_STRIDE);
-#pragma unroll
-            for (int i4 = 0; i4 < GAN_H1 / 4; ++i4) {
-                const float4 v00 = q00[i4], v01 = q01[i4], v10 = q10[i4], v11 = q11[i4];
-                z[4 * i4 + 0] += fmaf(w11, v11.x, fmaf(w10, v10.x, fmaf(w01, v01.x, w00 * v00.x)));
-                z[4 * i4 + 1] += fmaf(w11, v11.y, fmaf(w10, v10.y, fmaf(w01, v01.y, w00 * v00.y)));
-                z[4 * i4 + 2] += fmaf(w11, v11.z, fmaf(w10, v10.z, fmaf(w01, v01.z, w00 * v00.z)));
-                z[4 * i4 + 3] += fmaf(w11, v11.w, fmaf(w10, v10.w, fmaf(w01, v01.w, w00 * v00.w)));
-            }
-        }
         float2 u2[GAN_H2 / 2];
 #pragma unroll
         for (int j = 0; j < GAN_H2 / 2; ++j) u2[j] = make_float2(s_b2[2 * j], s_b2[2 * j + 1]);
+
+#pragma unroll 1
+        for (int ch0 = 0; ch0 < GAN_H1; ch0 += GAN_CH) {
+            float z[GAN_CH];
 #pragma unroll
-        for (int i = 0; i < GAN_H1; ++i) {
-            const float h = fmaxf(z[i], 0.0f);
-            const float2 hh = make_float2(h, h);
-            const float4* wrow = reinterpret_cast<const float4*>(s_w2t + i * GAN_H2);
+            for (int i = 0; i < GAN_CH; ++i) z[i] = s_b1[ch0 + i];
+#pragma unroll 1
+            for (int g = 0; g < a.n_groups; ++g) {
+                const int r = a.res[g];
+                if (!a.nhwc[g]) {
+                    const int64_t plane = (int64_t)r * r;
+                    const float* q = a.y[g] + (((int64_t)b * a.n_models + m) * GAN_H1 + ch0) * plane + (int64_t)oy * r + ox;
 #pragma unroll
-            for (int q = 0; q < GAN_H2 / 4; ++q) {
-                const float4 w = wrow[q];
-                u2[2 * q] = pk_fma(hh, make_float2(w.x, w.y), u2[2 * q]);
-                u2[2 * q + 1] = pk_fma(hh, make_float2(w.z, w.w), u2[2 * q + 1]);
+                    for (int i = 0; i < GAN_CH; ++i) z[i] += __ldg(q + (int64_t)i * plane);
+                    continue;
+                }
+                int fy0, fy1, fx0, fx1;
+                gan_src_range(oy0, GAN_TY, r, a.S, fy0, fy1);
+                gan_src_range(ox0, GAN_TX, r, a.S, fx0, fx1);
+                const int fw = fx1 - fx0 + 1, fh = fy1 - fy0 + 1;
+                __syncthreads();                                     // the previous footprint is consumed
+                for (int q = tid; q < fh * fw * (GAN_CH / 4); q += 128) {
+                    const int px = q / (GAN_CH / 4), c4 = q - px * (GAN_CH / 4);
+                    const int py = px / fw, pxx = px - py * fw;
+                    const float4 v = __ldg(reinterpret_cast<const float4*>(
+                        a.y[g] + (((int64_t)b * r + fy0 + py) * r + fx0 + pxx) * N + m * GAN_H1 + ch0) + c4);
+                    *reinterpret_cast<float4*>(s_src + px * GAN_SRC_STRIDE + c4 * 4) = v;
+                }
+                __syncthreads();
+                // nn.Upsample(scale_factor = S / r, mode='bilinear'), align_corners = False
+                const float sc = (float)r / (float)a.S;
+                const float fy = fmaxf(((float)oy + 0.5f) * sc - 0.5f, 0.0f), fx = fmaxf(((float)ox + 0.5f) * sc - 0.5f, 0.0f);
+                const int y0 = (int)fy, x0 = (int)fx;
+                const int y1 = min(y0 + 1, r - 1), x1 = min(x0 + 1, r - 1);
+                const float ly = fy - (float)y0, lx = fx - (float)x0;
+                const float w00 = (1.0f - ly) * (1.0f - lx), w01 = (1.0f - ly) * lx, w10 = ly * (1.0f - lx), w11 = ly * lx;
+                const float4* q00 = reinterpret_cast<const float4*>(s_src + ((y0 - fy0) * fw + x0 - fx0) * GAN_SRC_STRIDE);
+                const float4* q01 = reinterpret_cast<const float4*>(s_src + ((y0 - fy0) * fw + x1 - fx0) * GAN_SRC_STRIDE);
+                const float4* q10 = reinterpret_cast<const float4*>(s_src + ((y1 - fy0) * fw + x0 - fx0) * GAN_SRC_STRIDE);
+                const float4* q11 = reinterpret_cast<const float4*>(s_src + ((y1 - fy0) * fw + x1 - fx0) * GAN_SRC_STRIDE);
+#pragma unroll
+                for (int i4 = 0; i4 < GAN_CH / 4; ++i4) {
+                    const float4 v00 = q00[i4], v01 = q01[i4], v10 = q10[i4], v11 = q11[i4];
+                    z[4 * i4 + 0] += fmaf(w11, v11.x, fmaf(w10, v10.x, fmaf(w01, v01.x, w00 * v00.x)));
+                    z[4 * i4 + 1] += fmaf(w11, v11.y, fmaf(w10, v10.y, fmaf(w01, v01.y, w00 * v00.y)));
+                    z[4 * i4 + 2] += fmaf(w11, v11.z, fmaf(w10, v10.z, fmaf(w01, v01.z, w00 * v00.z)));
+                    z[4 * i4 + 3] += fmaf(w11, v11.w, fmaf(w10, v10.w, fmaf(w01, v01.w, w00 * v00.w)));
+                }
+            }
+            // fold the finished chunk into Linear2 (BatchNorm1 folded in)
+#pragma unroll
+            for (int i = 0; i < GAN_CH; ++i) {
+                const float h = fmaxf(z[i], 0.0f);
+                const float2 hh = make_float2(h, h);
+                const float4* wrow = reinterpret_cast<const float4*>(s_w2t + (ch0 + i) * GAN_H2);
+#pragma unroll
+                for (int q = 0; q < GAN_H2 / 4; ++q) {
+                    const float4 w = wrow[q];
+                    u2[2 * q] = pk_fma(hh, make_float2(w.x, w.y), u2[2 * q]);
+                    u2[2 * q + 1] = pk_fma(hh, make_float2(w.z, w.w), u2[2 * q + 1]);
+                }
             }
         }
         float u[GAN_H2];
@@ -488,13 +492,8 @@ extern "C" int sis_pixel_ensemble_label(sis_pixel_ensemble* e, int n_layers, con
     {
         ProfScope prof(PROF_LABEL, stream);
         if (tiled) {
-            static bool configured = false;
-            if (!configured) {
-                SIS_CHECK_CUDA(cudaFuncSetAttribute(dataset_gan_tail_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GAN_TILED_SMEM));
-                configured = true;
-            }
             const unsigned tiles = (unsigned)((int64_t)batch * (image_size / GAN_TX) * (image_size / GAN_TY));
-            dataset_gan_tail_tiled_kernel<<<tiles, 128, GAN_TILED_SMEM, stream>>>(t);
+            dataset_gan_tail_tiled_kernel<<<tiles, 128, 0, stream>>>(t);
         } else {
             dataset_gan_tail_kernel<<<(unsigned)ceil_div64(total, 128), 128, 0, stream>>>(t);
         }
