@@ -13,6 +13,8 @@ collective is the final all-reduce of the statistics vector.
   roofline   dominant kernel (tcgen05 modulated-conv GEMM): algorithmic conv FLOPs / its CUDA-event time
   cpu_baseline  the oracle (CPU restatement of the reference) on this box's host cores, bounded sample
   --impl reference   the oracle alone, all host threads (the reference has no CPU path of its own)
+  gpu_reference      (N=1) the reference's graph on this GPU as the reference runs it, SURVEY §8(d)
+  --leg contours | dataset_gan   stage benchmarks of the rows after the hot path, own JSON line
 """
 import argparse
 import json
@@ -233,6 +235,114 @@ def run_reference(args, rank, world, out):
     print(json.dumps(line), file=out, flush=True)
 
 
+def run_leg_contours(args, out):
+    """`--leg contours`: CPU timing of the contour stage on synthetic document-like masks: product
+    (synthesis_in_style_b200/contours.py) vs the restatement of the reference's algorithm (oracle/contour_oracle.py),
+    same inputs, results asserted equal.  No GPU needed."""
+    from concurrent.futures import ProcessPoolExecutor
+
+    import numpy
+
+    from oracle import contour_oracle as co
+    from synthesis_in_style_b200 import contours as pc
+    colors = {'background': (0, 0, 0), 'printed_text': (0, 0, 255), 'handwritten_text': (255, 0, 0)}
+    images_n, oracle_n, size = 16, 4, SIZE
+    workers = min(8, os.cpu_count() or 1)
+    pred = co.synthetic_document_masks(21, images_n, size)
+    cfg = pc.ContourConfig(size, colors, ['8', '9'], ['12', '13'], True, 10)
+    pc.segment_masks({k: {n: m[:1] for n, m in v.items()} for k, v in pred.items()}, 1, cfg)     # warm-up
+    t0 = time.perf_counter()
+    images, drop = pc.segment_masks(pred, images_n, cfg)
+    t_prod = time.perf_counter() - t0
+    with ProcessPoolExecutor(workers) as pool:
+        for _ in range(3):
+            pc.segment_masks_parallel(pred, images_n, cfg, pool)                                  # workers start lazily
+        t0 = time.perf_counter()
+        for _ in range(3):
+            images_p, drop_p = pc.segment_masks_parallel(pred, images_n, cfg, pool)
+        t_par = (time.perf_counter() - t0) / 3
+    assert numpy.array_equal(images, images_p) and sorted(drop) == sorted(drop_p)
+    sub = {k: {nm: m[:oracle_n] for nm, m in v.items()} for k, v in pred.items()}
+    t0 = time.perf_counter()
+    o_images, o_drop = co.create_segmentation_image(sub, oracle_n, size, colors, ['8', '9'], ['12', '13'], True, 10)
+    t_or = time.perf_counter() - t0
+    assert numpy.array_equal(o_images, images[:oracle_n]) and sorted(o_drop) == sorted(d for d in drop if d < oracle_n)
+    print(json.dumps({'leg': 'contours', 'image_size': size, 'images': images_n,
+                      'product_ms_per_image_1_core': round(t_prod / images_n * 1e3, 2),
+                      'product_images_per_s_pool': round(images_n / t_par, 1), 'pool_workers': workers,
+                      'reference_algorithm_ms_per_image_1_core': round(t_or / oracle_n * 1e3, 1),
+                      'speedup_1_core': round((t_or / oracle_n) / (t_prod / images_n), 1), 'results_equal': True}), file=out, flush=True)
+
+
+def run_leg_dataset_gan(args, out):
+    """`--leg dataset_gan`: throughput of the DatasetGAN labeller at the BASELINE shape: 256^2,
+    14 captures (F = 5888), 3 networks, 3 classes; captures from the B200 generator.  Timed with CUDA events:
+    sis_pixel_ensemble_label over a batch and its per-category split; beside it the reference's algorithm in PyTorch on
+    the same device (materialised [B,S,S,F] features, three fp32 MLPs, TF32 off) on a small batch, labels compared."""
+    from oracle import dataset_gan_oracle as dg
+    from oracle import stylegan2_oracle as so
+    from synthesis_in_style_b200 import _lib
+    from synthesis_in_style_b200 import dataset_gan as pg
+    from synthesis_in_style_b200.model import Generator
+    assert torch.cuda.is_available(), 'this leg needs a CUDA device'
+    dev = torch.device('cuda:0')
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    batch, ref_batch, iters = args.batch, 2, 5
+    spec, sd = oracle_state()
+    g = Generator(SIZE, STYLE_DIM, N_MLP)
+    g.load_state_dict(sd)
+    g = g.to(dev).eval()
+    torch.manual_seed(1)
+    with torch.no_grad():
+        _, acts = g([torch.randn(batch, STYLE_DIM).to(dev)], return_intermediate_activations=True, noise=[n.to(dev) for n in so.make_noise(spec)])
+    feat = sum(t.shape[1] for t in acts.values())
+    states = [dg.init_classifier_state(feat, 3, seed=50 + i, base_seed=49) for i in range(3)]
+    ens = pg.PixelEnsembleClassifier(3, 0, 0)
+    for st in states:
+        net = pg.PixelClassifier(3, feat)
+        net.load_state_dict(st)
+        ens.add_network(net.eval())
+    for _ in range(2):
+        labels, _, _ = ens.predict_label_images(acts, SIZE)
+    torch.cuda.synchronize()
+    _lib.profile_enable(True)
+    _lib.profile_collect()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        labels, _, _ = ens.predict_label_images(acts, SIZE)
+    e1.record()
+    torch.cuda.synchronize()
+    prof = _lib.profile_collect()
+    _lib.profile_enable(False)
+    ens.check(dev)
+    ms = e0.elapsed_time(e1) / iters
+    models = [dg.ClassifierParams({k: v.to(dev) for k, v in st.items()}) for st in states]
+    sub = {k: v[:ref_batch] for k, v in acts.items()}
+    with torch.no_grad():
+        dg.predict_labels(models, sub, SIZE)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        want, margin, _ = dg.predict_labels(models, sub, SIZE)
+        r1.record()
+        torch.cuda.synchronize()
+    ref_ms = r0.elapsed_time(r1)
+    safe = margin > 1e-3
+    got = labels[:ref_batch].float()
+    flops = 2.0 * batch * 384 * sum(t.shape[1] * t.shape[-1] ** 2 for t in acts.values())
+    print(json.dumps({'leg': 'dataset_gan', 'image_size': SIZE, 'batch': batch, 'features': feat, 'networks': 3,
+                      'ms_per_batch': round(ms, 3), 'images_per_s': round(batch / ms * 1e3, 1),
+                      'ms_by_category': {k: round(v[0] / iters, 3) for k, v in prof.items() if v[1]},
+                      'first_layer_alg_TFLOP/s': round(flops / (prof['conv_tc'][0] / iters * 1e-3) / 1e12, 1),
+                      'reference_algorithm_same_gpu': {'batch': ref_batch, 'ms_per_image': round(ref_ms / ref_batch, 2),
+                                                       'images_per_s': round(ref_batch / ref_ms * 1e3, 1),
+                                                       'note': 'materialised [B,S,S,F] features + three fp32 MLPs in PyTorch (TF32 off)'},
+                      'labels_equal_where_margin_gt_1e-3': bool((got[safe] == want[safe]).all()),
+                      'label_agreement': round(float((got == want).float().mean()), 6)}), file=out, flush=True)
+
+
 def claim_stdout():
     """Native libraries (NCCL's version banner, ...) write to fd 1; the contract is ONE JSON line on stdout.  Keep a
     private handle on the real stdout for that line and point fd 1 at stderr for everything else."""
@@ -253,6 +363,8 @@ def main():
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-steps', type=int, default=3)
+    ap.add_argument('--leg', default='', choices=['', 'contours', 'dataset_gan'],
+                    help='run one of the extra stage benchmarks (rows after the hot path) instead of the headline metric')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 
@@ -261,6 +373,10 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.impl == 'reference':
         run_reference(args, rank, world, out)
+        return
+    if args.leg:
+        if rank == 0:
+            (run_leg_contours if args.leg == 'contours' else run_leg_dataset_gan)(args, out)
         return
 
     import torch.distributed as dist

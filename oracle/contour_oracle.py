@@ -256,3 +256,53 @@ def create_segmentation_image(predicted: Dict[str, Dict[str, numpy.ndarray]], ba
     drop = images_to_drop(classified, image_size)
     images = render(predicted[keys_for_finegrained_segmentation[-1]], classified, batch_size, image_size, class_to_color)
     return images, drop
+
+
+# --------------------------------------------------------------------------- synthetic inputs (tests, bench legs)
+
+MASK_CLASSES = ('background', 'printed_text', 'handwritten_text')
+
+
+def synthetic_document_masks(seed, batch, size, blob_images=()):
+    """Masks that look like the labeller's output on documents: coarse blocky text regions for the two
+    class-determination keys (64^2 maps upsampled x4), stroke-like fine-grained masks at full resolution."""
+    rng = numpy.random.RandomState(seed)
+    coarse = size // 4
+    pred = {k: {n: numpy.zeros((batch, size, size), dtype=bool) for n in MASK_CLASSES} for k in ('8', '9', '12', '13')}
+    for b in range(batch):
+        n_regions = rng.randint(0, 6)
+        for _ in range(n_regions):
+            cls = 'printed_text' if rng.rand() < 0.6 else 'handwritten_text'
+            w, h = rng.randint(6, coarse // 2), rng.randint(2, 10)
+            x, y = rng.randint(0, coarse - w), rng.randint(0, coarse - h)
+            for key in ('8', '9'):
+                if rng.rand() < 0.12:
+                    continue                                             # a region one key misses
+                dx, dy = rng.randint(-2, 3), rng.randint(-1, 2)
+                blk = numpy.zeros((coarse, coarse), dtype=bool)
+                blk[max(0, y + dy):y + dy + h, max(0, x + dx):x + dx + w] = True
+                holes = rng.rand(coarse, coarse) < 0.04
+                blk &= ~holes
+                pred[key][cls][b] |= numpy.kron(blk, numpy.ones((4, 4), dtype=bool))
+            # strokes inside the region (fine-grained keys label all ink as printed_text; a few handwritten pixels)
+            for key in ('12', '13'):
+                for line in range(y * 4 + 2, (y + h) * 4 - 2, 7):
+                    xx = x * 4 + rng.randint(0, 4)
+                    while xx < (x + w) * 4 - 3:
+                        ww = rng.randint(2, 9)
+                        hh = rng.randint(2, 5)
+                        jit = rng.randint(-1, 2) if key == '13' else 0
+                        pred[key]['printed_text'][b, max(0, line + jit):line + jit + hh, xx:min(size, xx + ww)] = True
+                        xx += ww + rng.randint(1, 4)
+        # specks, and occasionally a page-sized blob that triggers the drop rule
+        for key in ('12', '13'):
+            specks = rng.rand(size, size) < 0.0015
+            pred[key]['printed_text'][b] |= specks
+        if rng.rand() < 0.15 or b in blob_images:
+            for key in ('8', '9', '12', '13'):
+                pred[key]['printed_text'][b, 2:size - 2, 2:size - 2] |= rng.rand(size - 4, size - 4) < 0.9
+        for key in pred:
+            any_text = pred[key]['printed_text'][b] | pred[key]['handwritten_text'][b]
+            pred[key]['handwritten_text'][b] &= ~pred[key]['printed_text'][b]
+            pred[key]['background'][b] = ~any_text
+    return pred

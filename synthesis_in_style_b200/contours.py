@@ -374,6 +374,7 @@ def segment_masks(predicted_clusters, batch_size: int, cfg: ContourConfig):
 
 def _segment_one(args):
     masks, cfg = args
+    cv2.setNumThreads(1)            # pool workers: one image per task, OpenCV's own thread pool only oversubscribes
     image, drop = segment_masks(masks, 1, cfg)
     return image[0], bool(drop)
 
