@@ -130,8 +130,14 @@ class LabelledPairGenerator:
 
     def __init__(self, generator: Generator, segmenter: ClusterSegmenter, config: Dict, seed: int = 1,
                  mean_latent: Optional[torch.Tensor] = None, rank: int = 0, world_size: int = 1,
-                 capture_only_labelled: bool = False, fused_labelling: bool = True):
+                 capture_only_labelled: bool = False, fused_labelling: bool = True, in_flight: int = 1):
+        """`in_flight` > 1 keeps that many batches in flight on as many CUDA streams, each with its own generator
+        workspace (a replica of `generator`: same weights, separate native plan).  Batches are independent, so the
+        latency-bound head of one step (mapping network, 4^2..16^2 layers) overlaps the tensor-bound body of the other;
+        the results are the same as with one stream (same RNG draw order), yielded in order."""
         self.generator, self.segmenter = generator, segmenter
+        self.in_flight = max(1, int(in_flight))
+        self._replicas, self._streams = None, None
         self.fused_labelling = fused_labelling
         self.config, self.seed, self.mean_latent = config, seed, mean_latent
         self.rank, self.world_size = rank, world_size
@@ -140,23 +146,68 @@ class LabelledPairGenerator:
         self.capture_layers = sorted({0} | {int(k) for k in segmenter.catalog}) if capture_only_labelled else None
         self.stats = {'pairs': 0, 'batches': 0}
 
+    def _lanes(self, device):
+        """(generator replica, stream) per in-flight lane; lane 0 is the user's generator on the current stream when
+        in_flight == 1."""
+        if self.in_flight == 1:
+            return [(self.generator, None)]
+        if self._replicas is None:
+            import copy
+            self._replicas = [self.generator] + [copy.deepcopy(self.generator).eval() for _ in range(self.in_flight - 1)]
+            self._streams = [torch.cuda.Stream(device=device) for _ in range(self.in_flight)]
+            # device-side caches (centroids, class-bit tables) are filled on the current stream before the lanes fork
+            self.segmenter.make_label_jobs(self.generator, self.config['batch_size'])
+        current = torch.cuda.current_stream(device)
+        for st in self._streams:
+            st.wait_stream(current)
+        return list(zip(self._replicas, self._streams))
+
+    @staticmethod
+    def _hand_over(tensors, event, device):
+        """Make tensors produced on a lane stream safe to use on the caller's current stream."""
+        current = torch.cuda.current_stream(device)
+        current.wait_event(event)
+        for t in tensors:
+            if t is not None and t.is_cuda:
+                t.record_stream(current)
+
     def __iter__(self) -> Iterator[LabelledBatch]:
+        import collections
+        import contextlib
         device = self.generator.input.input.device
-        for idx, latents in sharded_latent_stream(self.generator, self.config, self.seed, self.rank, self.world_size):
-            if self.fused_labelling:
-                # labelling runs inside the generator's native call (one pass over each labelled activation)
-                jobs = self.segmenter.make_label_jobs(self.generator, latents.latent.shape[0])
-                acts, image = generate_images(latents, self.generator, device=device, mean_latent=self.mean_latent,
-                                              capture_layers=self.capture_layers, label_jobs=jobs)
-                masks = self.segmenter._as_predicted(self.segmenter.jobs_to_stacked(jobs))
-            else:
-                acts, image = generate_images(latents, self.generator, device=device, mean_latent=self.mean_latent,
-                                              capture_layers=self.capture_layers)
-                masks = self.segmenter.prepare_image_segmentation(acts)
-            masks = self.segmenter.merge_sub_images(masks)
+        lanes = self._lanes(device)
+        pending = collections.deque()
+        stream = sharded_latent_stream(self.generator, self.config, self.seed, self.rank, self.world_size)
+        n = 0
+        while True:
+            g, st = lanes[n % len(lanes)]
+            with (torch.cuda.stream(st) if st is not None else contextlib.nullcontext()):
+                idx, latents = next(stream)          # the noise is drawn on this lane's stream, in the reference's order
+                if self.fused_labelling:
+                    # labelling runs inside the generator's native call (one pass over each labelled activation)
+                    jobs = self.segmenter.make_label_jobs(g, latents.latent.shape[0])
+                    acts, image = generate_images(latents, g, device=device, mean_latent=self.mean_latent,
+                                                  capture_layers=self.capture_layers, label_jobs=jobs)
+                    masks = self.segmenter._as_predicted(self.segmenter.jobs_to_stacked(jobs))
+                else:
+                    acts, image = generate_images(latents, g, device=device, mean_latent=self.mean_latent,
+                                                  capture_layers=self.capture_layers)
+                    masks = self.segmenter.prepare_image_segmentation(acts)
+                masks = self.segmenter.merge_sub_images(masks)
+                done = None
+                if st is not None:
+                    done = torch.cuda.Event()
+                    done.record(st)
             self.stats['pairs'] += image.shape[0]
             self.stats['batches'] += 1
-            yield LabelledBatch(idx, image, masks, acts)
+            pending.append((LabelledBatch(idx, image, masks, acts), done))
+            n += 1
+            if len(pending) >= len(lanes):
+                batch, done = pending.popleft()
+                if done is not None:
+                    self._hand_over([batch.image] + list(batch.activations.values())
+                                    + [m for per_class in batch.masks.values() for m in per_class.values()], done, device)
+                yield batch
 
     def iter_host(self, depth: int = 2, image_u8: bool = False) -> Iterator['HostBatch']:
         """The same loop with HOST buffers on both sides, as `build_dataset` needs them (its next steps are CPU code):
@@ -165,8 +216,11 @@ class LabelledPairGenerator:
         batch's kernels.  A yielded HostBatch stays valid until the next one is requested."""
         if self.segmenter.keys_to_merge:
             raise NotImplementedError('iter_host does not merge layers; use __iter__ for keys_to_merge configs')
+        import contextlib
         device = self.generator.input.input.device
         g, seg = self.generator, self.segmenter
+        lanes = self._lanes(device)
+        depth = max(depth, len(lanes))
         B, S = self.config['batch_size'], g.size
         copy_stream = torch.cuda.Stream(device=device)
         slots = [{'z': torch.empty(B, self.config['latent_size']).pin_memory(),
@@ -180,22 +234,26 @@ class LabelledPairGenerator:
             return HostBatch(slot['index'], slot['image'], dict(slot['masks']), slot['names'])
 
         n = 0
-        for idx, latents in sharded_latent_stream(g, self.config, self.seed, self.rank, self.world_size):
+        latent_stream = sharded_latent_stream(g, self.config, self.seed, self.rank, self.world_size)
+        while True:
             slot = slots[n % (depth + 1)]
-            slot['z'].copy_(latents.latent)
-            lat = Latents(slot['z'].to(device, non_blocking=True), latents.noise)
-            if self.fused_labelling:
-                jobs = seg.make_label_jobs(g, B)
-                acts, image = generate_images(lat, g, device=device, mean_latent=self.mean_latent, capture_layers=self.capture_layers,
-                                              label_jobs=jobs)
-                stacked = seg.jobs_to_stacked(jobs)
-            else:
-                acts, image = generate_images(lat, g, device=device, mean_latent=self.mean_latent, capture_layers=self.capture_layers)
-                stacked = seg.label_layers_stacked(acts)
-            if image_u8:
-                image = make_image(image)              # uint8 NHWC on the device: a quarter of the fp32 copy
-            ready = torch.cuda.Event()
-            ready.record(torch.cuda.current_stream(device))
+            g, st = lanes[n % len(lanes)]
+            with (torch.cuda.stream(st) if st is not None else contextlib.nullcontext()):
+                idx, latents = next(latent_stream)
+                slot['z'].copy_(latents.latent)
+                lat = Latents(slot['z'].to(device, non_blocking=True), latents.noise)
+                if self.fused_labelling:
+                    jobs = seg.make_label_jobs(g, B)
+                    acts, image = generate_images(lat, g, device=device, mean_latent=self.mean_latent, capture_layers=self.capture_layers,
+                                                  label_jobs=jobs)
+                    stacked = seg.jobs_to_stacked(jobs)
+                else:
+                    acts, image = generate_images(lat, g, device=device, mean_latent=self.mean_latent, capture_layers=self.capture_layers)
+                    stacked = seg.label_layers_stacked(acts)
+                if image_u8:
+                    image = make_image(image)              # uint8 NHWC on the device: a quarter of the fp32 copy
+                ready = torch.cuda.Event()
+                ready.record(torch.cuda.current_stream(device))
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(ready)
                 slot['image'].copy_(image, non_blocking=True)

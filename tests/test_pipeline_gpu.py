@@ -194,3 +194,35 @@ def test_build_dataset_writes_the_reference_layout(cuda_device, tmp_path):
     for i, f in enumerate(files):
         assert f.relative_to(tmp_path).as_posix() == f'0/0/{i:04d}.png'
         assert numpy.array_equal(numpy.array(Image.open(f)), expect[i])
+
+
+def test_two_batches_in_flight_equal_single_stream(cuda_device):
+    """in_flight=2 (two CUDA streams, two generator workspaces) yields the same batches, in order, as one stream."""
+    layers = ['4', '5', '6', '7']
+    spec, sd, g, seg, cents = make_setup(32, layers, cuda_device)
+    cfg = {'batch_size': 3, 'latent_size': 512}
+    single = [b for _, b in zip(range(5), dc.LabelledPairGenerator(g, seg, cfg, seed=1))]
+    double = [b for _, b in zip(range(5), dc.LabelledPairGenerator(g, seg, cfg, seed=1, in_flight=2))]
+    torch.cuda.synchronize()
+    for a, b in zip(single, double):
+        assert a.batch_index == b.batch_index
+        assert torch.equal(a.image, b.image)
+        for k in a.activations:
+            assert torch.equal(a.activations[k], b.activations[k])
+        for layer in layers:
+            for cn in NAMES:
+                assert torch.equal(a.masks[layer][cn], b.masks[layer][cn])
+    # the two pipelines share `g`: run them one after the other, not interleaved
+    host1 = dc.LabelledPairGenerator(g, seg, cfg, seed=1).iter_host(depth=2)
+    want = []
+    for _ in range(4):
+        h = next(host1)
+        want.append((h.batch_index, h.image.clone(), {k: v.clone() for k, v in h.masks.items()}))
+    del host1
+    torch.cuda.synchronize()
+    host2 = dc.LabelledPairGenerator(g, seg, cfg, seed=1, in_flight=2).iter_host(depth=2)
+    for idx, image, masks in want:
+        h = next(host2)
+        assert h.batch_index == idx and torch.equal(h.image, image)
+        for layer in layers:
+            assert torch.equal(h.masks[layer], masks[layer])
