@@ -363,7 +363,8 @@ def main():
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-steps', type=int, default=3)
-    ap.add_argument('--in-flight', type=int, default=2, help='batches in flight on separate CUDA streams / generator workspaces')
+    ap.add_argument('--in-flight', type=int, default=2, choices=[1, 2],
+                    help='batches in flight on separate CUDA streams / generator workspaces (3 measured slower: do not)')
     ap.add_argument('--leg', default='', choices=['', 'contours', 'dataset_gan'],
                     help='run one of the extra stage benchmarks (rows after the hot path) instead of the headline metric')
     args = ap.parse_args()
