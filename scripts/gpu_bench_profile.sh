@@ -13,7 +13,7 @@ python bench.py --steps 20 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.
 tail -c 1500 $OUT/bench_$TAG.json
 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/bench_ref_$TAG.json 2>> $OUT/bench_$TAG.err; echo "ref rc=$?"
 fi
-CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --profile-steps 1"
+CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --profile-steps 1 --in-flight 1"   # one lane: launch order = layer order
 # launches of my library per resident step: 12 mapping + 2 input + 13 conv + 6 blur + 6 torgb + 4 label = 43
 $CMD > $OUT/plain_$TAG.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_list_$TAG.log 2>&1

@@ -149,6 +149,8 @@ struct TcKernelArgs {
     float* out_f32; int out_h, out_w;
     const float* s_next; bf16* next_hi; bf16* next_lo;
     unsigned int* error;
+    int stages;                 // pipeline depth actually used (<= the configuration's maximum; 0 = maximum): a shallower
+                                // ring leaves shared memory for a co-resident block of another stream's memory-bound kernel
 };
 
 constexpr int BM = 128, UMMA_K = 16;
@@ -399,7 +401,7 @@ modconv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ T
     static_assert(TH * TW * TB == BM, "tile box must hold 128 pixels");
     static_assert(CG == 1 || CG == 2, "cta_group");
     using Cfg = TcCfg<BN, BK, CG>;
-    constexpr int STAGES = Cfg::STAGES;
+    const int STAGES = a.stages > 0 && a.stages < Cfg::STAGES ? a.stages : Cfg::STAGES;
     constexpr int A_TILE_BYTES = Cfg::A_TILE_BYTES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -560,7 +562,8 @@ template <int BN, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 modconv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcKernelArgs a) {
     using Cfg = TcHaloCfg<BN, CG>;
-    constexpr int NA = Cfg::NA, NB = Cfg::NB, BK = Cfg::BK;
+    constexpr int NA = Cfg::NA, BK = Cfg::BK;
+    const int NB = a.stages > 0 && a.stages < Cfg::NB ? a.stages : Cfg::NB;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_b = smem + NA * Cfg::A_STAGE;
@@ -1113,9 +1116,11 @@ static int launch_tc(const TcMaps& maps, const TcKernelArgs& a, cudaStream_t str
     }
     // persistent: one CTA (CG = 1) or one CTA pair (CG = 2) per SM (pair); a.total_tiles counts tiles resp. pair tiles
     int grid = a.total_tiles * CG < kNumSMs ? a.total_tiles * CG : kNumSMs;
+    const int st_used = a.stages > 0 && a.stages < Cfg::STAGES ? a.stages : Cfg::STAGES;
+    const size_t SMEM_USED = (size_t)st_used * Cfg::STAGE_BYTES + 1024 + 256;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc_threads()); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc_threads()); cfg.dynamicSmemBytes = SMEM_USED; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -1135,9 +1140,11 @@ static int launch_tc_halo(const TcMaps& maps, const TcKernelArgs& a, cudaStream_
         configured = true;
     }
     int grid = a.total_tiles * CG < kNumSMs ? a.total_tiles * CG : kNumSMs;
+    const int nb_used = a.stages > 0 && a.stages < Cfg::NB ? a.stages : Cfg::NB;
+    const size_t SMEM_USED = (size_t)Cfg::NA * Cfg::A_STAGE + (size_t)nb_used * Cfg::B_STAGE + 1024 + 512;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc_threads()); cfg.dynamicSmemBytes = Cfg::SMEM_BYTES; cfg.stream = stream;
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(tc_threads()); cfg.dynamicSmemBytes = SMEM_USED; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -1235,6 +1242,8 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
     a.demod = call.demod; a.noise = call.noise; a.noise_bstride = call.noise_bstride; a.noise_w = call.noise_w; a.bias = call.bias;
     a.error = ws.d_error;
     a.act = call.act ? 1 : 0;
+    static int stages_env = env_int("SIS_TC_STAGES", 0);      // experiment: cap the ring depth (0 = maximum)
+    a.stages = stages_env;
     a.im2col = im2col ? 1 : 0;
     int tiles = 0;   // tiles (CG = 1) or pair tiles (CG = 2)
     auto units = [&](TcSubProblem& s) {
