@@ -106,18 +106,20 @@ int launch_blur_noise_act(const BlurActArgs& a, cudaStream_t stream) {
 // shared memory in fixed order.  x is read exactly once with 128-bit loads.
 constexpr int RGB_SLICES = 8;
 
-__global__ void __launch_bounds__(32 * RGB_SLICES) torgb_kernel(ToRgbArgs a) {
+// blockDim = (32, slices): 8 channel slices per block for large maps, 32 for the 4^2..32^2 maps whose few blocks would
+// otherwise walk 64 channels per lane serially (latency-bound: 25 us per launch).
+__global__ void __launch_bounds__(1024) torgb_kernel(ToRgbArgs a) {
     extern __shared__ float smem[];
     float* swr = smem;                                  // [3][C]  scale*W
     float* red = smem + 3 * a.C;                        // [SLICES][3][4][32]
-    const int lane = threadIdx.x, slice = threadIdx.y;
+    const int lane = threadIdx.x, slice = threadIdx.y, nsl = blockDim.y;
     const int tid = slice * 32 + lane;
-    for (int i = tid; i < 3 * a.C; i += 32 * RGB_SLICES) swr[i] = a.w[i];
+    for (int i = tid; i < 3 * a.C; i += 32 * nsl) swr[i] = a.w[i];
     __syncthreads();
     const int64_t hw = (int64_t)a.H * a.W;
     const int64_t quads_per_sample = hw / 4;
     const int64_t total_quads = quads_per_sample * a.batch;
-    const int cps = (a.C + RGB_SLICES - 1) / RGB_SLICES;
+    const int cps = (a.C + nsl - 1) / nsl;
     const int c_begin = slice * cps, c_end = min(a.C, c_begin + cps);
 
     for (int64_t q0 = (int64_t)blockIdx.x * 32; q0 < total_quads; q0 += (int64_t)gridDim.x * 32) {
@@ -148,13 +150,12 @@ __global__ void __launch_bounds__(32 * RGB_SLICES) torgb_kernel(ToRgbArgs a) {
             for (int p = 0; p < 4; ++p) red[((slice * 3 + j) * 4 + p) * 32 + lane] = acc[j][p];
         __syncthreads();
         // 96 (j, p, lane) outputs per... : 3*4*32 = 384 results, 256 threads -> strided
-        for (int r = tid; r < 3 * 4 * 32; r += 32 * RGB_SLICES) {
+        for (int r = tid; r < 3 * 4 * 32; r += 32 * nsl) {
             const int ln = r % 32, p = (r / 32) % 4, j = r / 128;
             const int64_t qq = q0 + ln;
             if (qq >= total_quads) continue;
             float v = 0.0f;
-#pragma unroll
-            for (int s = 0; s < RGB_SLICES; ++s) v += red[((s * 3 + j) * 4 + p) * 32 + ln];
+            for (int s = 0; s < nsl; ++s) v += red[((s * 3 + j) * 4 + p) * 32 + ln];
             const int bb = (int)(qq / quads_per_sample);
             const int64_t px = (qq - (int64_t)bb * quads_per_sample) * 4 + p;
             const int y = (int)(px / a.W), x = (int)(px % a.W);
@@ -239,8 +240,16 @@ int launch_torgb(const ToRgbArgs& a, cudaStream_t stream) {
     int64_t blocks = ceil_div64(quads, 32);
     int64_t cap = (int64_t)kNumSMs * 8;
     int grid = (int)(blocks < cap ? blocks : cap);
-    size_t smem = (size_t)(3 * a.C + RGB_SLICES * 3 * 4 * 32) * sizeof(float);
-    torgb_kernel<<<grid, dim3(32, RGB_SLICES), smem, stream>>>(a);
+    const int slices = blocks < kNumSMs ? 32 : RGB_SLICES;
+    size_t smem = (size_t)(3 * a.C + slices * 3 * 4 * 32) * sizeof(float);
+    if (smem > 48 * 1024) {
+        static bool configured = false;
+        if (!configured) {
+            SIS_CHECK_CUDA(cudaFuncSetAttribute(torgb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            configured = true;
+        }
+    }
+    torgb_kernel<<<grid, dim3(32, slices), smem, stream>>>(a);
     SIS_CHECK_LAUNCH();
     return SIS_OK;
 }
