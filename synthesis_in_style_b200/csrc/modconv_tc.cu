@@ -684,6 +684,204 @@ modconv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const __grid_constan
     }
 }
 
+// ------------------------------------------------------------------------------- transposed halo variant (Cout = 128)
+// An M=128 x N=128 MMA fetches (128 + 128) rows x 32 B of operands for 64 clk of math: exactly the 128 B/clk the SM's
+// shared memory delivers (scripts/exp_mma_rate.cu), so the Cout = 128 layers run at ~2/3 of the tensor rate.  This
+// variant computes the TRANSPOSED product: the weights are the M = 128 operand, 256 pixels (a 32 x 8 tile) the N operand,
+// D[channel][pixel] -> (128 + 256) x 32 B per 128 clk = 96 B/clk, the same slack the Cout >= 256 layers have.
+// The pixels come from one 34 x 10 halo per 32-channel K chunk (64 B rows, SWIZZLE_64B, shifted descriptors with a
+// 640 B group stride: exp_halo_desc.cu covers this case), the weights stream per tap.  TMEM lanes are output channels, so
+// the epilogue thread owns ONE channel and 32 consecutive tile pixels per chunk: demod / bias are per-thread scalars, the
+// noise row is shared by the warp, and the fp32 NCHW capture is written as 32 B row segments.  Used for plain layers with
+// Cout = 128, H a multiple of 32 and no following conv (no bf16 planes to emit): 128 -> 128 at 256^2 in the 256^2 model.
+constexpr int HT_TH = 32, HT_TW = 8, HT_W = HT_TW + 2, HT_H = HT_TH + 2, HT_BK = 32, HT_N = HT_TH * HT_TW;
+struct TcHaloTCfg {
+    static constexpr int ROW = HT_BK * 2;                                        // 64 B operand rows
+    static constexpr int A_BYTES = HT_H * HT_W * ROW;                            // 21760 bytes per halo plane
+    static constexpr int A_PAD = (A_BYTES + 1023) / 1024 * 1024;                 // 22528
+    static constexpr int A_STAGE = 2 * A_PAD;
+    static constexpr int NA = 2;
+    static constexpr int W_TILE_BYTES = 128 * ROW;                               // 8192 per plane
+    static constexpr int W_STAGE = 2 * W_TILE_BYTES;
+    static constexpr int NW = 8;
+    static constexpr int SMEM_BYTES = NA * A_STAGE + NW * W_STAGE + 1024 + 512;
+    static constexpr int TMEM_COLS = 512;
+};
+
+__device__ __forceinline__ uint64_t make_halo_t_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)((HT_W * TcHaloTCfg::ROW) >> 4) << 32;   // 8-pixel row groups are one halo row (640 B) apart
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                                 // SWIZZLE_64B
+    return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+modconv_tc_halo_t_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcKernelArgs a) {
+    using Cfg = TcHaloTCfg;
+    constexpr int NA = Cfg::NA, NW = Cfg::NW, BK = HT_BK;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_w = smem + NA * Cfg::A_STAGE;
+    uint64_t* bars = (uint64_t*)(smem_w + NW * Cfg::W_STAGE);
+    uint64_t* full_bar = bars;                       // [NW] weights
+    uint64_t* empty_bar = bars + NW;                 // [NW]
+    uint64_t* afull_bar = bars + 2 * NW;             // [NA] halo tiles
+    uint64_t* aempty_bar = bars + 2 * NW + NA;       // [NA]
+    uint64_t* tfull_bar = bars + 2 * NW + 2 * NA;    // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;            // [2]
+    uint32_t* tmem_ptr_smem = (uint32_t*)(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_epi_warps = (int)(blockDim.x / 32) - 2;
+    const TcSubProblem& s = a.sub[0];
+    const int tiles_x = s.ow / HT_TW, tiles_y = s.oh / HT_TH;
+    const int m_tiles = a.batch * tiles_y * tiles_x;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&maps.a[0][0]); tma_prefetch_desc(&maps.a[0][1]);
+        tma_prefetch_desc(&maps.w[0]); tma_prefetch_desc(&maps.w[1]);
+        for (int i = 0; i < NW; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < NA; ++i) { mbar_init(&afull_bar[i], 1); mbar_init(&aempty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], n_epi_warps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (lane == 0) {
+            int as = 0; uint32_t aphase = 0;
+            int ws = 0; uint32_t wphase = 0;
+            for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+                const int m = t % m_tiles, n0 = (t / m_tiles) * 128;
+                const int x0 = (m % tiles_x) * HT_TW, y0 = ((m / tiles_x) % tiles_y) * HT_TH, b = m / (tiles_x * tiles_y);
+                for (int kc = 0; kc < a.kchunks; ++kc) {
+                    mbar_wait(&aempty_bar[as], aphase ^ 1, a.error, 0x500 + as);
+                    uint8_t* sa = smem + as * Cfg::A_STAGE;
+                    mbar_expect_tx(&afull_bar[as], 2 * Cfg::A_BYTES);
+                    tma_load_4d(&maps.a[0][0], &afull_bar[as], sa, kc * BK, x0 - 1, y0 - 1, b);
+                    tma_load_4d(&maps.a[0][1], &afull_bar[as], sa + Cfg::A_PAD, kc * BK, x0 - 1, y0 - 1, b);
+                    if (++as == NA) { as = 0; aphase ^= 1; }
+                    for (int tap = 0; tap < s.ntaps; ++tap) {
+                        mbar_wait(&empty_bar[ws], wphase ^ 1, a.error, 0x100 + ws);
+                        uint8_t* sw = smem_w + ws * Cfg::W_STAGE;
+                        mbar_expect_tx(&full_bar[ws], Cfg::W_STAGE);
+                        tma_load_3d(&maps.w[0], &full_bar[ws], sw, kc * BK, n0, s.widx[tap]);
+                        tma_load_3d(&maps.w[1], &full_bar[ws], sw + Cfg::W_TILE_BYTES, kc * BK, n0, s.widx[tap]);
+                        if (++ws == NW) { ws = 0; wphase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        if (lane == 0) {
+            // D[128 channels][256 pixels] = W[128][K] . X[256][K]^T : A = weights, B = pixels, both K-major
+            constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HT_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            int as = 0; uint32_t aphase = 0;
+            int ws = 0; uint32_t wphase = 0;
+            int acc = 0; uint32_t acc_phase = 0;
+            for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1, a.error, 0x200 + acc);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * HT_N);
+                for (int kc = 0; kc < a.kchunks; ++kc) {
+                    mbar_wait(&afull_bar[as], aphase, a.error, 0x600 + as);
+                    const uint32_t sa = smem_u32(smem + as * Cfg::A_STAGE);
+                    for (int tap = 0; tap < s.ntaps; ++tap) {
+                        mbar_wait(&full_bar[ws], wphase, a.error, 0x300 + ws);
+                        tc_fence_after();
+                        const uint32_t xoff = (uint32_t)(((s.dy[tap] + 1) * HT_W + (s.dx[tap] + 1)) * Cfg::ROW);
+                        const uint64_t d_xh = make_halo_t_desc(sa + xoff), d_xl = make_halo_t_desc(sa + Cfg::A_PAD + xoff);
+                        const uint32_t sw = smem_u32(smem_w + ws * Cfg::W_STAGE);
+                        const uint64_t d_wh = make_smem_desc<Cfg::ROW>(sw), d_wl = make_smem_desc<Cfg::ROW>(sw + Cfg::W_TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+                            umma_bf16(d_tmem, d_wh + koff, d_xh + koff, idesc, (kc | tap | k) ? 1u : 0u);
+                            umma_bf16(d_tmem, d_wl + koff, d_xh + koff, idesc, 1u);
+                            umma_bf16(d_tmem, d_wh + koff, d_xl + koff, idesc, 1u);
+                        }
+                        umma_commit(&empty_bar[ws]);
+                        if (++ws == NW) { ws = 0; wphase ^= 1; }
+                    }
+                    umma_commit(&aempty_bar[as]);
+                    if (++as == NA) { as = 0; aphase ^= 1; }
+                }
+                umma_commit(&tfull_bar[acc]);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ============================== epilogue: one output channel per thread ==============================
+        const int quarter = warp & 3;
+        const int chalf = (warp - 2) >> 2;
+        const int cstep = n_epi_warps * 8;                  // 4 epilogue warps: 32 columns, 8: 64
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+            const int m = t % m_tiles, n0 = (t / m_tiles) * 128;
+            const int x0 = (m % tiles_x) * HT_TW, y0 = ((m / tiles_x) % tiles_y) * HT_TH, b = m / (tiles_x * tiles_y);
+            const int ch = n0 + quarter * 32 + lane;
+            const float d = __ldg(a.demod + (int64_t)b * a.cout + ch);
+            const float bias = a.bias ? __ldg(a.bias + ch) : 0.0f;
+            float* plane = a.out_f32 + ((int64_t)b * a.cout + ch) * ((int64_t)a.out_h * a.out_w);
+            const float* nzp = a.noise ? a.noise + (int64_t)b * a.noise_bstride : nullptr;
+            mbar_wait(&tfull_bar[acc], acc_phase, a.error, 0x400 + acc);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * HT_N);
+#pragma unroll 1
+            for (int c0 = chalf * 32; c0 < HT_N; c0 += cstep) {
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + (uint32_t)c0, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {            // 32 columns = 4 tile rows of 8 pixels
+                    const int y = y0 + c0 / HT_TW + rr;
+                    float nz[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (nzp) {
+                        const float4 n0v = __ldg(reinterpret_cast<const float4*>(nzp + (int64_t)y * a.out_w + x0));
+                        const float4 n1v = __ldg(reinterpret_cast<const float4*>(nzp + (int64_t)y * a.out_w + x0) + 1);
+                        nz[0] = n0v.x; nz[1] = n0v.y; nz[2] = n0v.z; nz[3] = n0v.w; nz[4] = n1v.x; nz[5] = n1v.y; nz[6] = n1v.z; nz[7] = n1v.w;
+                    }
+                    float v[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float x = __fmul_rn(__uint_as_float(r[rr * 8 + j]), d);
+                        x = __fadd_rn(x, __fmul_rn(a.noise_w, nz[j]));
+                        if (a.bias) x = __fadd_rn(x, bias);
+                        if (a.act) x = lrelu_scale(x, 0.2f, 1.41421356237309504880f);
+                        v[j] = x;
+                    }
+                    float4* dst = reinterpret_cast<float4*>(plane + (int64_t)y * a.out_w + x0);
+                    dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+                    dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    }
+}
+
 // ------------------------------------------------------------------------------- blur + activation + split
 // Second half of the up-sampling StyledConv: Blur(4x4, pad (1,1)) + noise + bias + lrelu*sqrt2 over the NHWC fp32
 // scratch, writing the fp32 NCHW capture and the next conv's pre-scaled bf16 hi/lo NHWC planes in one pass.
@@ -1154,6 +1352,19 @@ static int launch_tc_halo(const TcMaps& maps, const TcKernelArgs& a, cudaStream_
     return SIS_OK;
 }
 
+static int launch_tc_halo_t(const TcMaps& maps, const TcKernelArgs& a, cudaStream_t stream) {
+    using Cfg = TcHaloTCfg;
+    static bool configured = false;
+    if (!configured) {
+        SIS_CHECK_CUDA(cudaFuncSetAttribute(modconv_tc_halo_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
+    modconv_tc_halo_t_kernel<<<grid, tc_threads(), Cfg::SMEM_BYTES, stream>>>(maps, a);
+    SIS_CHECK_LAUNCH();
+    return SIS_OK;
+}
+
 template <int CG>
 static int launch_tc_halo_any(int BN, const TcMaps& maps, const TcKernelArgs& a, cudaStream_t stream) {
     if (BN == 256) return launch_tc_halo<256, CG>(maps, a, stream);
@@ -1188,6 +1399,37 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
         bk_env = env_int("SIS_TC_BK", 64) == 32 ? 32 : 64; cg_env = env_int("SIS_TC_CG", 2) == 1 ? 1 : 2;
         im2col_env = env_int("SIS_TC_IM2COL", 1) != 0;
         halo_env = env_int("SIS_TC_HALO", 1) != 0;
+    }
+    // transposed halo kernel: Cout = 128 plain layers that feed no further conv (SIS_TC_TRANSPOSED=0 disables)
+    static int transposed_env = env_int("SIS_TC_TRANSPOSED", 1);
+    if (transposed_env && halo_env && !call.up && call.cout == 128 && call.cin % HT_BK == 0 && call.res_in % HT_TH == 0 && !call.s_next) {
+        SIS_REQUIRE(w.hi && w.cin == call.cin && w.cout == call.cout, "tc_modconv: weights not packed for this layer");
+        TcKernelArgs a;
+        memset(&a, 0, sizeof(a));
+        const int H = call.res_in;
+        a.batch = call.batch; a.cin = call.cin; a.cout = call.cout; a.kchunks = call.cin / HT_BK;
+        a.b_tiles = call.batch; a.n_tiles = call.cout / 128;
+        a.demod = call.demod; a.noise = call.noise; a.noise_bstride = call.noise_bstride; a.noise_w = call.noise_w; a.bias = call.bias;
+        a.error = ws.d_error; a.act = call.act ? 1 : 0; a.mode = 0; a.nsub = 1;
+        TcSubProblem& s = a.sub[0];
+        s.ntaps = 9;
+        for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx) { int t = ky * 3 + kx; s.dy[t] = (signed char)(ky - 1); s.dx[t] = (signed char)(kx - 1); s.widx[t] = (signed char)t; }
+        s.oh = H; s.ow = H; s.ostride = 1;
+        a.total_tiles = call.batch * (H / HT_TH) * (H / HT_TW) * a.n_tiles;
+        a.out_f32 = call.out_f32; a.out_h = H; a.out_w = H;
+        TcMaps maps;
+        memset(&maps, 0, sizeof(maps));
+        const uint64_t adims[4] = {(uint64_t)call.cin, (uint64_t)H, (uint64_t)H, (uint64_t)call.batch};
+        const uint32_t abox[4] = {(uint32_t)HT_BK, (uint32_t)HT_W, (uint32_t)HT_H, 1};
+        SIS_PROPAGATE(make_map(&maps.a[0][0], ws.a_hi[call.in_slot], 4, adims, abox, HT_BK * 2));
+        SIS_PROPAGATE(make_map(&maps.a[0][1], ws.a_lo[call.in_slot], 4, adims, abox, HT_BK * 2));
+        const uint64_t wdims[3] = {(uint64_t)call.cin, (uint64_t)call.cout, 9};
+        const uint32_t wbox[3] = {(uint32_t)HT_BK, 128, 1};
+        SIS_PROPAGATE(make_map(&maps.w[0], w.hi, 3, wdims, wbox, HT_BK * 2));
+        SIS_PROPAGATE(make_map(&maps.w[1], w.lo, 3, wdims, wbox, HT_BK * 2));
+        ProfScope prof(PROF_CONV_TC, stream);
+        return launch_tc_halo_t(maps, a, stream);
     }
     // halo reuse: plain 3x3 layers whose image holds whole 16 x 8 tiles and whose K chunks are 64 wide
     const bool halo = halo_env && !call.up && call.res_in >= HALO_TH && call.res_in % HALO_TH == 0 && call.cin % 64 == 0;
