@@ -4,7 +4,7 @@ off) over C in {64..512} and res in {8..512}, timed per category with the librar
 GEMM kernel time is separated from the operand pre-scale / blur passes around it.
 Prints one JSON line per case: algorithmic TFLOP/s (2*MACs, reference's transposed-conv count for `up`) of the GEMM
 launch, its fraction of the measured bf16 peak (x3 MMA passes stated), and the whole-op time.
-Usage: scripts/conv_sweep.py [--only CIN,COUT,RES,UP ...]
+Usage: scripts/conv_sweep.py [--only CIN,COUT,RES,UP[,BATCH] ...]
 """
 import json
 import os
@@ -46,7 +46,7 @@ def run_case(dev, cin, cout, res, up, demod, batch, iters=8):
         prof = _lib.profile_collect()
         _lib.profile_enable(False)
     ms_op = e0.elapsed_time(e1) / iters
-    ms_gemm = prof['conv_tc'][0] / max(1, prof['conv_tc'][1])
+    ms_gemm = prof['conv_tc'][0] / iters          # all GEMM launches of one call (the Cout = 128 up-conv issues two)
     flops = 2.0 * batch * res * res * 9 * cin * cout
     tf = flops / (ms_gemm * 1e-3) / 1e12
     return {'op': 'modulated_conv2d', 'cin': cin, 'cout': cout, 'res_in': res, 'up': up, 'demod': demod, 'B': batch,
@@ -60,8 +60,9 @@ def main():
     cases = []
     if '--only' in sys.argv:
         for spec in sys.argv[sys.argv.index('--only') + 1:]:
-            cin, cout, res, up = (int(v) for v in spec.split(','))
-            cases.append((cin, cout, res, bool(up), True))
+            f = [int(v) for v in spec.split(',')]
+            cin, cout, res, up = f[:4]
+            cases.append((cin, cout, res, bool(up), True) + ((f[4],) if len(f) > 4 else ()))
     else:
         for c in (64, 128, 256, 512):
             for res in (8, 32, 64, 128, 256, 512):
@@ -74,10 +75,11 @@ def main():
         cases.append((512, 512, 64, False, False))
         cases.append((512, 256, 64, True, True))
         cases.append((256, 128, 128, True, True))
-    for cin, cout, res, up, demod in cases:
+    for case in cases:
+        cin, cout, res, up, demod = case[:5]
         out_res = res * 2 if up else res
         per = (cin * res * res + cout * out_res * out_res * (3 if up else 1)) * 4 + cout * out_res * out_res * 4
-        batch = int(max(1, min(64, (1 << 30) // per)))
+        batch = case[5] if len(case) > 5 else int(max(1, min(64, (1 << 30) // per)))
         print(json.dumps(run_case(dev, cin, cout, res, up, demod, batch)), flush=True)
 
 

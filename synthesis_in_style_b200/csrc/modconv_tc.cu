@@ -121,7 +121,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // ------------------------------------------------------------------------------------------------ kernel
 struct TcSubProblem {
     int ntaps;
-    signed char dy[9], dx[9], widx[9];
+    short dy[9], dx[9];         // tap offsets (may carry a sub-problem origin: border strips of the transposed conv)
+    signed char widx[9];
     int oh, ow;                 // extent of this sub-problem's output grid
     int ostride, ooff_y, ooff_x;
     int tiles_y, tiles_x;       // tiled A mode: spatial tiles of the box
@@ -736,9 +737,11 @@ modconv_tc_halo_t_kernel(const __grid_constant__ TcMaps maps, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_epi_warps = (int)(blockDim.x / 32) - 2;
-    const TcSubProblem& s = a.sub[0];
-    const int tiles_x = s.ow / HT_TW, tiles_y = s.oh / HT_TH;
+    // tiles: n-tile slowest, then spatial tile, then (transposed conv) the 4 output phases, rotated by the spatial index so
+    // that a CTA's static stride (148 = 4 * 37) does not lock onto one phase (they have 4 / 2 / 2 / 1 taps)
+    const int tiles_x = a.sub[0].ow / HT_TW, tiles_y = a.sub[0].oh / HT_TH;
     const int m_tiles = a.batch * tiles_y * tiles_x;
+    const int per = a.nsub;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&maps.a[0][0]); tma_prefetch_desc(&maps.a[0][1]);
@@ -763,7 +766,9 @@ modconv_tc_halo_t_kernel(const __grid_constant__ TcMaps maps, const __grid_const
             int as = 0; uint32_t aphase = 0;
             int ws = 0; uint32_t wphase = 0;
             for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-                const int m = t % m_tiles, n0 = (t / m_tiles) * 128;
+                const int rt = t % (m_tiles * per), n0 = (t / (m_tiles * per)) * 128;
+                const int m = rt / per;
+                const TcSubProblem& s = a.sub[per == 1 ? 0 : ((rt % per) + m) & 3];
                 const int x0 = (m % tiles_x) * HT_TW, y0 = ((m / tiles_x) % tiles_y) * HT_TH, b = m / (tiles_x * tiles_y);
                 for (int kc = 0; kc < a.kchunks; ++kc) {
                     mbar_wait(&aempty_bar[as], aphase ^ 1, a.error, 0x500 + as);
@@ -792,6 +797,8 @@ modconv_tc_halo_t_kernel(const __grid_constant__ TcMaps maps, const __grid_const
             int ws = 0; uint32_t wphase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
+                const int rt = t % (m_tiles * per);
+                const TcSubProblem& s = a.sub[per == 1 ? 0 : ((rt % per) + rt / per) & 3];
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1, a.error, 0x200 + acc);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * HT_N);
@@ -829,7 +836,9 @@ modconv_tc_halo_t_kernel(const __grid_constant__ TcMaps maps, const __grid_const
         const int cstep = n_epi_warps * 8;                  // 4 epilogue warps: 32 columns, 8: 64
         int acc = 0; uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
-            const int m = t % m_tiles, n0 = (t / m_tiles) * 128;
+            const int rt = t % (m_tiles * per), n0 = (t / (m_tiles * per)) * 128;
+            const int m = rt / per;
+            const TcSubProblem& s = a.sub[per == 1 ? 0 : ((rt % per) + m) & 3];
             const int x0 = (m % tiles_x) * HT_TW, y0 = ((m / tiles_x) % tiles_y) * HT_TH, b = m / (tiles_x * tiles_y);
             const int ch = n0 + quarter * 32 + lane;
             const float d = __ldg(a.demod + (int64_t)b * a.cout + ch);
@@ -844,6 +853,18 @@ modconv_tc_halo_t_kernel(const __grid_constant__ TcMaps maps, const __grid_const
                 uint32_t r[32];
                 tmem_ld_32x32(taddr + (uint32_t)c0, r);
                 tmem_ld_wait();
+                if (a.mode == 1) {
+                    // transposed-conv phase: demodulated fp32 into the NHWC scratch at (2y + py, 2x + px); for every pixel
+                    // the warp writes 32 consecutive channels = one 128 B line
+#pragma unroll
+                    for (int rr = 0; rr < 4; ++rr) {
+                        const int oy = (y0 + c0 / HT_TW + rr) * s.ostride + s.ooff_y;
+                        float* row = a.out_f32 + (((int64_t)b * a.out_h + oy) * a.out_w + x0 * s.ostride + s.ooff_x) * a.cout + ch;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) row[(int64_t)j * s.ostride * a.cout] = __fmul_rn(__uint_as_float(r[rr * 8 + j]), d);
+                    }
+                    continue;
+                }
 #pragma unroll
                 for (int rr = 0; rr < 4; ++rr) {            // 32 columns = 4 tile rows of 8 pixels
                     const int y = y0 + c0 / HT_TW + rr;
@@ -1390,6 +1411,32 @@ static int launch_tc_any(int BN, int th, int tw, int tb, const TcMaps& maps, con
     return launch_tc_bn<32, BK, CG>(th, tw, tb, maps, a, stream);
 }
 
+// Second half of an up-sampling layer: Blur(4x4, pad 1) + noise + bias + lrelu over the fp32 NHWC scratch.
+static int tc_blur_after_upconv(TcWorkspace& ws, const TcConvCall& call, cudaStream_t stream) {
+    const int B = call.batch, H = call.res_in;
+        BlurSplitArgs bs;
+        bs.in = call.upconv_tmp; bs.IH = 2 * H + 1; bs.IW = 2 * H + 1;
+        bs.out_f32 = call.out_f32; bs.OH = call.res_out; bs.OW = call.res_out; bs.C = call.cout; bs.batch = B;
+        bs.blur_k = call.blur_k; bs.noise = call.noise; bs.noise_bstride = call.noise_bstride; bs.noise_w = call.noise_w; bs.bias = call.bias;
+        bs.s_next = call.s_next; bs.next_hi = (bf16*)ws.a_hi[call.out_slot]; bs.next_lo = (bf16*)ws.a_lo[call.out_slot];
+        bs.act = call.act ? 1 : 0;
+        SIS_REQUIRE(bs.C % 32 == 0, "tc_modconv: the blur pass needs Cout %% 32 == 0 (got %d)", bs.C);
+        static int blocks_per_sm[2] = {0, 0};
+        const int sep = call.blur_separable ? 1 : 0;
+        auto kern = sep ? blur_act_split_kernel<true> : blur_act_split_kernel<false>;
+        if (!blocks_per_sm[sep]) {
+            SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BS_SMEM));
+            SIS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[sep], kern, 256, BS_SMEM));
+            if (blocks_per_sm[sep] < 1) blocks_per_sm[sep] = 1;
+        }
+        const int64_t total = (int64_t)B * ceil_div(bs.OH, BS_TH) * ceil_div(bs.OW, BS_TW) * ceil_div(bs.C, BS_C);
+        const int grid = (int)std::min<int64_t>(total, (int64_t)kNumSMs * blocks_per_sm[sep]);   // exactly one resident wave
+        ProfScope prof(PROF_BLUR_SPLIT, stream);
+        kern<<<grid, 256, BS_SMEM, stream>>>(bs);
+        SIS_CHECK_LAUNCH();
+    return SIS_OK;
+}
+
 int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, cudaStream_t stream) {
     // Tunables for A/B runs: SIS_TC_BK (64 default | 32: stage depth along K), SIS_TC_CG (2 default | 1: CTA pairs)
     //                       SIS_TC_IM2COL (1 default | 0: spatial-box A tiles instead of flattened 128-pixel runs)
@@ -1414,7 +1461,7 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
         TcSubProblem& s = a.sub[0];
         s.ntaps = 9;
         for (int ky = 0; ky < 3; ++ky)
-            for (int kx = 0; kx < 3; ++kx) { int t = ky * 3 + kx; s.dy[t] = (signed char)(ky - 1); s.dx[t] = (signed char)(kx - 1); s.widx[t] = (signed char)t; }
+            for (int kx = 0; kx < 3; ++kx) { int t = ky * 3 + kx; s.dy[t] = (short)(ky - 1); s.dx[t] = (short)(kx - 1); s.widx[t] = (signed char)t; }
         s.oh = H; s.ow = H; s.ostride = 1;
         a.total_tiles = call.batch * (H / HT_TH) * (H / HT_TW) * a.n_tiles;
         a.out_f32 = call.out_f32; a.out_h = H; a.out_w = H;
@@ -1430,6 +1477,89 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
         SIS_PROPAGATE(make_map(&maps.w[1], w.lo, 3, wdims, wbox, HT_BK * 2));
         ProfScope prof(PROF_CONV_TC, stream);
         return launch_tc_halo_t(maps, a, stream);
+    }
+    // Cout = 128 up-convs: the interior H x H of the four phase grids on the transposed halo kernel (exact 32 x 8 tiles),
+    // the one extra row / column of the (H+1)-extent phases as four thin strips on the per-tap kernel below
+    static int up_t_env = env_int("SIS_TC_UP_T", 1) != 0;
+    const bool up_split = transposed_env && halo_env && im2col_env && call.up && call.cout == 128 && call.cin % 64 == 0 &&
+                          call.res_in % HT_TH == 0 && call.res_in <= 128 /* im2col box corners are 8-bit */ && up_t_env;
+    if (up_split) {
+        SIS_REQUIRE(w.hi && w.cin == call.cin && w.cout == call.cout, "tc_modconv: weights not packed for this layer");
+        TcKernelArgs a;
+        memset(&a, 0, sizeof(a));
+        const int H = call.res_in;
+        a.batch = call.batch; a.cin = call.cin; a.cout = call.cout; a.kchunks = call.cin / HT_BK;
+        a.b_tiles = call.batch; a.n_tiles = 1;
+        a.demod = call.demod; a.error = ws.d_error; a.mode = 1; a.nsub = 4;
+        int si = 0;
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+                TcSubProblem& s = a.sub[si++];
+                s.ntaps = 0;
+                for (int ky = py; ky < 3; ky += 2)
+                    for (int kx = px; kx < 3; kx += 2) {
+                        s.dy[s.ntaps] = (short)(-(ky / 2)); s.dx[s.ntaps] = (short)(-(kx / 2));
+                        s.widx[s.ntaps] = (signed char)(ky * 3 + kx); s.ntaps++;
+                    }
+                s.oh = H; s.ow = H; s.ostride = 2; s.ooff_y = py; s.ooff_x = px;
+            }
+        a.total_tiles = call.batch * (H / HT_TH) * (H / HT_TW) * 4;
+        a.out_f32 = call.upconv_tmp; a.out_h = 2 * H + 1; a.out_w = 2 * H + 1;
+        TcMaps maps;
+        memset(&maps, 0, sizeof(maps));
+        const uint64_t adims[4] = {(uint64_t)call.cin, (uint64_t)H, (uint64_t)H, (uint64_t)call.batch};
+        const uint32_t abox[4] = {(uint32_t)HT_BK, (uint32_t)HT_W, (uint32_t)HT_H, 1};
+        SIS_PROPAGATE(make_map(&maps.a[0][0], ws.a_hi[call.in_slot], 4, adims, abox, HT_BK * 2));
+        SIS_PROPAGATE(make_map(&maps.a[0][1], ws.a_lo[call.in_slot], 4, adims, abox, HT_BK * 2));
+        const uint64_t wdims[3] = {(uint64_t)call.cin, (uint64_t)call.cout, 9};
+        const uint32_t wbox[3] = {(uint32_t)HT_BK, 128, 1};
+        SIS_PROPAGATE(make_map(&maps.w[0], w.hi, 3, wdims, wbox, HT_BK * 2));
+        SIS_PROPAGATE(make_map(&maps.w[1], w.lo, 3, wdims, wbox, HT_BK * 2));
+        {
+            ProfScope prof(PROF_CONV_TC, stream);
+            SIS_PROPAGATE(launch_tc_halo_t(maps, a, stream));
+        }
+        // strips: (py=0) row yy = H of phases (0,0) [xx 0..H] and (0,1) [xx 0..H-1]; (px=0) column xx = H of phases
+        // (0,0) and (1,0) [yy 0..H-1].  Origins are folded into the tap offsets and the output offsets.
+        TcKernelArgs b;
+        memset(&b, 0, sizeof(b));
+        b.batch = call.batch; b.cin = call.cin; b.cout = call.cout; b.kchunks = call.cin / 64;
+        b.b_tiles = call.batch; b.n_tiles = 1;
+        b.demod = call.demod; b.error = ws.d_error; b.mode = 1; b.im2col = 1; b.nsub = 4;
+        b.out_f32 = call.upconv_tmp; b.out_h = 2 * H + 1; b.out_w = 2 * H + 1;
+        struct Strip { int py, px, y0, x0, oh, ow; };
+        const Strip strips[4] = {{0, 0, H, 0, 1, H + 1}, {0, 1, H, 0, 1, H}, {0, 0, 0, H, H, 1}, {1, 0, 0, H, H, 1}};
+        TcMaps mb;
+        memset(&mb, 0, sizeof(mb));
+        int tiles = 0;
+        for (int i = 0; i < 4; ++i) {
+            const Strip& sp = strips[i];
+            TcSubProblem& s = b.sub[i];
+            s.ntaps = 0;
+            for (int ky = sp.py; ky < 3; ky += 2)
+                for (int kx = sp.px; kx < 3; kx += 2) {
+                    s.dy[s.ntaps] = (short)(sp.y0 - ky / 2); s.dx[s.ntaps] = (short)(sp.x0 - kx / 2);
+                    s.widx[s.ntaps] = (signed char)(ky * 3 + kx); s.ntaps++;
+                }
+            s.oh = sp.oh; s.ow = sp.ow; s.ostride = 2; s.ooff_y = 2 * sp.y0 + sp.py; s.ooff_x = 2 * sp.x0 + sp.px;
+            s.m_tiles = (int)ceil_div64((int64_t)call.batch * s.oh * s.ow, BM);
+            s.base_dy = 32767; s.base_dx = 32767;
+            for (int t = 0; t < s.ntaps; ++t) { s.base_dy = std::min<int>(s.base_dy, s.dy[t]); s.base_dx = std::min<int>(s.base_dx, s.dx[t]); }
+            s.tiles_y = 1; s.tiles_x = 1; s.tile_begin = tiles;
+            tiles += s.m_tiles;
+            const int lw = s.base_dx, lh = s.base_dy, uw = s.base_dx + s.ow - H, uh = s.base_dy + s.oh - H;
+            SIS_PROPAGATE(make_im2col_map(&mb.a[i][0], ws.a_hi[call.in_slot], call.cin, H, H, call.batch, lw, lh, uw, uh, 64, 128));
+            SIS_PROPAGATE(make_im2col_map(&mb.a[i][1], ws.a_lo[call.in_slot], call.cin, H, H, call.batch, lw, lh, uw, uh, 64, 128));
+        }
+        b.total_tiles = tiles;
+        const uint32_t wbox64[3] = {64, 128, 1};
+        SIS_PROPAGATE(make_map(&mb.w[0], w.hi, 3, wdims, wbox64, 128));
+        SIS_PROPAGATE(make_map(&mb.w[1], w.lo, 3, wdims, wbox64, 128));
+        {
+            ProfScope prof(PROF_CONV_TC, stream);
+            SIS_PROPAGATE((launch_tc<128, 8, 16, 1, 64, 1>(mb, b, stream)));
+        }
+        return tc_blur_after_upconv(ws, call, stream);
     }
     // halo reuse: plain 3x3 layers whose image holds whole 16 x 8 tiles and whose K chunks are 64 wide
     const bool halo = halo_env && !call.up && call.res_in >= HALO_TH && call.res_in % HALO_TH == 0 && call.cin % 64 == 0;
@@ -1499,7 +1629,7 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
         TcSubProblem& s = a.sub[0];
         s.ntaps = 9;
         for (int ky = 0; ky < 3; ++ky)
-            for (int kx = 0; kx < 3; ++kx) { int t = ky * 3 + kx; s.dy[t] = (signed char)(ky - 1); s.dx[t] = (signed char)(kx - 1); s.widx[t] = (signed char)t; }
+            for (int kx = 0; kx < 3; ++kx) { int t = ky * 3 + kx; s.dy[t] = (short)(ky - 1); s.dx[t] = (short)(kx - 1); s.widx[t] = (signed char)t; }
         s.oh = H; s.ow = H; s.ostride = 1; s.ooff_y = 0; s.ooff_x = 0;
         s.tiles_y = ceil_div(H, th); s.tiles_x = ceil_div(H, tw); s.tile_begin = 0;
         tiles = units(s);
@@ -1515,7 +1645,7 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
                 s.ntaps = 0;
                 for (int ky = py; ky < 3; ky += 2)
                     for (int kx = px; kx < 3; kx += 2) {
-                        s.dy[s.ntaps] = (signed char)(-(ky / 2)); s.dx[s.ntaps] = (signed char)(-(kx / 2));
+                        s.dy[s.ntaps] = (short)(-(ky / 2)); s.dx[s.ntaps] = (short)(-(kx / 2));
                         s.widx[s.ntaps] = (signed char)(ky * 3 + kx); s.ntaps++;
                     }
                 s.oh = H + (py == 0 ? 1 : 0); s.ow = H + (px == 0 ? 1 : 0);
@@ -1567,28 +1697,7 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
     }
     SIS_PROPAGATE(st);
 
-    if (call.up) {
-        BlurSplitArgs bs;
-        bs.in = call.upconv_tmp; bs.IH = 2 * H + 1; bs.IW = 2 * H + 1;
-        bs.out_f32 = call.out_f32; bs.OH = call.res_out; bs.OW = call.res_out; bs.C = call.cout; bs.batch = B;
-        bs.blur_k = call.blur_k; bs.noise = call.noise; bs.noise_bstride = call.noise_bstride; bs.noise_w = call.noise_w; bs.bias = call.bias;
-        bs.s_next = call.s_next; bs.next_hi = (bf16*)ws.a_hi[call.out_slot]; bs.next_lo = (bf16*)ws.a_lo[call.out_slot];
-        bs.act = call.act ? 1 : 0;
-        SIS_REQUIRE(bs.C % 32 == 0, "tc_modconv: the blur pass needs Cout %% 32 == 0 (got %d)", bs.C);
-        static int blocks_per_sm[2] = {0, 0};
-        const int sep = call.blur_separable ? 1 : 0;
-        auto kern = sep ? blur_act_split_kernel<true> : blur_act_split_kernel<false>;
-        if (!blocks_per_sm[sep]) {
-            SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BS_SMEM));
-            SIS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[sep], kern, 256, BS_SMEM));
-            if (blocks_per_sm[sep] < 1) blocks_per_sm[sep] = 1;
-        }
-        const int64_t total = (int64_t)B * ceil_div(bs.OH, BS_TH) * ceil_div(bs.OW, BS_TW) * ceil_div(bs.C, BS_C);
-        const int grid = (int)std::min<int64_t>(total, (int64_t)kNumSMs * blocks_per_sm[sep]);   // exactly one resident wave
-        ProfScope prof(PROF_BLUR_SPLIT, stream);
-        kern<<<grid, 256, BS_SMEM, stream>>>(bs);
-        SIS_CHECK_LAUNCH();
-    }
+    if (call.up) SIS_PROPAGATE(tc_blur_after_upconv(ws, call, stream));
     return SIS_OK;
 }
 
