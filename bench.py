@@ -524,7 +524,7 @@ def main():
                     'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': traffic,
                     'peak_source': f'{peaks["source"]} bf16 sustained (kernel timed inside a long step)',
                     'passes': 3 if conv_key == 'conv_tc' else 1,
-                    'note': 'algorithmic FLOPs (2*MACs, SURVEY 8d) of all 13 StyledConv launches per step / their summed '
+                    'note': 'algorithmic FLOPs (2*MACs, SURVEY 8d) of the 13 StyledConv layers (14 GEMM launches) per step / their summed '
                             'CUDA-event time; the bf16x3 split issues 3 MMA passes per algorithmic FLOP, so tensor-pipe '
                             'work is 3x achieved',
                     'share_of_step': conv_ms / sum(v['ms_per_step'] for v in kernels.values())}

@@ -14,13 +14,13 @@ tail -c 1500 $OUT/bench_$TAG.json
 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/bench_ref_$TAG.json 2>> $OUT/bench_$TAG.err; echo "ref rc=$?"
 fi
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --profile-steps 1 --in-flight 1"   # one lane: launch order = layer order
-# launches of my library per resident step: 12 mapping + 2 input + 13 conv + 6 blur + 6 torgb + 4 label = 43
+# launches of my library per resident step: 12 mapping + 2 input + 14 conv + 6 blur + 6 torgb + 4 label = 44
 $CMD > $OUT/plain_$TAG.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_list_$TAG.log 2>&1
 echo "ncu list rc=$?"
-# all 13 conv GEMM launches of the 4th step (3 warm-up steps skipped)
+# all 14 conv GEMM launches of the 4th step (13 layers; the Cout = 128 up-conv issues two; 3 warm-up steps skipped)
 $CMD > $OUT/plain2_$TAG.log 2>&1 && \
-ncu --set full --clock-control none -k regex:modconv_tc -s 39 -c 13 -f -o /tmp/prof_conv_$TAG $CMD > $OUT/ncu_conv_$TAG.log 2>&1
+ncu --set full --clock-control none -k regex:modconv_tc -s 42 -c 14 -f -o /tmp/prof_conv_$TAG $CMD > $OUT/ncu_conv_$TAG.log 2>&1
 echo "ncu conv rc=$?"
 ncu -i /tmp/prof_conv_$TAG.ncu-rep --page raw --csv > $OUT/prof_conv_$TAG.csv 2>/dev/null
 # the memory-bound kernels of the 4th step: 6 blur + 6 torgb + 4 label (the 7th ToRGB is fused into the last label launch)
@@ -30,7 +30,7 @@ echo "ncu mem rc=$?"
 ncu -i /tmp/prof_mem_$TAG.ncu-rep --page raw --csv > $OUT/prof_mem_$TAG.csv 2>/dev/null
 # one launch of the dominant kernel (last plain conv, 128->128 at 256^2) with source, kept as a report
 $CMD > $OUT/plain4_$TAG.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:modconv_tc -s 51 -c 1 -f -o $OUT/prof_conv_last_$TAG $CMD > $OUT/ncu_conv_last_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:modconv_tc -s 55 -c 1 -f -o $OUT/prof_conv_last_$TAG $CMD > $OUT/ncu_conv_last_$TAG.log 2>&1
 echo "ncu conv-last rc=$?"
 du -sh $OUT; ls -la $OUT | head -40
 ncu -i $OUT/prof_conv_last_$TAG.ncu-rep --page source --csv > $OUT/prof_conv_last_source_$TAG.csv 2>/dev/null

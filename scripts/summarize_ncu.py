@@ -90,13 +90,13 @@ def reps():
             vals = [f'{float(v):.3f}' if re.match(r'^-?\d+\.\d+$', v) else v for v in vals]
             out.append(f'| `{short(r[col["Kernel Name"]])}` | ' + ' | '.join(vals) + ' |')
         if f.startswith('prof_conv_') and 'last' not in f and len(rows) - 2 == 13:
-            # DRAM traffic of the 13 conv GEMM launches of one step -> bench.py's roofline.traffic
+            # DRAM traffic of the conv GEMM launches of one step -> bench.py's roofline.traffic
             import json
             def gb(r, k):
                 v, u = float(r[col[k]]), units[col[k]]
                 return v * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0, 'Tbyte': 1e12}.get(u, 1.0)
             tot = sum(gb(r, 'dram__bytes_read.sum') + gb(r, 'dram__bytes_write.sum') for r in rows[2:])
-            json.dump({'conv_tc': tot, 'unit': 'bytes per step (13 launches, B=32, 256^2)', 'source': f'profiles/{f.replace(".csv", ".md")}'},
+            json.dump({'conv_tc': tot, 'unit': 'bytes per step (all conv GEMM launches of one step, B=32, 256^2)', 'source': f'profiles/{f.replace(".csv", ".md")}'},
                       open(os.path.join(P, 'traffic.json'), 'w'))
         name = f.replace('.ncu-rep', '.md').replace('.csv', '.md')
         open(os.path.join(P, name), 'w').write('\n'.join(out) + '\n')
