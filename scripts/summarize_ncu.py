@@ -89,7 +89,7 @@ def reps():
             vals = [r[col[k]] if k in col else '-' for k in METRICS]
             vals = [f'{float(v):.3f}' if re.match(r'^-?\d+\.\d+$', v) else v for v in vals]
             out.append(f'| `{short(r[col["Kernel Name"]])}` | ' + ' | '.join(vals) + ' |')
-        if f.startswith('prof_conv_') and 'last' not in f and len(rows) - 2 == 13:
+        if f.startswith('prof_conv_') and 'last' not in f and len(rows) - 2 in (13, 14):
             # DRAM traffic of the conv GEMM launches of one step -> bench.py's roofline.traffic
             import json
             def gb(r, k):
