@@ -694,7 +694,8 @@ modconv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const __grid_constan
 // 640 B group stride: exp_halo_desc.cu covers this case), the weights stream per tap.  TMEM lanes are output channels, so
 // the epilogue thread owns ONE channel and 32 consecutive tile pixels per chunk: demod / bias are per-thread scalars, the
 // noise row is shared by the warp, and the fp32 NCHW capture is written as 32 B row segments.  Used for plain layers with
-// Cout = 128, H a multiple of 32 and no following conv (no bf16 planes to emit): 128 -> 128 at 256^2 in the 256^2 model.
+// Cout = 128 and H a multiple of 32 (128 -> 128 at 256^2); when a conv follows, the epilogue also emits its pre-scaled
+// bf16 hi/lo NHWC planes (lane pairs trade values: one bf16x2 store per lane and pixel pair).
 constexpr int HT_TH = 32, HT_TW = 8, HT_W = HT_TW + 2, HT_H = HT_TH + 2, HT_BK = 32, HT_N = HT_TH * HT_TW;
 struct TcHaloTCfg {
     static constexpr int ROW = HT_BK * 2;                                        // 64 B operand rows
@@ -843,6 +844,7 @@ modconv_tc_halo_t_kernel(const __grid_constant__ TcMaps maps, const __grid_const
             const int ch = n0 + quarter * 32 + lane;
             const float d = __ldg(a.demod + (int64_t)b * a.cout + ch);
             const float bias = a.bias ? __ldg(a.bias + ch) : 0.0f;
+            const float sn = a.s_next ? __ldg(a.s_next + (int64_t)b * a.cout + ch) : 0.0f;
             float* plane = a.out_f32 + ((int64_t)b * a.cout + ch) * ((int64_t)a.out_h * a.out_w);
             const float* nzp = a.noise ? a.noise + (int64_t)b * a.noise_bstride : nullptr;
             mbar_wait(&tfull_bar[acc], acc_phase, a.error, 0x400 + acc);
@@ -886,6 +888,25 @@ modconv_tc_halo_t_kernel(const __grid_constant__ TcMaps maps, const __grid_const
                     float4* dst = reinterpret_cast<float4*>(plane + (int64_t)y * a.out_w + x0);
                     dst[0] = make_float4(v[0], v[1], v[2], v[3]);
                     dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+                    if (a.s_next) {
+                        // the next conv's pre-scaled bf16 hi/lo NHWC planes: per pixel the warp writes 32 consecutive
+                        // channels (64 B); lane pairs trade values so that every lane stores a bf16x2 for half of the pixels
+                        const int64_t off = (((int64_t)b * a.out_h + y) * a.out_w + x0) * a.cout + (ch & ~1);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float xs = __fmul_rn(v[j], sn);
+                            const float other = __shfl_xor_sync(0xffffffffu, xs, 1);
+                            if ((j & 1) == (lane & 1)) {
+                                const float c0v = (lane & 1) ? other : xs, c1v = (lane & 1) ? xs : other;   // channels ch&~1, ch|1
+                                const bf16 h0 = __float2bfloat16_rn(c0v), h1 = __float2bfloat16_rn(c1v);
+                                const bf16 l0 = __float2bfloat16_rn(c0v - __bfloat162float(h0)), l1 = __float2bfloat16_rn(c1v - __bfloat162float(h1));
+                                *reinterpret_cast<uint32_t*>(a.next_hi + off + (int64_t)j * a.cout) =
+                                    (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                                *reinterpret_cast<uint32_t*>(a.next_lo + off + (int64_t)j * a.cout) =
+                                    (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                            }
+                        }
+                    }
                 }
             }
             tc_fence_before();
@@ -1449,7 +1470,7 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
     }
     // transposed halo kernel: Cout = 128 plain layers that feed no further conv (SIS_TC_TRANSPOSED=0 disables)
     static int transposed_env = env_int("SIS_TC_TRANSPOSED", 1);
-    if (transposed_env && halo_env && !call.up && call.cout == 128 && call.cin % HT_BK == 0 && call.res_in % HT_TH == 0 && !call.s_next) {
+    if (transposed_env && halo_env && !call.up && call.cout == 128 && call.cin % HT_BK == 0 && call.res_in % HT_TH == 0) {
         SIS_REQUIRE(w.hi && w.cin == call.cin && w.cout == call.cout, "tc_modconv: weights not packed for this layer");
         TcKernelArgs a;
         memset(&a, 0, sizeof(a));
@@ -1465,6 +1486,7 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
         s.oh = H; s.ow = H; s.ostride = 1;
         a.total_tiles = call.batch * (H / HT_TH) * (H / HT_TW) * a.n_tiles;
         a.out_f32 = call.out_f32; a.out_h = H; a.out_w = H;
+        a.s_next = call.s_next; a.next_hi = (bf16*)ws.a_hi[call.out_slot]; a.next_lo = (bf16*)ws.a_lo[call.out_slot];
         TcMaps maps;
         memset(&maps, 0, sizeof(maps));
         const uint64_t adims[4] = {(uint64_t)call.cin, (uint64_t)H, (uint64_t)H, (uint64_t)call.batch};
