@@ -498,6 +498,12 @@ using namespace sis;
 
 namespace sis {
 
+static int64_t wide_min_quads() {
+    static int64_t v = -1;
+    if (v < 0) { const char* e = getenv("SIS_LABEL_WIDE_MIN_QUADS"); v = e ? atoll(e) : (int64_t)kNumSMs * 160; }   // measured: the wide kernel wins from ~24 k quads (64^2 maps at batch 32: 80 -> 67 us)
+    return v;
+}
+
 int launch_label(const LabelArgs& a_in, int mode, const ToRgbArgs* fuse_rgb, bool* fused, cudaStream_t stream) {
     LabelArgs a = a_in;
     if (fused) *fused = false;
@@ -533,7 +539,7 @@ int launch_label(const LabelArgs& a_in, int mode, const ToRgbArgs* fuse_rgb, boo
     // wide path: enough pixel quads to fill the GPU without slicing channels, integer (or no) mask replication,
     // rows that are a multiple of 4 pixels, k small enough for 4 x k register accumulators
     const int64_t quads = (int64_t)h * w / 4 * batch;
-    const bool wide_ok = vec4 && k <= 24 && (size_t)channels * 24 * 8 <= 160 * 1024 && w % 4 == 0 && quads >= (int64_t)kNumSMs * 512 && ((int64_t)h * w / 4) % 256 == 0 &&
+    const bool wide_ok = vec4 && k <= 24 && (size_t)channels * 24 * 8 <= 160 * 1024 && w % 4 == 0 && quads >= wide_min_quads() && ((int64_t)h * w / 4) % 256 == 0 &&
                          (!a.masks || (int_ratio && ((((uintptr_t)a.masks) & 15) == 0))) &&
                          (!a.ids_u8 || ((((uintptr_t)a.ids_u8) & 3) == 0)) && (!a.margin || ((((uintptr_t)a.margin) & 15) == 0));
     if (wide_ok) {

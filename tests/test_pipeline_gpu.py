@@ -129,7 +129,7 @@ def test_iter_host_equals_device_iteration(cuda_device):
 
 def test_in_forward_labelling_equals_separate_calls(cuda_device):
     """label_jobs inside Generator.forward (fused ToRGB + labelling pass on the large maps) gives the same image, masks,
-    ids and histograms as the separate sis_label_assign launches."""
+    ids and histograms as the separate sis_label_assign launches (to rounding: the summation orders differ)."""
     layers = ['8', '9', '12', '13']
     spec, sd, g, seg, cents = make_setup(256, layers, cuda_device)
     cfg = {'batch_size': 4, 'latent_size': 512}
@@ -138,11 +138,14 @@ def test_in_forward_labelling_equals_separate_calls(cuda_device):
     for v in seg.cluster_pixel_counts.values():
         v.zero_()
     b = next(iter(dc.LabelledPairGenerator(g, seg, cfg, seed=3, fused_labelling=True)))
-    assert torch.equal(a.image, b.image)
+    # the fused pass sums the ToRGB channels (and, on large maps, the distances) in a different order than the separate
+    # kernels: equal to rounding, not bit for bit
+    assert float((a.image - b.image).abs().max()) <= 2e-5 * float(a.image.abs().max())
     for layer in layers:
         for cn in NAMES:
-            assert torch.equal(a.masks[layer][cn], b.masks[layer][cn]), (layer, cn)
-        assert torch.equal(counts_a[layer], seg.cluster_pixel_counts[layer])
+            assert float((a.masks[layer][cn] != b.masks[layer][cn]).float().mean()) <= 1e-4, (layer, cn)
+        diff = (counts_a[layer] - seg.cluster_pixel_counts[layer]).abs().sum()
+        assert int(diff) <= 1e-4 * int(counts_a[layer].sum()), layer
 
 
 def test_create_segmentation_image_equals_oracle_contour_stage(cuda_device):
