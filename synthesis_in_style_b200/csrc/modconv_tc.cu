@@ -971,11 +971,16 @@ __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 // generic 16-tap path.  The bf16 hi/lo NHWC planes are written straight from registers (128 B per pixel per plane);
 // the fp32 NCHW capture goes through a shared-memory transpose that re-uses the input tile's storage.  All index
 // arithmetic is hoisted out of the per-element loops: the kernel is HBM-bound only if its instruction count is small.
-template <bool SEP>
-__global__ void __launch_bounds__(256, 3) blur_act_split_kernel(BlurSplitArgs a) {
-    extern __shared__ __align__(16) float stile[];    // [11*19][64] fp32; re-used as sout[64][129]
+// TMA = true: the input tile comes from ONE TMA box load (fp32 NHWC scratch, out-of-bounds rows / columns / channels are
+// zero-filled by the tensor map) into a two-deep ring, issued a tile ahead by thread 0: no per-thread staging
+// instructions (11 % of the kernel's issue slots) and the load of tile i+1 overlaps the math and stores of tile i.
+template <bool SEP, bool TMA>
+__global__ void __launch_bounds__(256, TMA ? 2 : 3) blur_act_split_kernel(BlurSplitArgs a, const __grid_constant__ CUtensorMap in_map) {
+    extern __shared__ __align__(128) float stile_raw[];    // [11*19][64] fp32 (x2 with TMA); re-used as sout[64][129]
     __shared__ float sk[16], skx[4], sky[4];
     __shared__ float snz[BS_TH * BS_TW];
+    __shared__ uint64_t tma_bar[2];
+    float* stile = TMA ? (float*)(((uintptr_t)stile_raw + 127) & ~(uintptr_t)127) : stile_raw;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 16) sk[tid] = a.blur_k[(3 - tid / 4) * 4 + (3 - tid % 4)];   // flipped taps
     __syncthreads();
@@ -983,18 +988,50 @@ __global__ void __launch_bounds__(256, 3) blur_act_split_kernel(BlurSplitArgs a)
     const int tiles_x = (a.OW + BS_TW - 1) / BS_TW, tiles_y = (a.OH + BS_TH - 1) / BS_TH;
     const int cgroups = (a.C + BS_C - 1) / BS_C;     // C = 32 (1024^2 layers): half of the lanes idle
     const int64_t total = (int64_t)a.batch * tiles_y * tiles_x * cgroups;
-    const uint32_t stile_u32 = smem_u32(stile);
-    const float2* st2 = reinterpret_cast<const float2*>(stile);    // [pix][32 lanes]
     const int part = tid & 15;
-
-    for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    float* const ring0 = stile;
+    auto tile_coords = [&](int64_t tile, int& b, int& y0, int& x0, int& c0) {
         const int cg = (int)(tile % cgroups);
         int64_t r = tile / cgroups;
         const int tx = (int)(r % tiles_x); r /= tiles_x;
         const int ty = (int)(r % tiles_y);
-        const int b = (int)(r / tiles_y);
-        const int y0 = ty * BS_TH, x0 = tx * BS_TW, c0 = cg * BS_C;
+        b = (int)(r / tiles_y); y0 = ty * BS_TH; x0 = tx * BS_TW; c0 = cg * BS_C;
+    };
+    if (TMA) {
+        if (tid == 0) {
+            mbar_init(&tma_bar[0], 1); mbar_init(&tma_bar[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            if ((int64_t)blockIdx.x < total) {
+                int b, y0, x0, c0;
+                tile_coords(blockIdx.x, b, y0, x0, c0);
+                mbar_expect_tx(&tma_bar[0], BS_SMEM);
+                tma_load_4d(&in_map, &tma_bar[0], ring0, c0, x0 - 1, y0 - 1, b);
+            }
+        }
+    }
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        int b, y0, x0, c0;
+        tile_coords(tile, b, y0, x0, c0);
+        if (TMA) stile = ring0 + (it & 1) * (BS_SMEM / 4);
+        const uint32_t stile_u32 = smem_u32(stile);
+        const float2* st2 = reinterpret_cast<const float2*>(stile);    // [pix][32 lanes]
         __syncthreads();     // previous tile's transpose reads are done (and the tap tables are visible)
+        if (TMA) {
+            // the other ring slot held the previous tile (its transposed output was just consumed): refill it a tile ahead
+            if (tid == 0 && tile + gridDim.x < total) {
+                int nb, ny0, nx0, nc0;
+                tile_coords(tile + gridDim.x, nb, ny0, nx0, nc0);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy accesses of that slot are done
+                mbar_expect_tx(&tma_bar[(it + 1) & 1], BS_SMEM);
+                tma_load_4d(&in_map, &tma_bar[(it + 1) & 1], ring0 + ((it + 1) & 1) * (BS_SMEM / 4), nc0, nx0 - 1, ny0 - 1, nb);
+            }
+            if (tid < BS_TH * BS_TW) {
+                const int oy = y0 + (tid >> 4), ox = x0 + (tid & 15);
+                snz[tid] = (a.noise && oy < a.OH && ox < a.OW) ? a.noise_w * __ldg(a.noise + (int64_t)b * a.noise_bstride + (int64_t)oy * a.OW + ox) : 0.0f;
+            }
+            mbar_wait(&tma_bar[it & 1], (uint32_t)((it >> 1) & 1), nullptr, 0);
+        } else {
         // ---- stage the input tile: 16 threads per pixel (16-byte parts), 16 pixels per pass
         {
             const float* src_base = a.in + (int64_t)b * a.IH * a.IW * a.C + c0 + part * 4;
@@ -1014,6 +1051,7 @@ __global__ void __launch_bounds__(256, 3) blur_act_split_kernel(BlurSplitArgs a)
             }
         }
         cp_async_wait_all();
+        }
         __syncthreads();
 
         // ---- blur: column pair (px, px+1), rows top to bottom
@@ -1203,6 +1241,24 @@ static PFN_encodeTiled get_encode_fn() {
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
     fn = (PFN_encodeTiled)p;
     return fn;
+}
+
+// fp32 tensor, no swizzle (the blur kernel's input tiles)
+static int make_map_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint32_t* box) {
+    PFN_encodeTiled enc = get_encode_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return SIS_ERR_CUDA; }
+    cuuint64_t gdim[5]; cuuint64_t gstride[4]; cuuint32_t bdim[5]; cuuint32_t estr[5];
+    uint64_t stride = 4;
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1;
+        stride *= dims[i];
+        if (i < rank - 1) gstride[i] = stride;
+    }
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstride, bdim, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (fp32) failed with CUresult %d", (int)r); return SIS_ERR_CUDA; }
+    return SIS_OK;
 }
 
 static int make_map(CUtensorMap* map, void* base, int rank, const uint64_t* dims, const uint32_t* box, int swizzle_bytes) {
@@ -1442,18 +1498,31 @@ static int tc_blur_after_upconv(TcWorkspace& ws, const TcConvCall& call, cudaStr
         bs.s_next = call.s_next; bs.next_hi = (bf16*)ws.a_hi[call.out_slot]; bs.next_lo = (bf16*)ws.a_lo[call.out_slot];
         bs.act = call.act ? 1 : 0;
         SIS_REQUIRE(bs.C % 32 == 0, "tc_modconv: the blur pass needs Cout %% 32 == 0 (got %d)", bs.C);
-        static int blocks_per_sm[2] = {0, 0};
+        // SIS_BLUR_TMA (1 default | 0): TMA-fed two-deep input ring (2 blocks / SM) or cp.async staging (3 blocks / SM)
+        static int tma_env = env_int("SIS_BLUR_TMA", 1) != 0;
+        const bool tma = tma_env && (bs.C * 4) % 16 == 0;
+        static int blocks_per_sm[4] = {0, 0, 0, 0};
         const int sep = call.blur_separable ? 1 : 0;
-        auto kern = sep ? blur_act_split_kernel<true> : blur_act_split_kernel<false>;
-        if (!blocks_per_sm[sep]) {
-            SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, BS_SMEM));
-            SIS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[sep], kern, 256, BS_SMEM));
-            if (blocks_per_sm[sep] < 1) blocks_per_sm[sep] = 1;
+        const int variant = sep + (tma ? 2 : 0);
+        const size_t smem = tma ? 2 * (size_t)BS_SMEM + 128 : (size_t)BS_SMEM;
+        auto kern = tma ? (sep ? blur_act_split_kernel<true, true> : blur_act_split_kernel<false, true>)
+                        : (sep ? blur_act_split_kernel<true, false> : blur_act_split_kernel<false, false>);
+        if (!blocks_per_sm[variant]) {
+            SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            SIS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[variant], kern, 256, smem));
+            if (blocks_per_sm[variant] < 1) blocks_per_sm[variant] = 1;
+        }
+        CUtensorMap in_map;
+        memset(&in_map, 0, sizeof(in_map));
+        if (tma) {
+            const uint64_t dims[4] = {(uint64_t)bs.C, (uint64_t)bs.IW, (uint64_t)bs.IH, (uint64_t)B};
+            const uint32_t box[4] = {(uint32_t)BS_C, (uint32_t)BS_IW, (uint32_t)BS_IH, 1};
+            SIS_PROPAGATE(make_map_f32(&in_map, bs.in, 4, dims, box));
         }
         const int64_t total = (int64_t)B * ceil_div(bs.OH, BS_TH) * ceil_div(bs.OW, BS_TW) * ceil_div(bs.C, BS_C);
-        const int grid = (int)std::min<int64_t>(total, (int64_t)kNumSMs * blocks_per_sm[sep]);   // exactly one resident wave
+        const int grid = (int)std::min<int64_t>(total, (int64_t)kNumSMs * blocks_per_sm[variant]);   // exactly one resident wave
         ProfScope prof(PROF_BLUR_SPLIT, stream);
-        kern<<<grid, 256, BS_SMEM, stream>>>(bs);
+        kern<<<grid, 256, smem, stream>>>(bs, in_map);
         SIS_CHECK_LAUNCH();
     return SIS_OK;
 }
