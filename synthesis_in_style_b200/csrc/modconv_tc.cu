@@ -974,8 +974,9 @@ __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 // TMA = true: the input tile comes from ONE TMA box load (fp32 NHWC scratch, out-of-bounds rows / columns / channels are
 // zero-filled by the tensor map) into a two-deep ring, issued a tile ahead by thread 0: no per-thread staging
 // instructions (11 % of the kernel's issue slots) and the load of tile i+1 overlaps the math and stores of tile i.
-template <bool SEP, bool TMA>
-__global__ void __launch_bounds__(256, TMA ? 2 : 3) blur_act_split_kernel(BlurSplitArgs a, const __grid_constant__ CUtensorMap in_map) {
+template <bool SEP, int RING>     // RING: 0 = cp.async staging, 1 / 2 = TMA ring depth
+__global__ void __launch_bounds__(256, RING == 2 ? 2 : 3) blur_act_split_kernel(BlurSplitArgs a, const __grid_constant__ CUtensorMap in_map) {
+    constexpr bool TMA = RING > 0;
     extern __shared__ __align__(128) float stile_raw[];    // [11*19][64] fp32 (x2 with TMA); re-used as sout[64][129]
     __shared__ float sk[16], skx[4], sky[4];
     __shared__ float snz[BS_TH * BS_TW];
@@ -1001,7 +1002,7 @@ __global__ void __launch_bounds__(256, TMA ? 2 : 3) blur_act_split_kernel(BlurSp
         if (tid == 0) {
             mbar_init(&tma_bar[0], 1); mbar_init(&tma_bar[1], 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            if ((int64_t)blockIdx.x < total) {
+            if (RING == 2 && (int64_t)blockIdx.x < total) {
                 int b, y0, x0, c0;
                 tile_coords(blockIdx.x, b, y0, x0, c0);
                 mbar_expect_tx(&tma_bar[0], BS_SMEM);
@@ -1013,24 +1014,30 @@ __global__ void __launch_bounds__(256, TMA ? 2 : 3) blur_act_split_kernel(BlurSp
     for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
         int b, y0, x0, c0;
         tile_coords(tile, b, y0, x0, c0);
-        if (TMA) stile = ring0 + (it & 1) * (BS_SMEM / 4);
+        if (RING == 2) stile = ring0 + (it & 1) * (BS_SMEM / 4);
         const uint32_t stile_u32 = smem_u32(stile);
         const float2* st2 = reinterpret_cast<const float2*>(stile);    // [pix][32 lanes]
         __syncthreads();     // previous tile's transpose reads are done (and the tap tables are visible)
         if (TMA) {
             // the other ring slot held the previous tile (its transposed output was just consumed): refill it a tile ahead
-            if (tid == 0 && tile + gridDim.x < total) {
+            if (RING == 2 && tid == 0 && tile + gridDim.x < total) {
                 int nb, ny0, nx0, nc0;
                 tile_coords(tile + gridDim.x, nb, ny0, nx0, nc0);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy accesses of that slot are done
                 mbar_expect_tx(&tma_bar[(it + 1) & 1], BS_SMEM);
                 tma_load_4d(&in_map, &tma_bar[(it + 1) & 1], ring0 + ((it + 1) & 1) * (BS_SMEM / 4), nc0, nx0 - 1, ny0 - 1, nb);
             }
+            if (RING == 1 && tid == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&tma_bar[0], BS_SMEM);
+                tma_load_4d(&in_map, &tma_bar[0], ring0, c0, x0 - 1, y0 - 1, b);
+            }
             if (tid < BS_TH * BS_TW) {
                 const int oy = y0 + (tid >> 4), ox = x0 + (tid & 15);
                 snz[tid] = (a.noise && oy < a.OH && ox < a.OW) ? a.noise_w * __ldg(a.noise + (int64_t)b * a.noise_bstride + (int64_t)oy * a.OW + ox) : 0.0f;
             }
-            mbar_wait(&tma_bar[it & 1], (uint32_t)((it >> 1) & 1), nullptr, 0);
+            if (RING == 2) mbar_wait(&tma_bar[it & 1], (uint32_t)((it >> 1) & 1), nullptr, 0);
+            else mbar_wait(&tma_bar[0], (uint32_t)(it & 1), nullptr, 0);
         } else {
         // ---- stage the input tile: 16 threads per pixel (16-byte parts), 16 pixels per pass
         {
@@ -1498,15 +1505,16 @@ static int tc_blur_after_upconv(TcWorkspace& ws, const TcConvCall& call, cudaStr
         bs.s_next = call.s_next; bs.next_hi = (bf16*)ws.a_hi[call.out_slot]; bs.next_lo = (bf16*)ws.a_lo[call.out_slot];
         bs.act = call.act ? 1 : 0;
         SIS_REQUIRE(bs.C % 32 == 0, "tc_modconv: the blur pass needs Cout %% 32 == 0 (got %d)", bs.C);
-        // SIS_BLUR_TMA (1 default | 0): TMA-fed two-deep input ring (2 blocks / SM) or cp.async staging (3 blocks / SM)
-        static int tma_env = env_int("SIS_BLUR_TMA", 1) != 0;
-        const bool tma = tma_env && (bs.C * 4) % 16 == 0;
-        static int blocks_per_sm[4] = {0, 0, 0, 0};
+        static int ring_env = env_int("SIS_BLUR_TMA", 2);      // 0: cp.async, 1: TMA single buffer (3 blocks/SM), 2: TMA ring of 2
+        const int ring = (bs.C * 4) % 16 == 0 ? (ring_env < 0 ? 0 : ring_env > 2 ? 2 : ring_env) : 0;
+        const bool tma = ring > 0;
+        static int blocks_per_sm[6] = {0, 0, 0, 0, 0, 0};
         const int sep = call.blur_separable ? 1 : 0;
-        const int variant = sep + (tma ? 2 : 0);
-        const size_t smem = tma ? 2 * (size_t)BS_SMEM + 128 : (size_t)BS_SMEM;
-        auto kern = tma ? (sep ? blur_act_split_kernel<true, true> : blur_act_split_kernel<false, true>)
-                        : (sep ? blur_act_split_kernel<true, false> : blur_act_split_kernel<false, false>);
+        const int variant = sep + 2 * ring;
+        const size_t smem = ring == 2 ? 2 * (size_t)BS_SMEM + 128 : ring == 1 ? (size_t)BS_SMEM + 128 : (size_t)BS_SMEM;
+        auto kern = ring == 2 ? (sep ? blur_act_split_kernel<true, 2> : blur_act_split_kernel<false, 2>)
+                  : ring == 1 ? (sep ? blur_act_split_kernel<true, 1> : blur_act_split_kernel<false, 1>)
+                              : (sep ? blur_act_split_kernel<true, 0> : blur_act_split_kernel<false, 0>);
         if (!blocks_per_sm[variant]) {
             SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             SIS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[variant], kern, 256, smem));
