@@ -23,9 +23,9 @@ $CMD > $OUT/plain2_$TAG.log 2>&1 && \
 ncu --set full --clock-control none -k regex:modconv_tc -s 42 -c 14 -f -o /tmp/prof_conv_$TAG $CMD > $OUT/ncu_conv_$TAG.log 2>&1
 echo "ncu conv rc=$?"
 ncu -i /tmp/prof_conv_$TAG.ncu-rep --page raw --csv > $OUT/prof_conv_$TAG.csv 2>/dev/null
-# the memory-bound kernels of the 4th step: 6 blur + 6 torgb + 4 label (the 7th ToRGB is fused into the last label launch)
+# the memory-bound kernels of the 4th step: 6 blur + 5 torgb + 4 label (the 64^2 and 256^2 ToRGBs are fused into label launches)
 $CMD > $OUT/plain3_$TAG.log 2>&1 && \
-ncu --set full --clock-control none -k regex:"label_|blur_act_split|torgb_" -s 48 -c 16 -f -o /tmp/prof_mem_$TAG $CMD > $OUT/ncu_mem_$TAG.log 2>&1
+ncu --set full --clock-control none -k regex:"label_|blur_act_split|torgb_" -s 45 -c 15 -f -o /tmp/prof_mem_$TAG $CMD > $OUT/ncu_mem_$TAG.log 2>&1
 echo "ncu mem rc=$?"
 ncu -i /tmp/prof_mem_$TAG.ncu-rep --page raw --csv > $OUT/prof_mem_$TAG.csv 2>/dev/null
 # one launch of the dominant kernel (last plain conv, 128->128 at 256^2) with source, kept as a report
