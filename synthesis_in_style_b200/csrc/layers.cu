@@ -170,7 +170,9 @@ extern "C" int sis_modulated_conv2d(const float* d_x, int batch, int cin, int re
         const size_t need = (size_t)batch * cin * res * res * 2;
         if (need > L.tc_plane_bytes || L.tcws.batch != batch) {
             tc_free_workspace(L.tcws);
-            SIS_PROPAGATE(tc_ensure_workspace(L.tcws, batch, res, cin, std::map<int, int>{{4, cin}, {8, cin}, {16, cin}, {32, cin}, {64, cin},
+            int res_p2 = 4;                       // the workspace is sized per power-of-two resolution; round odd sizes up
+            while (res_p2 < res) res_p2 *= 2;
+            SIS_PROPAGATE(tc_ensure_workspace(L.tcws, batch, res_p2, cin, std::map<int, int>{{4, cin}, {8, cin}, {16, cin}, {32, cin}, {64, cin},
                                                                                           {128, cin}, {256, cin}, {512, cin}, {1024, cin}}));
             L.tc_plane_bytes = L.tcws.a_bytes;
         }

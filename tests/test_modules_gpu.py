@@ -29,7 +29,11 @@ def test_equal_linear_and_pixel_norm(cuda_device):
 
 
 @pytest.mark.parametrize('precision,tol', [('fp32', 2e-5), ('bf16x3', 5e-4)])
-@pytest.mark.parametrize('cfg', [(64, 128, 16, False, True), (128, 64, 8, True, True), (64, 64, 32, False, False), (32, 32, 16, True, True)])
+@pytest.mark.parametrize('cfg', [(64, 128, 16, False, True), (128, 64, 8, True, True), (64, 64, 32, False, False), (32, 32, 16, True, True),
+                                 # Cout = 128 with H a multiple of 32: the transposed-product kernels (plain: 32 x 8 halo tiles;
+                                 # up: phase interiors + border strips), incl. a non-power-of-two size and demod off
+                                 (128, 128, 32, False, True), (64, 128, 96, False, True), (96, 128, 64, False, False),
+                                 (128, 128, 32, True, True), (64, 128, 64, True, True)])
 def test_modulated_and_styled_conv(cuda_device, cfg, precision, tol):
     cin, cout, res, up, demod = cfg
     torch.manual_seed(cin + cout + res)
