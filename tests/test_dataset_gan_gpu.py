@@ -106,6 +106,12 @@ def test_checkpoint_loading_and_errors(cuda_device, tmp_path):
     assert images.shape == (2, 16, 16, 3) and drop == []
     want, _, _ = dg.predict_labels([dg.ClassifierParams(s) for s in states], {k: v.cpu() for k, v in acts.items()}, 16)
     assert float((seg.predict_labels(acts).cpu().float() == want).float().mean()) >= 0.99
+    # an image size that is not a multiple of the 16 x 8 tile takes the generic (untiled) tail kernel
+    small = {0: torch.randn(2, 32, 4, 4, device=cuda_device), 1: torch.randn(2, 32, 8, 8, device=cuda_device)}
+    got8, votes8, _ = seg.ensemble.predict_label_images(small, 8, want_votes=True)
+    want8, margin8, want_votes8 = dg.predict_labels([dg.ClassifierParams(s) for s in states], {k: v.cpu() for k, v in small.items()}, 8)
+    safe8 = margin8 > 1e-3
+    assert bool((got8.cpu().float()[safe8] == want8[safe8]).all()) and votes8.shape == (2, 8, 8, 2)
     with pytest.raises(RuntimeError):                      # feature size mismatch
         seg.ensemble.predict_label_images({0: torch.randn(2, 32, 4, 4, device=cuda_device)}, 16)
     with pytest.raises(RuntimeError):                      # host tensors are refused: no CPU fallback
