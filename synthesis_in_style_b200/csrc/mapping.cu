@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(32 * SM_COLS) linear_small_m_kernel(const Line
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m0 + r < job.M) {
             const float* src = job.A + (int64_t)(m0 + r) * job.lda + c4 * 4;
-            v = make_float4(src[0], src[1], src[2], src[3]);
+            if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) v = __ldg(reinterpret_cast<const float4*>(src));   // one 128-bit load
+            else v = make_float4(src[0], src[1], src[2], src[3]);
             if (job.square_a) { v.x *= v.x; v.y *= v.y; v.z *= v.z; v.w *= v.w; }
         }
         reinterpret_cast<float4*>(xs)[i] = v;
