@@ -1178,22 +1178,33 @@ __global__ void __launch_bounds__(256) prescale_split_kernel(bf16* __restrict__ 
 }
 
 // NCHW fp32 plane set -> a channel slice [c_off, c_off + C) of an NHWC bf16 hi/lo plane pair with c_total channels
-// (unscaled).  64 channels x 32 pixels per block through shared memory: reads are 128 B runs along the pixels, writes
-// 128 B runs along the channels.  Used by the DatasetGAN labeller to stack the captures of one resolution along K.
+// (unscaled), through a shared-memory transpose.  Used by the DatasetGAN labeller to stack the captures of one resolution along K.
 __global__ void __launch_bounds__(256) nchw_to_nhwc_split_kernel(bf16* __restrict__ hi, bf16* __restrict__ lo, const float* __restrict__ x,
                                                                  int C, int64_t hw, int c_total, int c_off) {
-    __shared__ float tile[64][33];
+    // 64 channels x 64 pixels per block: 128-bit loads along the pixels (when hw is a multiple of 4), 128 B stores along
+    // the channels
+    __shared__ float tile[64][65];
     const int b = blockIdx.z, c0 = blockIdx.y * 64;
-    const int64_t p0 = (int64_t)blockIdx.x * 32;
+    const int64_t p0 = (int64_t)blockIdx.x * 64;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int cc = w; cc < 64; cc += 8) {
-        const int c = c0 + cc;
-        float v = 0.0f;
-        if (c < C && p0 + lane < hw) v = __ldg(x + ((int64_t)b * C + c) * hw + p0 + lane);
-        tile[cc][lane] = v;
+    const bool vec = (hw & 3) == 0;
+    if (vec) {
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            const int cc = i >> 4, q = i & 15;
+            const int c = c0 + cc;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < C && p0 + 4 * q < hw) v = __ldg(reinterpret_cast<const float4*>(x + ((int64_t)b * C + c) * hw + p0) + q);
+            tile[cc][4 * q] = v.x; tile[cc][4 * q + 1] = v.y; tile[cc][4 * q + 2] = v.z; tile[cc][4 * q + 3] = v.w;
+        }
+    } else {
+        for (int i = threadIdx.x; i < 64 * 64; i += 256) {
+            const int cc = i >> 6, pp = i & 63;
+            const int c = c0 + cc;
+            tile[cc][pp] = (c < C && p0 + pp < hw) ? __ldg(x + ((int64_t)b * C + c) * hw + p0 + pp) : 0.0f;
+        }
     }
     __syncthreads();
-    for (int pp = w; pp < 32; pp += 8) {
+    for (int pp = w; pp < 64; pp += 8) {
         const int64_t p = p0 + pp;
         const int c = c0 + 2 * lane;
         if (p >= hw || c >= C) continue;
@@ -1803,7 +1814,7 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
 // ------------------------------------------------------------------------------- 1x1 GEMM (DatasetGAN labeller)
 int tc_nchw_to_nhwc_split(void* hi, void* lo, const float* x, int batch, int c, int64_t hw, int c_total, int c_off, cudaStream_t stream) {
     SIS_REQUIRE(c % 2 == 0 && c_off % 2 == 0 && c_total % 2 == 0, "nchw_to_nhwc_split: channel counts must be even");
-    dim3 grid((unsigned)ceil_div64(hw, 32), (unsigned)ceil_div(c, 64), (unsigned)batch);
+    dim3 grid((unsigned)ceil_div64(hw, 64), (unsigned)ceil_div(c, 64), (unsigned)batch);
     ProfScope prof(PROF_OTHER, stream);
     nchw_to_nhwc_split_kernel<<<grid, 256, 0, stream>>>((bf16*)hi, (bf16*)lo, x, c, hw, c_total, c_off);
     SIS_CHECK_LAUNCH();
