@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(128) dataset_gan_tail_kernel(GanTailArgs a) {
 // is read directly (consecutive lanes = consecutive pixels).  Working in 32-channel chunks keeps a thread at 32
 // activations + 32 second-layer accumulators (the chunk is folded into Linear2 as soon as it is complete), so four
 // blocks fit on an SM.
-constexpr int GAN_TX = 16, GAN_TY = 8, GAN_CH = 32, GAN_SRC_STRIDE = GAN_CH + 4, GAN_SRC_PIX = 60;
+constexpr int GAN_TX = 16, GAN_TY = 8, GAN_CH = 32, GAN_SRC_STRIDE = GAN_CH + 4;
+constexpr int GAN_SRC_PIX = 60 + 24 + 12 + 9 + 9 + 9 + 9;      // footprints of up to 7 low-resolution products, scales 2, 4, 8, >= 16
 
 __device__ __forceinline__ void gan_src_range(int o0, int n, int r, int S, int& lo, int& hi) {
     const float sc = (float)r / (float)S;
@@ -193,6 +194,31 @@ __global__ void __launch_bounds__(128, 4) dataset_gan_tail_tiled_kernel(GanTailA
             float z[GAN_CH];
 #pragma unroll
             for (int i = 0; i < GAN_CH; ++i) z[i] = s_b1[ch0 + i];
+            // stage the footprints of ALL low-resolution products for this chunk at once (at most 60 + 24 + 12 + 9 + 9 + 6
+            // source pixels for scales 2 .. 64): two block barriers per chunk instead of two per product
+            __syncthreads();                                     // the previous chunk's taps are consumed
+            int base_px[GAN_MAX_GROUPS];
+            {
+                int acc_px = 0;
+                for (int g = 0; g < a.n_groups; ++g) {
+                    base_px[g] = acc_px;
+                    if (!a.nhwc[g]) continue;
+                    const int r = a.res[g];
+                    int fy0, fy1, fx0, fx1;
+                    gan_src_range(oy0, GAN_TY, r, a.S, fy0, fy1);
+                    gan_src_range(ox0, GAN_TX, r, a.S, fx0, fx1);
+                    const int fw = fx1 - fx0 + 1, fh = fy1 - fy0 + 1;
+                    for (int q = tid; q < fh * fw * (GAN_CH / 4); q += 128) {
+                        const int px = q / (GAN_CH / 4), c4 = q - px * (GAN_CH / 4);
+                        const int py = px / fw, pxx = px - py * fw;
+                        const float4 v = __ldg(reinterpret_cast<const float4*>(
+                            a.y[g] + (((int64_t)b * r + fy0 + py) * r + fx0 + pxx) * N + m * GAN_H1 + ch0) + c4);
+                        *reinterpret_cast<float4*>(s_src + (acc_px + px) * GAN_SRC_STRIDE + c4 * 4) = v;
+                    }
+                    acc_px += fh * fw;
+                }
+            }
+            __syncthreads();
 #pragma unroll 1
             for (int g = 0; g < a.n_groups; ++g) {
                 const int r = a.res[g];
@@ -206,16 +232,8 @@ __global__ void __launch_bounds__(128, 4) dataset_gan_tail_tiled_kernel(GanTailA
                 int fy0, fy1, fx0, fx1;
                 gan_src_range(oy0, GAN_TY, r, a.S, fy0, fy1);
                 gan_src_range(ox0, GAN_TX, r, a.S, fx0, fx1);
-                const int fw = fx1 - fx0 + 1, fh = fy1 - fy0 + 1;
-                __syncthreads();                                     // the previous footprint is consumed
-                for (int q = tid; q < fh * fw * (GAN_CH / 4); q += 128) {
-                    const int px = q / (GAN_CH / 4), c4 = q - px * (GAN_CH / 4);
-                    const int py = px / fw, pxx = px - py * fw;
-                    const float4 v = __ldg(reinterpret_cast<const float4*>(
-                        a.y[g] + (((int64_t)b * r + fy0 + py) * r + fx0 + pxx) * N + m * GAN_H1 + ch0) + c4);
-                    *reinterpret_cast<float4*>(s_src + px * GAN_SRC_STRIDE + c4 * 4) = v;
-                }
-                __syncthreads();
+                const int fw = fx1 - fx0 + 1;
+                const float* src = s_src + base_px[g] * GAN_SRC_STRIDE;
                 // nn.Upsample(scale_factor = S / r, mode='bilinear'), align_corners = False
                 const float sc = (float)r / (float)a.S;
                 const float fy = fmaxf(((float)oy + 0.5f) * sc - 0.5f, 0.0f), fx = fmaxf(((float)ox + 0.5f) * sc - 0.5f, 0.0f);
@@ -223,10 +241,10 @@ __global__ void __launch_bounds__(128, 4) dataset_gan_tail_tiled_kernel(GanTailA
                 const int y1 = min(y0 + 1, r - 1), x1 = min(x0 + 1, r - 1);
                 const float ly = fy - (float)y0, lx = fx - (float)x0;
                 const float w00 = (1.0f - ly) * (1.0f - lx), w01 = (1.0f - ly) * lx, w10 = ly * (1.0f - lx), w11 = ly * lx;
-                const float4* q00 = reinterpret_cast<const float4*>(s_src + ((y0 - fy0) * fw + x0 - fx0) * GAN_SRC_STRIDE);
-                const float4* q01 = reinterpret_cast<const float4*>(s_src + ((y0 - fy0) * fw + x1 - fx0) * GAN_SRC_STRIDE);
-                const float4* q10 = reinterpret_cast<const float4*>(s_src + ((y1 - fy0) * fw + x0 - fx0) * GAN_SRC_STRIDE);
-                const float4* q11 = reinterpret_cast<const float4*>(s_src + ((y1 - fy0) * fw + x1 - fx0) * GAN_SRC_STRIDE);
+                const float4* q00 = reinterpret_cast<const float4*>(src + ((y0 - fy0) * fw + x0 - fx0) * GAN_SRC_STRIDE);
+                const float4* q01 = reinterpret_cast<const float4*>(src + ((y0 - fy0) * fw + x1 - fx0) * GAN_SRC_STRIDE);
+                const float4* q10 = reinterpret_cast<const float4*>(src + ((y1 - fy0) * fw + x0 - fx0) * GAN_SRC_STRIDE);
+                const float4* q11 = reinterpret_cast<const float4*>(src + ((y1 - fy0) * fw + x1 - fx0) * GAN_SRC_STRIDE);
 #pragma unroll
                 for (int i4 = 0; i4 < GAN_CH / 4; ++i4) {
                     const float4 v00 = q00[i4], v01 = q01[i4], v10 = q10[i4], v11 = q11[i4];
@@ -473,7 +491,15 @@ extern "C" int sis_pixel_ensemble_label(sis_pixel_ensemble* e, int n_layers, con
     memset(&t, 0, sizeof(t));
     // tiled tail: 16 x 8 pixel tiles, power-of-two integer scale factors (footprints of at most 6 x 10 source pixels)
     bool tiled = image_size % GAN_TX == 0 && image_size % GAN_TY == 0;
-    for (auto& g : e->groups) tiled = tiled && image_size % g.res == 0 && (g.res == image_size || image_size / g.res >= 2);
+    int footprint_px = 0;                     // conservative bound of the staged source pixels of all low-resolution products
+    for (auto& g : e->groups) {
+        tiled = tiled && image_size % g.res == 0 && (g.res == image_size || image_size / g.res >= 2);
+        if (g.res < image_size && image_size % g.res == 0) {
+            const int scale = image_size / g.res;
+            footprint_px += std::min(g.res, ceil_div(GAN_TY, scale) + 2) * std::min(g.res, ceil_div(GAN_TX, scale) + 2);
+        }
+    }
+    tiled = tiled && footprint_px <= GAN_SRC_PIX;
     int gi = 0;
     for (auto& g : e->groups) {
         int koff = 0;
