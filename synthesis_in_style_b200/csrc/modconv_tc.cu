@@ -1509,40 +1509,40 @@ static int launch_tc_any(int BN, int th, int tw, int tb, const TcMaps& maps, con
 // Second half of an up-sampling layer: Blur(4x4, pad 1) + noise + bias + lrelu over the fp32 NHWC scratch.
 static int tc_blur_after_upconv(TcWorkspace& ws, const TcConvCall& call, cudaStream_t stream) {
     const int B = call.batch, H = call.res_in;
-        BlurSplitArgs bs;
-        bs.in = call.upconv_tmp; bs.IH = 2 * H + 1; bs.IW = 2 * H + 1;
-        bs.out_f32 = call.out_f32; bs.OH = call.res_out; bs.OW = call.res_out; bs.C = call.cout; bs.batch = B;
-        bs.blur_k = call.blur_k; bs.noise = call.noise; bs.noise_bstride = call.noise_bstride; bs.noise_w = call.noise_w; bs.bias = call.bias;
-        bs.s_next = call.s_next; bs.next_hi = (bf16*)ws.a_hi[call.out_slot]; bs.next_lo = (bf16*)ws.a_lo[call.out_slot];
-        bs.act = call.act ? 1 : 0;
-        SIS_REQUIRE(bs.C % 32 == 0, "tc_modconv: the blur pass needs Cout %% 32 == 0 (got %d)", bs.C);
-        static int ring_env = env_int("SIS_BLUR_TMA", 2);      // 0: cp.async, 1: TMA single buffer (3 blocks/SM), 2: TMA ring of 2
-        const int ring = (bs.C * 4) % 16 == 0 ? (ring_env < 0 ? 0 : ring_env > 2 ? 2 : ring_env) : 0;
-        const bool tma = ring > 0;
-        static int blocks_per_sm[6] = {0, 0, 0, 0, 0, 0};
-        const int sep = call.blur_separable ? 1 : 0;
-        const int variant = sep + 2 * ring;
-        const size_t smem = ring == 2 ? 2 * (size_t)BS_SMEM + 128 : ring == 1 ? (size_t)BS_SMEM + 128 : (size_t)BS_SMEM;
-        auto kern = ring == 2 ? (sep ? blur_act_split_kernel<true, 2> : blur_act_split_kernel<false, 2>)
-                  : ring == 1 ? (sep ? blur_act_split_kernel<true, 1> : blur_act_split_kernel<false, 1>)
-                              : (sep ? blur_act_split_kernel<true, 0> : blur_act_split_kernel<false, 0>);
-        if (!blocks_per_sm[variant]) {
-            SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            SIS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[variant], kern, 256, smem));
-            if (blocks_per_sm[variant] < 1) blocks_per_sm[variant] = 1;
-        }
-        CUtensorMap in_map;
-        memset(&in_map, 0, sizeof(in_map));
-        if (tma) {
-            const uint64_t dims[4] = {(uint64_t)bs.C, (uint64_t)bs.IW, (uint64_t)bs.IH, (uint64_t)B};
-            const uint32_t box[4] = {(uint32_t)BS_C, (uint32_t)BS_IW, (uint32_t)BS_IH, 1};
-            SIS_PROPAGATE(make_map_f32(&in_map, bs.in, 4, dims, box));
-        }
-        const int64_t total = (int64_t)B * ceil_div(bs.OH, BS_TH) * ceil_div(bs.OW, BS_TW) * ceil_div(bs.C, BS_C);
-        const int grid = (int)std::min<int64_t>(total, (int64_t)kNumSMs * blocks_per_sm[variant]);   // exactly one resident wave
-        ProfScope prof(PROF_BLUR_SPLIT, stream);
-        kern<<<grid, 256, smem, stream>>>(bs, in_map);
-        SIS_CHECK_LAUNCH();
+    BlurSplitArgs bs;
+    bs.in = call.upconv_tmp; bs.IH = 2 * H + 1; bs.IW = 2 * H + 1;
+    bs.out_f32 = call.out_f32; bs.OH = call.res_out; bs.OW = call.res_out; bs.C = call.cout; bs.batch = B;
+    bs.blur_k = call.blur_k; bs.noise = call.noise; bs.noise_bstride = call.noise_bstride; bs.noise_w = call.noise_w; bs.bias = call.bias;
+    bs.s_next = call.s_next; bs.next_hi = (bf16*)ws.a_hi[call.out_slot]; bs.next_lo = (bf16*)ws.a_lo[call.out_slot];
+    bs.act = call.act ? 1 : 0;
+    SIS_REQUIRE(bs.C % 32 == 0, "tc_modconv: the blur pass needs Cout %% 32 == 0 (got %d)", bs.C);
+    static int ring_env = env_int("SIS_BLUR_TMA", 2);      // 0: cp.async, 1: TMA single buffer (3 blocks/SM), 2: TMA ring of 2
+    const int ring = (bs.C * 4) % 16 == 0 ? (ring_env < 0 ? 0 : ring_env > 2 ? 2 : ring_env) : 0;
+    const bool tma = ring > 0;
+    static int blocks_per_sm[6] = {0, 0, 0, 0, 0, 0};
+    const int sep = call.blur_separable ? 1 : 0;
+    const int variant = sep + 2 * ring;
+    const size_t smem = ring == 2 ? 2 * (size_t)BS_SMEM + 128 : ring == 1 ? (size_t)BS_SMEM + 128 : (size_t)BS_SMEM;
+    auto kern = ring == 2 ? (sep ? blur_act_split_kernel<true, 2> : blur_act_split_kernel<false, 2>)
+              : ring == 1 ? (sep ? blur_act_split_kernel<true, 1> : blur_act_split_kernel<false, 1>)
+                          : (sep ? blur_act_split_kernel<true, 0> : blur_act_split_kernel<false, 0>);
+    if (!blocks_per_sm[variant]) {
+        SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SIS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[variant], kern, 256, smem));
+        if (blocks_per_sm[variant] < 1) blocks_per_sm[variant] = 1;
+    }
+    CUtensorMap in_map;
+    memset(&in_map, 0, sizeof(in_map));
+    if (tma) {
+        const uint64_t dims[4] = {(uint64_t)bs.C, (uint64_t)bs.IW, (uint64_t)bs.IH, (uint64_t)B};
+        const uint32_t box[4] = {(uint32_t)BS_C, (uint32_t)BS_IW, (uint32_t)BS_IH, 1};
+        SIS_PROPAGATE(make_map_f32(&in_map, bs.in, 4, dims, box));
+    }
+    const int64_t total = (int64_t)B * ceil_div(bs.OH, BS_TH) * ceil_div(bs.OW, BS_TW) * ceil_div(bs.C, BS_C);
+    const int grid = (int)std::min<int64_t>(total, (int64_t)kNumSMs * blocks_per_sm[variant]);   // exactly one resident wave
+    ProfScope prof(PROF_BLUR_SPLIT, stream);
+    kern<<<grid, 256, smem, stream>>>(bs, in_map);
+    SIS_CHECK_LAUNCH();
     return SIS_OK;
 }
 
