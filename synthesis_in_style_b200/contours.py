@@ -41,9 +41,8 @@ class Raster:
 
     def __init__(self, contour: Contour):
         self.contour = contour
-        pts = contour.reshape(-1, 2)
-        self.x0, self.y0 = int(pts[:, 0].min()), int(pts[:, 1].min())
-        self.x1, self.y1 = int(pts[:, 0].max()), int(pts[:, 1].max())
+        x, y, w, h = cv2.boundingRect(contour)          # = min / max of the points (segmentation_utils.py BBox of a contour)
+        self.x0, self.y0, self.x1, self.y1 = x, y, x + w - 1, y + h - 1
         self.mask = numpy.zeros((self.y1 - self.y0 + 1, self.x1 - self.x0 + 1), dtype=numpy.uint8)
         cv2.drawContours(self.mask, [contour - (self.x0, self.y0)], 0, 1, cv2.FILLED)
 
@@ -137,10 +136,20 @@ def merge_contours(contours: Sequence[Contour], only_keep_overlapping: bool = Fa
     n = len(contours)
     if n == 0:
         return []
-    rasters: List[Raster] = [cache.get(c) for c in contours]
+    # bounding boxes first (cheap); a contour is rasterised only when a pair it belongs to is actually tested, so the
+    # isolated specks that dominate fine-grained masks never are
     box = numpy.empty((2 * n, 4), dtype=numpy.int64)
-    for i, r in enumerate(rasters):
-        box[i] = (r.x0, r.y0, r.x1, r.y1)
+    for i, c in enumerate(contours):
+        x, y, w, h = cv2.boundingRect(c)
+        box[i] = (x, y, x + w - 1, y + h - 1)
+    rasters: List[Optional[Raster]] = [None] * n
+    shapes: List[Contour] = list(contours)
+
+    def raster(i: int) -> Raster:
+        if rasters[i] is None:
+            rasters[i] = cache.get(shapes[i])
+        return rasters[i]
+
     alive = [True] * n
     members = [1] * n
     b = box[:n]
@@ -151,11 +160,12 @@ def merge_contours(contours: Sequence[Contour], only_keep_overlapping: bool = Fa
         i, j = heapq.heappop(heap)
         if not (alive[i] and alive[j]):
             continue
-        if raster_overlap(rasters[i], rasters[j]) <= 0:
+        if raster_overlap(raster(i), raster(j)) <= 0:
             continue
-        merged = raster_union(rasters[i], rasters[j])
+        merged = raster_union(raster(i), raster(j))
         cache.put(merged)
-        k = len(rasters)
+        k = len(shapes)
+        shapes.append(merged.contour)
         rasters.append(merged)
         box[k] = (merged.x0, merged.y0, merged.x1, merged.y1)
         alive[i] = alive[j] = False
@@ -166,7 +176,7 @@ def merge_contours(contours: Sequence[Contour], only_keep_overlapping: bool = Fa
         for q in partners.tolist():
             if alive[q]:
                 heapq.heappush(heap, (q, k))
-    return [rasters[i].contour for i in range(len(rasters)) if alive[i] and (members[i] > 1 or not only_keep_overlapping)]
+    return [shapes[i] for i in range(len(shapes)) if alive[i] and (members[i] > 1 or not only_keep_overlapping)]
 
 
 # --------------------------------------------------------------------------- batch-level methods (reference names)
