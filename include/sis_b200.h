@@ -37,12 +37,18 @@ typedef enum { SIS_F32 = 0, SIS_F16 = 1, SIS_F64 = 2 } sis_dtype;
 
 SIS_API const char* sis_last_error(void);
 SIS_API int sis_version(void);
+/* Every device-side wait of the tcgen05 kernels is bounded (~2 s); a wait that gives up writes its code (0x100.. producer,
+ * 0x200.. MMA issuer, 0x300.. operand ring, 0x400.. epilogue, 0x500/0x600 halo ring) to a word of mapped host memory and
+ * traps.  The trap poisons the CUDA context (every later call fails with a sticky launch error); this word is still
+ * readable.  0 = no watchdog fired since load / the last clear. */
+SIS_API unsigned int sis_watchdog_code(void);
+SIS_API void sis_watchdog_clear(void);
 /* Number of kernel launches issued by this library on the calling process since load (all threads). */
 SIS_API uint64_t sis_launch_count(void);
 
 /* Optional timing of the library's own launches with CUDA events recorded on the launching stream, by kernel
  * category (0 mapping/modulation, 1 tcgen05 conv GEMM, 2 blur+act+split, 3 ToRGB, 4 fp32 conv, 5 labelling,
- * 6 fp32 blur+act, 7 other).  Used by bench.py for the roofline figures; off by default (no events recorded).
+ * 6 fp32 blur+act, 7 other, 8 tcgen05 conv GEMM of layers with Cout <= 64).  Used by bench.py for the roofline figures; off by default (no events recorded).
  * sis_profile_collect synchronises on the recorded events, sums per category and clears the log. */
 SIS_API int sis_profile_enable(int on);
 SIS_API int sis_profile_collect(double* ms_by_category, uint64_t* count_by_category, int n_categories);
@@ -141,6 +147,8 @@ typedef struct {
 } sis_forward_args;
 
 SIS_API int sis_generator_forward(sis_generator* g, const sis_forward_args* args, void* stream);
+/* Synchronises `stream` and reports a fired tcgen05 watchdog ("... watchdog fired: code 0x...") or the stream's error. */
+SIS_API int sis_generator_check(sis_generator* g, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Stand-alone layers — the reference's module-level forwards outside the fused plan (same kernels, one layer per call,

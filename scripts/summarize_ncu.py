@@ -73,7 +73,7 @@ def reps():
             if os.path.exists(os.path.join(G, f.replace('.ncu-rep', '.csv'))):
                 continue
             text = subprocess.run(['ncu', '-i', os.path.join(G, f), '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
-        elif f.startswith('prof_') and f.endswith(f'_{tag}.csv'):
+        elif f.startswith('prof_') and f.endswith(f'_{tag}.csv') and '_source_' not in f:
             text = open(os.path.join(G, f)).read()
         else:
             continue
@@ -103,5 +103,50 @@ def reps():
         print('\n'.join(out))
 
 
+def source_pages(top=30):
+    """`ncu --page source --csv` of a capture taken with --import-source on: line 1 names the kernel, line 2 is the
+    header, then one row per SASS instruction.  Keeps the `top` instructions by warp-stall samples with their opcode text,
+    share of all samples, executed count and dominant stall reason."""
+    for f in sorted(os.listdir(G)):
+        if not (f.startswith('prof_') and '_source_' in f and f.endswith(f'_{tag}.csv')):
+            continue
+        rows = list(csv.reader(open(os.path.join(G, f))))
+        if len(rows) < 3:
+            continue
+        kernel = rows[0][1] if len(rows[0]) > 1 else '?'
+        hdr = rows[1]
+        col = {h: i for i, h in enumerate(hdr)}
+        s_col = col.get('# Samples', col.get('Warp Stall Sampling (All Samples)'))
+        stall_cols = [(h, i) for h, i in col.items() if h.startswith('stall_') and '(Not Issued)' not in h]
+
+        def num(r, i):
+            try:
+                return float(r[i].replace(',', '')) if i is not None and i < len(r) and r[i] not in ('', '-') else 0.0
+            except ValueError:
+                return 0.0
+        body = [r for r in rows[2:] if len(r) > 2]
+        total = sum(num(r, s_col) for r in body) or 1.0
+        ranked = sorted(body, key=lambda r: -num(r, s_col))[:top]
+        out = [f'# ncu source page `{f}`', '', f'kernel: `{short(kernel)}`; {len(body)} SASS instructions, {int(total)} warp-stall samples; '
+               f'top {len(ranked)} instructions by samples (share of all samples, executions, dominant stall reason).', '',
+               '| # | address | SASS | samples | share | executed | top stall |', '|---:|---|---|---:|---:|---:|---|']
+        for n, r in enumerate(ranked, 1):
+            stalls = sorted(((num(r, i), h) for h, i in stall_cols), reverse=True)
+            top_stall = f'{stalls[0][1]} ({stalls[0][0]:.0f})' if stalls and stalls[0][0] > 0 else '-'
+            sass = re.sub(r'\s+', ' ', r[col['Source']]).strip()[:90]
+            out.append(f'| {n} | {r[col["Address"]][-6:]} | `{sass}` | {int(num(r, s_col))} | {100 * num(r, s_col) / total:.1f} % | '
+                       f'{int(num(r, col.get("Instructions Executed")))} | {top_stall} |')
+        by_op = {}
+        for r in body:
+            op = r[col['Source']].strip().split(' ')[0].lstrip('@!P0123456789 ') or r[col['Source']].strip().split(' ')[0]
+            toks = [t for t in r[col['Source']].strip().split(' ') if t and not t.startswith('@')]
+            op = toks[0].split('.')[0] if toks else '?'
+            by_op[op] = by_op.get(op, 0.0) + num(r, s_col)
+        out += ['', 'Samples by opcode: ' + ', '.join(f'`{k}` {100 * v / total:.1f} %' for k, v in sorted(by_op.items(), key=lambda kv: -kv[1])[:12])]
+        open(os.path.join(P, f.replace('.csv', '.md')), 'w').write('\n'.join(out) + '\n')
+        print('\n'.join(out[:12]))
+
+
 launches()
 reps()
+source_pages()

@@ -51,6 +51,8 @@ _SIGNATURES = {
     'sis_last_error': (c_char_p, []),
     'sis_version': (c_int, []),
     'sis_launch_count': (c_uint64, []),
+    'sis_watchdog_code': (c_uint32, []),
+    'sis_watchdog_clear': (None, []),
     'sis_profile_enable': (c_int, [c_int]),
     'sis_profile_collect': (c_int, [POINTER(ctypes.c_double), POINTER(c_uint64), c_int]),
     'sis_fused_bias_act': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int64, c_int64, c_int64, c_int, c_int,
@@ -66,6 +68,7 @@ _SIGNATURES = {
     'sis_generator_activation_shape': (c_int, [c_void_p, c_int, POINTER(c_int), POINTER(c_int)]),
     'sis_generator_style': (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     'sis_generator_forward': (c_int, [c_void_p, POINTER(ForwardArgs), c_void_p]),
+    'sis_generator_check': (c_int, [c_void_p, c_void_p]),
     'sis_modulated_conv2d': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_int,
                                      c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]),
     'sis_to_rgb': (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -114,10 +117,12 @@ def load():
 def check(status: int):
     if status != 0:
         msg = load().sis_last_error()
-        raise RuntimeError(f'libsis_b200: {msg.decode() if msg else "unknown error"} (status {status})')
+        wd = int(load().sis_watchdog_code())
+        tail = f'; tcgen05 watchdog fired earlier: code 0x{wd:x}' if wd else ''
+        raise RuntimeError(f'libsis_b200: {msg.decode() if msg else "unknown error"} (status {status}){tail}')
 
 
-PROFILE_CATEGORIES = ('mapping', 'conv_tc', 'blur_split', 'torgb', 'conv_simt', 'label', 'blur_simt', 'other')
+PROFILE_CATEGORIES = ('mapping', 'conv_tc', 'blur_split', 'torgb', 'conv_simt', 'label', 'blur_simt', 'other', 'conv_tc_narrow')
 
 
 def profile_enable(on: bool):

@@ -14,6 +14,22 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static unsigned int* g_watchdog = nullptr;
+unsigned int* watchdog_word() {
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        if (cudaHostAlloc(&p, sizeof(unsigned int), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess) {
+            g_watchdog = (unsigned int*)p;      // unified addressing: the same pointer is valid on every device
+            *g_watchdog = 0;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    return g_watchdog;
+}
+
 bool g_prof_on = false;
 struct ProfEvent { int cat; cudaEvent_t a, b; };
 static std::vector<ProfEvent> g_prof_events;
@@ -55,6 +71,14 @@ extern "C" int sis_profile_collect(double* ms_by_category, uint64_t* count_by_ca
     }
     g_prof_events.clear();
     return SIS_OK;
+}
+
+extern "C" unsigned int sis_watchdog_code(void) {
+    unsigned int* w = sis::g_watchdog;
+    return w ? *(volatile unsigned int*)w : 0u;
+}
+extern "C" void sis_watchdog_clear(void) {
+    if (sis::g_watchdog) *(volatile unsigned int*)sis::g_watchdog = 0u;
 }
 
 extern "C" const char* sis_last_error(void) { return sis::g_error; }

@@ -13,6 +13,10 @@ namespace sis {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<unsigned long long> g_launches;
+// One word of mapped, portable pinned host memory shared by every bounded device-side wait of the library: a watchdog
+// writes its code there before it traps, so the host can still read WHICH wait gave up after the trap has poisoned the
+// CUDA context (sis_watchdog_code).  Null when the allocation failed (the kernels then only trap).
+unsigned int* watchdog_word();
 inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 #define SIS_CHECK_CUDA(expr)                                                                      \
@@ -52,7 +56,7 @@ constexpr int kNumSMs = 148;
 
 // Optional per-kernel-category timing with CUDA events on the launching stream (bench.py's roofline leg).
 enum ProfCat { PROF_MAPPING = 0, PROF_CONV_TC = 1, PROF_BLUR_SPLIT = 2, PROF_TORGB = 3, PROF_CONV_SIMT = 4,
-               PROF_LABEL = 5, PROF_BLUR_SIMT = 6, PROF_OTHER = 7, PROF_NUM = 8 };
+               PROF_LABEL = 5, PROF_BLUR_SIMT = 6, PROF_OTHER = 7, PROF_CONV_TC_NARROW = 8, PROF_NUM = 9 };
 extern bool g_prof_on;
 void prof_begin(int cat, cudaStream_t stream);
 void prof_end(int cat, cudaStream_t stream);

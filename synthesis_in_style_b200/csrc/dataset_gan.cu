@@ -354,7 +354,7 @@ extern "C" void sis_pixel_ensemble_destroy(sis_pixel_ensemble* e) {
     if (!e) return;
     sis::free_groups(e);
     cudaFree(e->d_w1); cudaFree(e->d_b1); cudaFree(e->d_w2t); cudaFree(e->d_b2); cudaFree(e->d_w3); cudaFree(e->d_b3);
-    cudaFree(e->d_error); cudaFree(e->d_colors);
+    cudaFree(e->d_colors);
     delete e;
 }
 
@@ -424,10 +424,7 @@ extern "C" int sis_pixel_ensemble_prepare(sis_pixel_ensemble* e, void* stream_) 
     };
     SIS_PROPAGATE(upload(e->d_w1, w1)); SIS_PROPAGATE(upload(e->d_b1, b1)); SIS_PROPAGATE(upload(e->d_w2t, w2t));
     SIS_PROPAGATE(upload(e->d_b2, b2)); SIS_PROPAGATE(upload(e->d_w3, w3)); SIS_PROPAGATE(upload(e->d_b3, b3));
-    if (!e->d_error) {
-        SIS_CHECK_CUDA(cudaMalloc((void**)&e->d_error, sizeof(unsigned int)));
-        SIS_CHECK_CUDA(cudaMemsetAsync(e->d_error, 0, sizeof(unsigned int), stream));
-    }
+    if (!e->d_error) e->d_error = watchdog_word();
     SIS_CHECK_CUDA(cudaStreamSynchronize(stream));      // the host vectors go out of scope
     free_groups(e);
     e->prepared = true;
@@ -531,10 +528,9 @@ extern "C" int sis_pixel_ensemble_label(sis_pixel_ensemble* e, int n_layers, con
 extern "C" int sis_pixel_ensemble_check(sis_pixel_ensemble* e, void* stream_) {
     using namespace sis;
     SIS_REQUIRE(e, "sis_pixel_ensemble_check: null ensemble");
-    if (!e->d_error) return SIS_OK;
-    unsigned int h = 0;
-    SIS_CHECK_CUDA(cudaMemcpyAsync(&h, e->d_error, sizeof(h), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
-    SIS_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream_));
-    if (h) { set_error("tcgen05 conv watchdog fired: code 0x%x", h); return SIS_ERR_CUDA; }
+    const cudaError_t sync = cudaStreamSynchronize((cudaStream_t)stream_);
+    const unsigned int h = e->d_error ? *(volatile unsigned int*)e->d_error : 0u;
+    if (h) { set_error("tcgen05 conv watchdog fired: code 0x%x (%s)", h, cudaGetErrorString(sync)); return SIS_ERR_CUDA; }
+    if (sync != cudaSuccess) { set_error("cudaStreamSynchronize failed: %s", cudaGetErrorString(sync)); return SIS_ERR_CUDA; }
     return SIS_OK;
 }

@@ -344,6 +344,11 @@ static int run_label_jobs(const sis_forward_args* a, int idx, const float* act, 
     return SIS_OK;
 }
 
+extern "C" int sis_generator_check(sis_generator* g, void* stream_) {
+    SIS_REQUIRE(g != nullptr, "generator_check: null generator");
+    return tc_check_error(g->tc_ws, (cudaStream_t)stream_);
+}
+
 extern "C" int sis_generator_forward(sis_generator* g, const sis_forward_args* a, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SIS_REQUIRE(g && a, "generator_forward: null argument");

@@ -58,9 +58,13 @@ def build_latent_and_noise_generator(autoencoder, config: Dict, seed=1) -> Itera
 
 
 def generate_images(batch: Latents, autoencoder, device: str = 'cuda', mean_latent: Optional[torch.Tensor] = None,
-                    capture_layers=None, label_jobs=None) -> Tuple[Dict[int, torch.Tensor], torch.Tensor]:
+                    capture_layers=None, label_jobs=None, mix_inject_index: Optional[int] = None
+                    ) -> Tuple[Dict[int, torch.Tensor], torch.Tensor]:
     """(activations, image) exactly as utils/dataset_creation.py:40-58: truncation 0.7 iff mean_latent is given.
-    `capture_layers` / `label_jobs` are forwarded to the generator (extensions, see Generator.forward)."""
+    `capture_layers` / `label_jobs` are forwarded to the generator (extensions, see Generator.forward).
+    `mix_inject_index` (extension; the reference script never passes two styles, BASELINE config 4 asks for it): style
+    mixing through the generator's own two-style path (model.py:521-528) with an explicit crossover index; the second
+    style of sample i is the latent of sample i-1 of the same batch (no extra draw: the stream stays the reference's)."""
     if not isinstance(batch, Latents):
         raise NotImplementedError('the encoder path (dict batches) is outside the hot path (SURVEY.md §2 row 16)')
     latents = batch.to(device)
@@ -70,11 +74,20 @@ def generate_images(batch: Latents, autoencoder, device: str = 'cuda', mean_late
         kwargs['capture_layers'] = capture_layers
     if label_jobs is not None:
         kwargs['label_jobs'] = label_jobs
+    styles = [latents.latent]
+    if mix_inject_index is not None:
+        styles.append(mixing_partner(latents.latent))
+        kwargs['inject_index'] = int(mix_inject_index)
     with torch.no_grad():
         image, activations = decoder(
-            [latents.latent], input_is_latent=False, noise=latents.noise, return_intermediate_activations=True,
+            styles, input_is_latent=False, noise=latents.noise, return_intermediate_activations=True,
             truncation=0.7 if mean_latent is not None else 1, truncation_latent=mean_latent, **kwargs)
     return activations, image
+
+
+def mixing_partner(latent: torch.Tensor) -> torch.Tensor:
+    """Second style of the style-mixing extension: sample i is paired with sample i-1 of its batch."""
+    return torch.roll(latent, shifts=1, dims=0)
 
 
 # ------------------------------------------------------------------------------------------- sharding
@@ -83,16 +96,44 @@ def owned_batches(rank: int, world_size: int, num_batches: int) -> List[int]:
     return list(range(rank, num_batches, world_size))
 
 
-def sharded_latent_stream(generator: Generator, config: Dict, seed: int, rank: int, world_size: int) -> Iterator[Tuple[int, Latents]]:
-    """Replay of the reference's single stream: every rank draws every batch (CPU latents are positional; the
-    device Philox stream advances identically on every GPU) and yields only its own."""
-    stream = iter(build_latent_and_noise_generator(generator, config, seed=seed))
-    idx = 0
+def sharded_latent_stream(generator: Generator, config: Dict, seed: int, rank: int, world_size: int,
+                          replay: bool = False) -> Iterator[Tuple[int, Latents]]:
+    """This rank's batches (index b = rank mod world_size) of the reference's single (latent, noise) stream.
+
+    `replay=True` (and every CPU-device run): every rank draws every batch and yields only its own -- O(world_size) draws
+    per kept batch.  Default on CUDA: the streams are addressed by POSITION instead.  CPU latents: one
+    `randn(world_size * B, latent_size)` per round equals the concatenation of the reference's per-batch draws (the CPU
+    normal fill works on 16-element blocks; checked by `tests/test_host_logic.py`), and the rank keeps its rows.  Device
+    noise: the default CUDA generator is counter based (Philox), one `make_noise()` advances its offset by a constant
+    measured on the first batch, so batch b starts at offset0 + b * delta: `set_offset` jumps there and the rank draws
+    only its own maps.  Both give bit-identical batches to the replay (tests/test_pipeline_gpu.py)."""
+    device = generator.input.input.device
+    B, L = config['batch_size'], config['latent_size']
+    positional = (not replay) and world_size > 1 and device.type == 'cuda' and (B * L) % 16 == 0
+    if not positional:
+        stream = iter(build_latent_and_noise_generator(generator, config, seed=seed))
+        idx = 0
+        while True:
+            batch = next(stream)
+            if idx % world_size == rank:
+                yield idx, batch
+            idx += 1
+    torch.random.manual_seed(seed)
+    gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+    offset0 = gen.get_offset()
+    first_noise = generator.make_noise()
+    delta = gen.get_offset() - offset0
+    rnd = 0
     while True:
-        batch = next(stream)
-        if idx % world_size == rank:
-            yield idx, batch
-        idx += 1
+        z = torch.randn(world_size * B, L)
+        idx = rnd * world_size + rank
+        if idx == 0:
+            noise = first_noise
+        else:
+            gen.set_offset(offset0 + idx * delta)
+            noise = generator.make_noise()
+        yield idx, Latents(z[rank * B:(rank + 1) * B].clone(), noise)
+        rnd += 1
 
 
 @dataclass
@@ -101,6 +142,8 @@ class LabelledBatch:
     image: torch.Tensor                      # [B, 3, S, S] fp32, unclamped (what the reference hands to make_image)
     masks: Dict[str, Dict[str, torch.Tensor]]  # PredictedClusters at S x S (bool)
     activations: Dict[int, torch.Tensor]
+    ids: Optional[Dict[str, torch.Tensor]] = None      # {layer: uint8 [B, H, H]} cluster ids at native resolution
+    margins: Optional[Dict[str, torch.Tensor]] = None  # {layer: fp32 [B, H, H]} d2 - d1 (only with want_margin)
 
 
 @dataclass
@@ -109,6 +152,7 @@ class HostBatch:
     image: torch.Tensor                      # pinned host [B, 3, S, S] fp32, or uint8 [B, S, S, 3] (image_u8=True)
     masks: Dict[str, torch.Tensor]           # pinned host {layer: uint8 [n_class, B, S, S]}
     class_names: Dict[str, List[str]]        # {layer: class name of each mask plane}
+    ids: Optional[Dict[str, torch.Tensor]] = None   # pinned host {layer: uint8 [B, H, H]} cluster ids at native resolution
 
 
 @dataclass
@@ -130,7 +174,8 @@ class LabelledPairGenerator:
 
     def __init__(self, generator: Generator, segmenter: ClusterSegmenter, config: Dict, seed: int = 1,
                  mean_latent: Optional[torch.Tensor] = None, rank: int = 0, world_size: int = 1,
-                 capture_only_labelled: bool = False, fused_labelling: bool = True, in_flight: int = 1):
+                 capture_only_labelled: bool = False, fused_labelling: bool = True, in_flight: int = 1,
+                 want_margin: bool = False, mix_inject_index: Optional[int] = None):
         """`in_flight` > 1 keeps that many batches in flight on as many CUDA streams, each with its own generator
         workspace (a replica of `generator`: same weights, separate native plan).  Batches are independent, so the
         latency-bound head of one step (mapping network, 4^2..16^2 layers) overlaps the tensor-bound body of the other;
@@ -139,6 +184,9 @@ class LabelledPairGenerator:
         self.in_flight = max(1, int(in_flight))
         self._replicas, self._streams = None, None
         self.fused_labelling = fused_labelling
+        self.want_margin = want_margin      # fused jobs also write the nearest-centroid margin (parity checks)
+        self.mix_inject_index = mix_inject_index
+        self.replay_stream = False          # True: every rank replays every draw instead of addressing the streams by position
         self.config, self.seed, self.mean_latent = config, seed, mean_latent
         self.rank, self.world_size = rank, world_size
         # key 0 must always be present: the reference reads the batch size from activations[0]
@@ -177,7 +225,7 @@ class LabelledPairGenerator:
         device = self.generator.input.input.device
         lanes = self._lanes(device)
         pending = collections.deque()
-        stream = sharded_latent_stream(self.generator, self.config, self.seed, self.rank, self.world_size)
+        stream = sharded_latent_stream(self.generator, self.config, self.seed, self.rank, self.world_size, self.replay_stream)
         n = 0
         while True:
             g, st = lanes[n % len(lanes)]
@@ -185,14 +233,17 @@ class LabelledPairGenerator:
                 idx, latents = next(stream)          # the noise is drawn on this lane's stream, in the reference's order
                 if self.fused_labelling:
                     # labelling runs inside the generator's native call (one pass over each labelled activation)
-                    jobs = self.segmenter.make_label_jobs(g, latents.latent.shape[0])
+                    jobs = self.segmenter.make_label_jobs(g, latents.latent.shape[0], want_margin=self.want_margin)
                     acts, image = generate_images(latents, g, device=device, mean_latent=self.mean_latent,
-                                                  capture_layers=self.capture_layers, label_jobs=jobs)
+                                                  capture_layers=self.capture_layers, label_jobs=jobs,
+                                                  mix_inject_index=self.mix_inject_index)
                     masks = self.segmenter._as_predicted(self.segmenter.jobs_to_stacked(jobs))
+                    ids, margins = self.segmenter.jobs_to_ids(jobs), self.segmenter.jobs_to_margins(jobs)
                 else:
                     acts, image = generate_images(latents, g, device=device, mean_latent=self.mean_latent,
-                                                  capture_layers=self.capture_layers)
-                    masks = self.segmenter.prepare_image_segmentation(acts)
+                                                  capture_layers=self.capture_layers, mix_inject_index=self.mix_inject_index)
+                    ids, margins = {}, None
+                    masks = self.segmenter._as_predicted(self.segmenter.label_layers_stacked(acts, ids_out=ids))
                 masks = self.segmenter.merge_sub_images(masks)
                 done = None
                 if st is not None:
@@ -200,12 +251,13 @@ class LabelledPairGenerator:
                     done.record(st)
             self.stats['pairs'] += image.shape[0]
             self.stats['batches'] += 1
-            pending.append((LabelledBatch(idx, image, masks, acts), done))
+            pending.append((LabelledBatch(idx, image, masks, acts, ids, margins), done))
             n += 1
             if len(pending) >= len(lanes):
                 batch, done = pending.popleft()
                 if done is not None:
-                    self._hand_over([batch.image] + list(batch.activations.values())
+                    self._hand_over([batch.image] + list(batch.activations.values()) + list(batch.ids.values())
+                                    + list((batch.margins or {}).values())
                                     + [m for per_class in batch.masks.values() for m in per_class.values()], done, device)
                 yield batch
 
@@ -214,8 +266,6 @@ class LabelledPairGenerator:
         latents are staged in pinned memory and copied in, the fp32 image and the per-layer uint8 mask stacks are
         copied out to pinned memory on a side stream, with `depth` batches in flight so the copies overlap the next
         batch's kernels.  A yielded HostBatch stays valid until the next one is requested."""
-        if self.segmenter.keys_to_merge:
-            raise NotImplementedError('iter_host does not merge layers; use __iter__ for keys_to_merge configs')
         import contextlib
         device = self.generator.input.input.device
         g, seg = self.generator, self.segmenter
@@ -225,16 +275,16 @@ class LabelledPairGenerator:
         copy_stream = torch.cuda.Stream(device=device)
         slots = [{'z': torch.empty(B, self.config['latent_size']).pin_memory(),
                   'image': (torch.empty(B, S, S, 3, dtype=torch.uint8) if image_u8 else torch.empty(B, 3, S, S)).pin_memory(),
-                  'masks': {}} for _ in range(depth + 1)]
+                  'masks': {}, 'ids': {}} for _ in range(depth + 1)]
         in_flight = []
 
         def finish(slot):
             slot['done'].synchronize()
             slot['keep'] = None
-            return HostBatch(slot['index'], slot['image'], dict(slot['masks']), slot['names'])
+            return HostBatch(slot['index'], slot['image'], dict(slot['masks']), slot['names'], dict(slot['ids']))
 
         n = 0
-        latent_stream = sharded_latent_stream(g, self.config, self.seed, self.rank, self.world_size)
+        latent_stream = sharded_latent_stream(g, self.config, self.seed, self.rank, self.world_size, self.replay_stream)
         while True:
             slot = slots[n % (depth + 1)]
             g, st = lanes[n % len(lanes)]
@@ -245,11 +295,15 @@ class LabelledPairGenerator:
                 if self.fused_labelling:
                     jobs = seg.make_label_jobs(g, B)
                     acts, image = generate_images(lat, g, device=device, mean_latent=self.mean_latent, capture_layers=self.capture_layers,
-                                                  label_jobs=jobs)
-                    stacked = seg.jobs_to_stacked(jobs)
+                                                  label_jobs=jobs, mix_inject_index=self.mix_inject_index)
+                    stacked, ids = seg.jobs_to_stacked(jobs), seg.jobs_to_ids(jobs)
                 else:
-                    acts, image = generate_images(lat, g, device=device, mean_latent=self.mean_latent, capture_layers=self.capture_layers)
-                    stacked = seg.label_layers_stacked(acts)
+                    acts, image = generate_images(lat, g, device=device, mean_latent=self.mean_latent, capture_layers=self.capture_layers,
+                                                  mix_inject_index=self.mix_inject_index)
+                    ids = {}
+                    stacked = seg.label_layers_stacked(acts, ids_out=ids)
+                if seg.keys_to_merge:
+                    stacked = seg.merge_stacked(stacked)   # merged destination keys (black_white...segmenter.py:31-40)
                 if image_u8:
                     image = make_image(image)              # uint8 NHWC on the device: a quarter of the fp32 copy
                 ready = torch.cuda.Event()
@@ -261,10 +315,14 @@ class LabelledPairGenerator:
                     if layer not in slot['masks']:
                         slot['masks'][layer] = torch.empty(m.shape, dtype=torch.uint8).pin_memory()
                     slot['masks'][layer].copy_(m, non_blocking=True)
+                for layer, t in ids.items():
+                    if layer not in slot['ids']:
+                        slot['ids'][layer] = torch.empty(t.shape, dtype=torch.uint8).pin_memory()
+                    slot['ids'][layer].copy_(t, non_blocking=True)
                 slot['done'] = torch.cuda.Event()
                 slot['done'].record(copy_stream)
             # the device tensors must outlive the asynchronous copies
-            slot['keep'], slot['index'] = (image, stacked, lat), idx
+            slot['keep'], slot['index'] = (image, stacked, ids, lat), idx
             slot['names'] = {layer: names for layer, (names, _) in stacked.items()}
             in_flight.append(slot)
             self.stats['pairs'] += B

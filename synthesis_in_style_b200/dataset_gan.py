@@ -64,6 +64,7 @@ class PixelEnsembleClassifier:
             self.last_net_id += 1
         self._handle = None
         self._feature_size = None
+        self._built_from = None
 
     def get_networks(self):
         return self.networks
@@ -88,8 +89,19 @@ class PixelEnsembleClassifier:
         except Exception:
             pass
 
+    def _signature(self, feature_size: int):
+        """Identity of everything the native ensemble was built from: a replaced tensor (`load_state_dict` on a fresh
+        module, `set_network`) changes `data_ptr`, an in-place update (`load_state_dict`, an optimiser step, `copy_`) bumps
+        `_version`."""
+        sig = [feature_size, self.numpy_class]
+        for name, net in self.networks.items():
+            sd = net.state_dict()
+            sig.append((name, tuple((key, sd[key].data_ptr(), sd[key]._version, tuple(sd[key].shape)) for key in PARAM_KEYS)))
+        return tuple(sig)
+
     def _sync(self, feature_size: int, stream):
-        if self._handle is not None and self._feature_size == feature_size:
+        signature = self._signature(feature_size)
+        if self._handle is not None and self._built_from == signature:
             return
         self._release()
         lib = _lib.load()
@@ -104,7 +116,7 @@ class PixelEnsembleClassifier:
                 t = sd[key].detach().to('cpu', torch.float32).contiguous()
                 _lib.check(lib.sis_pixel_ensemble_set_param(handle, i, key.encode(), ctypes.c_void_p(t.data_ptr()), t.numel()))
         _lib.check(lib.sis_pixel_ensemble_prepare(handle, stream))
-        self._handle, self._feature_size = handle, feature_size
+        self._handle, self._feature_size, self._built_from = handle, feature_size, signature
 
     def predict_label_images(self, activations: Dict[int, torch.Tensor], image_size: int, colors: Optional[Sequence[Tuple[int, int, int]]] = None,
                              want_votes: bool = False):

@@ -121,7 +121,9 @@ class LabelJobSpec:
 def extract_centroids_from_pickle(path) -> Dict[str, numpy.ndarray]:
     """Read a reference catalog pickle (`catalogs/{k}.pkl`: {str(layer): FactorCatalog, 'id_to_size_map': ...},
     scf/create_semantic_segmentation.py:123-137) WITHOUT importing sklearn or the reference: every unknown class is
-    replaced by a plain attribute bag, and `_factorization.cluster_centers_` is pulled out."""
+    replaced by a plain attribute bag, and `_factorization.cluster_centers_` is pulled out.  Only an explicit whitelist of
+    constructors is resolved, so a crafted catalog cannot reach `builtins.eval` and friends (the reference's plain
+    `pickle.load` can); prefer the `.npz` catalog format where you control the files."""
 
     class _Bag:
         def __init__(self, *a, **k):
@@ -135,9 +137,20 @@ def extract_centroids_from_pickle(path) -> Dict[str, numpy.ndarray]:
                 if isinstance(state[0], dict):
                     self.__dict__.update(state[0])
 
+    # exact (module, name) pairs the container structure and numpy arrays need; everything else -- including the rest of
+    # `builtins` (eval, exec, getattr, __import__ ...) -- resolves to an inert attribute bag
+    allowed = {('collections', 'OrderedDict'), ('collections', 'defaultdict'), ('copyreg', '_reconstructor'), ('_codecs', 'encode'),
+               ('builtins', 'object'), ('builtins', 'dict'), ('builtins', 'list'), ('builtins', 'tuple'), ('builtins', 'set'),
+               ('builtins', 'frozenset'), ('builtins', 'bytearray'), ('builtins', 'complex'), ('builtins', 'slice'),
+               ('numpy', 'ndarray'), ('numpy', 'dtype'), ('numpy.core.multiarray', '_reconstruct'), ('numpy.core.multiarray', 'scalar'),
+               ('numpy._core.multiarray', '_reconstruct'), ('numpy._core.multiarray', 'scalar'),
+               ('numpy.core.numeric', '_frombuffer'), ('numpy._core.numeric', '_frombuffer'),
+               ('numpy.random._pickle', '__randomstate_ctor'), ('numpy.random._pickle', '__bit_generator_ctor'),
+               ('numpy.random._pickle', '__generator_ctor')}
+
     class _Unpickler(pickle.Unpickler):
         def find_class(self, module, name):
-            if module.split('.')[0] in ('numpy', 'builtins', 'collections', 'copyreg', '_codecs'):
+            if (module, name) in allowed:
                 return super().find_class(module, name)
             return type(name, (_Bag,), {})
 
@@ -297,7 +310,7 @@ class ClusterSegmenter(BaseDatasetSegmenter):
             self._bits_cache[key] = (names, torch.from_numpy(bits.view(numpy.int32)).to(device))
         return self._bits_cache[key]
 
-    def _label_layer(self, layer_id, act, class_label_map, image_size):
+    def _label_layer(self, layer_id, act, class_label_map, image_size, ids_out=None):
         cat = self.catalog[layer_id]
         names, bits = self._class_bits(layer_id, class_label_map, act.device)
         hist = self.cluster_pixel_counts.get(layer_id)
@@ -305,24 +318,29 @@ class ClusterSegmenter(BaseDatasetSegmenter):
             hist = torch.zeros(cat.k, dtype=torch.int64, device=act.device)
             self.cluster_pixel_counts[layer_id] = hist
         _, out = label_assign(act, cat.centroids_on(act.device), class_bits=bits, n_class=len(names),
-                              image_size=image_size, hist=hist)
+                              image_size=image_size, want_ids_u8=ids_out is not None, hist=hist)
+        if ids_out is not None:
+            ids_out[layer_id] = out['ids_u8']
         return names, out['masks']
 
-    def label_layers_stacked(self, activations, class_label_map=None, native: bool = False):
+    def label_layers_stacked(self, activations, class_label_map=None, native: bool = False, ids_out: Optional[Dict] = None):
         """{layer: (class names, uint8 [n_class, B, S, S])}: the kernel's own output layout, one tensor per layer
-        (what `LabelledPairGenerator.iter_host` copies to pinned memory in one transfer)."""
+        (what `LabelledPairGenerator.iter_host` copies to pinned memory in one transfer).  `ids_out` (a dict) receives
+        the uint8 [B, H, H] cluster-id map of every layer."""
         class_label_map = class_label_map if class_label_map is not None else self.class_label_map
         acts = {str(k): v for k, v in activations.items()}
         out = {}
         for layer_id in self.catalog:
             a = acts[layer_id]
             size = a.shape[-1] if (native or a.shape[-1] >= self.image_size) else self.image_size
-            out[layer_id] = self._label_layer(layer_id, a, class_label_map, size)
+            out[layer_id] = self._label_layer(layer_id, a, class_label_map, size, ids_out)
         return out
 
-    def make_label_jobs(self, generator, batch: int, class_label_map=None) -> List[LabelJobSpec]:
-        """Jobs for `Generator.forward(..., label_jobs=...)`: one per catalog layer, masks written at image size.
-        Read the results with `jobs_to_stacked(jobs)` / `_as_predicted(...)` after the forward."""
+    def make_label_jobs(self, generator, batch: int, class_label_map=None, want_margin: bool = False) -> List[LabelJobSpec]:
+        """Jobs for `Generator.forward(..., label_jobs=...)`: one per catalog layer; every job writes the cluster-id map at
+        the layer's native resolution (uint8 [B, H, H]: SURVEY.md §8(d) counts it as part of a labelled pair) and the class
+        masks at image size; `want_margin` adds the fp32 nearest-centroid margin d2 - d1 (parity checks).
+        Read the results with `jobs_to_stacked(jobs)` / `jobs_to_ids(jobs)` / `_as_predicted(...)` after the forward."""
         class_label_map = class_label_map if class_label_map is not None else self.class_label_map
         device = generator.input.input.device
         jobs = []
@@ -336,11 +354,20 @@ class ClusterSegmenter(BaseDatasetSegmenter):
                 hist = torch.zeros(cat.k, dtype=torch.int64, device=device)
                 self.cluster_pixel_counts[layer_id] = hist
             masks = torch.empty((len(names), batch, size, size), dtype=torch.uint8, device=device)
-            need_u8 = size % res != 0
-            ids8 = torch.empty((batch, res, res), dtype=torch.uint8, device=device) if need_u8 else None
+            ids8 = torch.empty((batch, res, res), dtype=torch.uint8, device=device)
+            margin = torch.empty((batch, res, res), dtype=torch.float32, device=device) if want_margin else None
             jobs.append(LabelJobSpec(int(layer_id), cat.centroids_on(device), bits, len(names), size, masks=masks, ids_u8=ids8,
-                                     hist=hist, names=names))
+                                     margin=margin, hist=hist, names=names))
         return jobs
+
+    @staticmethod
+    def jobs_to_ids(jobs: List[LabelJobSpec]) -> Dict[str, torch.Tensor]:
+        """{layer: uint8 [B, H, H] cluster ids at the layer's native resolution}."""
+        return {str(j.activation_idx): j.ids_u8 for j in jobs}
+
+    @staticmethod
+    def jobs_to_margins(jobs: List[LabelJobSpec]) -> Dict[str, torch.Tensor]:
+        return {str(j.activation_idx): j.margin for j in jobs if j.margin is not None}
 
     @staticmethod
     def jobs_to_stacked(jobs: List[LabelJobSpec]):
@@ -374,6 +401,30 @@ class ClusterSegmenter(BaseDatasetSegmenter):
             predicted_clusters[dst_key] = merged
         return predicted_clusters
 
+
+    def merge_stacked(self, stacked):
+        """`merge_sub_images` on the kernel's stacked layout: adds {dst_key: (class names, uint8 [n_class, B, S, S])} for
+        every `keys_to_merge` entry (class planes in `class_to_color_map` order, OR over the source layers)."""
+        lib = _lib.load()
+        for dst_key, keys in self.keys_to_merge.items():
+            names = list(self.class_to_color_map)
+            planes = []
+            for class_name in names:
+                acc = None
+                for k in keys:
+                    src_names, src = stacked[k]
+                    plane = src[src_names.index(class_name)] if class_name in src_names else None
+                    if plane is None:
+                        raise KeyError(class_name)
+                    if acc is None:
+                        acc = plane.contiguous().clone()
+                    else:
+                        plane = plane.contiguous()
+                        with torch.cuda.device(acc.device):
+                            _lib.check(lib.sis_or_u8(_lib.ptr(acc), _lib.ptr(plane), acc.numel(), _lib.current_stream_ptr(acc.device)))
+                planes.append(acc)
+            stacked[dst_key] = (names, torch.stack(planes, dim=0))
+        return stacked
 
     # -- host-side contour stage (contours.py; base_cluster_based…:148-450, black_white…:42-99) ------------------
     def contour_config(self):

@@ -376,6 +376,15 @@ class Generator(nn.Module):
         self._plan.signature = signature
         return dev
 
+    def check(self):
+        """Drain the current stream and raise if a bounded device-side wait of the tcgen05 kernels gave up
+        (`sis_generator_check`); tests and bench.py call it after a run."""
+        if self._plan.handle is None:
+            return
+        dev = self.input.input.device
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().sis_generator_check(self._handle, _lib.current_stream_ptr(dev)))
+
     def _style(self, z: torch.Tensor) -> torch.Tensor:
         _lib.require_cuda(z, 'input')
         dev = self._sync()

@@ -1,10 +1,15 @@
 """fused bias + leaky ReLU, host side.
 
-Mirrors scf/networks/stylegan2/op/fused_act.py: `fused_leaky_relu(input, bias, negative_slope=0.2, scale=2**0.5)`,
+Drop-in for scf/networks/stylegan2/op/fused_act.py: `fused_leaky_relu(input, bias, negative_slope=0.2, scale=2**0.5)`,
 `FusedLeakyReLU(channel, negative_slope=0.2, scale=2**0.5)` and the raw extension entry point
 `fused_bias_act(input, bias, refer, act, grad, alpha, scale)` (fused_bias_act.cpp:11-20), all running the sm_100a
-kernel in csrc/fused_bias_act.cu through the C-ABI.  Autograd (first and second order) follows the reference's
-two Function classes with the same kernel modes (act=3, grad=0/1).
+kernel in csrc/fused_bias_act.cu through the C-ABI.
+
+Autograd.  y = lrelu(x + b) * scale.  Its Jacobian w.r.t. x is diagonal: g -> g * gate(y) * scale with gate = 1 where
+y > 0 and `negative_slope` elsewhere -- the kernel's (act=3, grad=1) mode with `ref = y`.  A diagonal map is its own
+adjoint, so ONE Function (`_LeakyGate`) whose backward applies itself again serves every derivative order; the bias
+gradient is a plain `sum` that autograd differentiates by itself.  (The reference spells the same mathematics as a
+Function pair with a hand-written double-backward, fused_act.py:19-70.)
 """
 import torch
 from torch import nn
@@ -13,6 +18,7 @@ from torch.autograd import Function
 from .. import _lib
 
 _DTYPES = {torch.float32: _lib.SIS_F32, torch.float16: _lib.SIS_F16, torch.float64: _lib.SIS_F64}
+_ACT_LRELU, _MODE_VALUE, _MODE_GATE = 3, 0, 1
 
 
 def fused_bias_act(input: torch.Tensor, bias: torch.Tensor, refer: torch.Tensor, act: int, grad: int, alpha: float,
@@ -36,41 +42,41 @@ def fused_bias_act(input: torch.Tensor, bias: torch.Tensor, refer: torch.Tensor,
     return y
 
 
-class FusedLeakyReLUFunctionBackward(Function):
-    @staticmethod
-    def forward(ctx, grad_output, out, negative_slope, scale):
-        ctx.save_for_backward(out)
-        ctx.negative_slope, ctx.scale = negative_slope, scale
-        empty = grad_output.new_empty(0)
-        grad_input = fused_bias_act(grad_output, empty, out, 3, 1, negative_slope, scale)
-        dims = [0] + list(range(2, grad_input.ndim))
-        grad_bias = grad_input.sum(dims).detach()
-        return grad_input, grad_bias
+class _LeakyGate(Function):
+    """g -> g * gate(y) * scale.  Linear in g and self-adjoint, so `backward` is the Function itself."""
 
     @staticmethod
-    def backward(ctx, gradgrad_input, gradgrad_bias):
-        out, = ctx.saved_tensors
-        gradgrad_out = fused_bias_act(gradgrad_input, gradgrad_bias, out, 3, 1, ctx.negative_slope, ctx.scale)
-        return gradgrad_out, None, None, None
-
-
-class FusedLeakyReLUFunction(Function):
-    @staticmethod
-    def forward(ctx, input, bias, negative_slope, scale):
-        out = fused_bias_act(input, bias, input.new_empty(0), 3, 0, negative_slope, scale)
-        ctx.save_for_backward(out)
-        ctx.negative_slope, ctx.scale = negative_slope, scale
-        return out
+    def forward(ctx, g, y, slope, scale):
+        ctx.save_for_backward(y)
+        ctx.slope, ctx.scale = slope, scale
+        return fused_bias_act(g, g.new_empty(0), y, _ACT_LRELU, _MODE_GATE, slope, scale)
 
     @staticmethod
-    def backward(ctx, grad_output):
-        out, = ctx.saved_tensors
-        grad_input, grad_bias = FusedLeakyReLUFunctionBackward.apply(grad_output, out, ctx.negative_slope, ctx.scale)
-        return grad_input, grad_bias, None, None
+    def backward(ctx, gg):
+        y, = ctx.saved_tensors
+        return _LeakyGate.apply(gg, y, ctx.slope, ctx.scale), None, None, None
+
+
+class _BiasLeakyReLU(Function):
+    @staticmethod
+    def forward(ctx, x, bias, slope, scale):
+        y = fused_bias_act(x, bias, x.new_empty(0), _ACT_LRELU, _MODE_VALUE, slope, scale)
+        ctx.save_for_backward(y)
+        ctx.slope, ctx.scale, ctx.has_bias = slope, scale, bias.numel() > 0
+        return y
+
+    @staticmethod
+    def backward(ctx, g):
+        y, = ctx.saved_tensors
+        gx = _LeakyGate.apply(g, y, ctx.slope, ctx.scale)
+        gb = None
+        if ctx.has_bias and ctx.needs_input_grad[1]:
+            gb = gx.sum([d for d in range(gx.ndim) if d != 1])       # bias broadcasts over every dim but 1
+        return gx, gb, None, None
 
 
 def fused_leaky_relu(input, bias, negative_slope=0.2, scale=2 ** 0.5):
-    return FusedLeakyReLUFunction.apply(input, bias, negative_slope, scale)
+    return _BiasLeakyReLU.apply(input, bias, negative_slope, scale)
 
 
 class FusedLeakyReLU(nn.Module):

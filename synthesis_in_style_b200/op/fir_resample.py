@@ -1,10 +1,17 @@
 """upfirdn2d, host side.
 
-Mirrors scf/networks/stylegan2/op/upfirdn2d.py: `upfirdn2d(input[B,C,H,W], kernel[kh,kw], up=1, down=1, pad=(0,0))`
+Drop-in for scf/networks/stylegan2/op/upfirdn2d.py: `upfirdn2d(input[B,C,H,W], kernel[kh,kw], up=1, down=1, pad=(0,0))`
 and the raw extension entry point `upfirdn2d_op(input[major,H,W,minor], kernel, up_x, up_y, down_x, down_y,
 pad_x0, pad_x1, pad_y0, pad_y1)` (upfirdn2d.cpp:12-23), both running csrc/upfirdn2d.cu through the C-ABI.
-The gradient is the same op with the flipped kernel and swapped up/down (upfirdn2d.py:18-84).
+
+Autograd.  For fixed taps the op is a linear map; its adjoint is the same op with the taps flipped, up and down swapped
+and the pads mirrored (`_FirGeometry.adjoint`), and the adjoint of the adjoint is the original map.  ONE Function
+(`_FirResample`) whose backward applies itself with the adjoint geometry therefore serves every derivative order.  (The
+reference writes this as a Function pair with explicit gradient pads, upfirdn2d.py:18-84; the pad formulas agree.)
+As in the reference the taps receive no gradient.
 """
+from typing import NamedTuple, Tuple
+
 import torch
 from torch.autograd import Function
 
@@ -38,56 +45,45 @@ def upfirdn2d_op(input: torch.Tensor, kernel: torch.Tensor, up_x: int, up_y: int
     return out
 
 
-class UpFirDn2dBackward(Function):
-    @staticmethod
-    def forward(ctx, grad_output, kernel, grad_kernel, up, down, pad, g_pad, in_size, out_size):
-        up_x, up_y = up
-        down_x, down_y = down
-        g_pad_x0, g_pad_x1, g_pad_y0, g_pad_y1 = g_pad
-        grad_output = grad_output.reshape(-1, out_size[0], out_size[1], 1)
-        grad_input = upfirdn2d_op(grad_output, grad_kernel, down_x, down_y, up_x, up_y, g_pad_x0, g_pad_x1, g_pad_y0,
-                                  g_pad_y1)
-        grad_input = grad_input.view(in_size[0], in_size[1], in_size[2], in_size[3])
-        ctx.save_for_backward(kernel)
-        ctx.up, ctx.down, ctx.pad = up, down, pad
-        ctx.in_size, ctx.out_size = in_size, out_size
-        return grad_input
+class _FirGeometry(NamedTuple):
+    """Resampling geometry of one application on [B, C, H, W] planes: (x, y) factors, (x0, x1, y0, y1) pads, plane sizes."""
+    up: Tuple[int, int]
+    down: Tuple[int, int]
+    pad: Tuple[int, int, int, int]
+    taps: Tuple[int, int]          # (kh, kw)
+    src: Tuple[int, int]           # (H, W) of the input planes
+    dst: Tuple[int, int]           # (H, W) of the output planes
 
-    @staticmethod
-    def backward(ctx, gradgrad_input):
-        kernel, = ctx.saved_tensors
-        gradgrad_input = gradgrad_input.reshape(-1, ctx.in_size[2], ctx.in_size[3], 1)
-        out = upfirdn2d_op(gradgrad_input, kernel, ctx.up[0], ctx.up[1], ctx.down[0], ctx.down[1], *ctx.pad)
-        out = out.view(ctx.in_size[0], ctx.in_size[1], ctx.out_size[0], ctx.out_size[1])
-        return out, None, None, None, None, None, None, None, None
+    def adjoint(self) -> '_FirGeometry':
+        """Geometry of the transposed map (dst-sized planes -> src-sized planes) for the flipped taps."""
+        (ux, uy), (dx, dy), (px0, _, py0, _) = self.up, self.down, self.pad
+        kh, kw = self.taps
+        (h, w), (oh, ow) = self.src, self.dst
+        pad = (kw - px0 - 1, w * ux - ow * dx + px0 - ux + 1, kh - py0 - 1, h * uy - oh * dy + py0 - uy + 1)
+        return _FirGeometry(self.down, self.up, pad, self.taps, self.dst, self.src)
 
 
-class UpFirDn2d(Function):
+class _FirResample(Function):
     @staticmethod
-    def forward(ctx, input, kernel, up, down, pad):
-        up_x, up_y = up
-        down_x, down_y = down
-        pad_x0, pad_x1, pad_y0, pad_y1 = pad
-        kernel_h, kernel_w = kernel.shape
-        batch, channel, in_h, in_w = input.shape
-        ctx.in_size = input.shape
-        out = upfirdn2d_op(input.reshape(-1, in_h, in_w, 1), kernel, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0,
-                           pad_y1)
-        out_h, out_w = out.shape[1], out.shape[2]
-        ctx.save_for_backward(kernel, torch.flip(kernel, [0, 1]))
-        ctx.out_size = (out_h, out_w)
-        ctx.up, ctx.down, ctx.pad = (up_x, up_y), (down_x, down_y), (pad_x0, pad_x1, pad_y0, pad_y1)
-        ctx.g_pad = (kernel_w - pad_x0 - 1, in_w * up_x - out_w * down_x + pad_x0 - up_x + 1,
-                     kernel_h - pad_y0 - 1, in_h * up_y - out_h * down_y + pad_y0 - up_y + 1)
-        return out.view(-1, channel, out_h, out_w)
+    def forward(ctx, planes, taps, geo: _FirGeometry):
+        lead = planes.shape[:-2]
+        out = upfirdn2d_op(planes.reshape(-1, geo.src[0], geo.src[1], 1), taps, geo.up[0], geo.up[1], geo.down[0], geo.down[1],
+                           *geo.pad)
+        assert tuple(out.shape[1:3]) == tuple(geo.dst), (out.shape, geo)
+        ctx.save_for_backward(taps)
+        ctx.geo = geo
+        return out.reshape(*lead, geo.dst[0], geo.dst[1])
 
     @staticmethod
-    def backward(ctx, grad_output):
-        kernel, grad_kernel = ctx.saved_tensors
-        grad_input = UpFirDn2dBackward.apply(grad_output, kernel, grad_kernel, ctx.up, ctx.down, ctx.pad, ctx.g_pad,
-                                             ctx.in_size, ctx.out_size)
-        return grad_input, None, None, None, None
+    def backward(ctx, g):
+        taps, = ctx.saved_tensors
+        return _FirResample.apply(g, torch.flip(taps, [0, 1]), ctx.geo.adjoint()), None, None
 
 
 def upfirdn2d(input, kernel, up=1, down=1, pad=(0, 0)):
-    return UpFirDn2d.apply(input, kernel, (up, up), (down, down), (pad[0], pad[1], pad[0], pad[1]))
+    lib = _lib.load()
+    kh, kw = kernel.shape
+    h, w = input.shape[-2:]
+    dst = (lib.sis_upfirdn2d_out_size(h, up, down, pad[0], pad[1], kh), lib.sis_upfirdn2d_out_size(w, up, down, pad[0], pad[1], kw))
+    geo = _FirGeometry((up, up), (down, down), (pad[0], pad[1], pad[0], pad[1]), (kh, kw), (h, w), dst)
+    return _FirResample.apply(input, kernel, geo)

@@ -116,3 +116,31 @@ def test_checkpoint_loading_and_errors(cuda_device, tmp_path):
         seg.ensemble.predict_label_images({0: torch.randn(2, 32, 4, 4, device=cuda_device)}, 16)
     with pytest.raises(RuntimeError):                      # host tensors are refused: no CPU fallback
         seg.ensemble.predict_label_images({0: torch.randn(2, 64, 4, 4)}, 16)
+
+
+def test_weight_updates_between_predicts_are_seen(cuda_device):
+    """The native ensemble is rebuilt when a network's tensors change in place or are replaced (load_state_dict, copy_):
+    labels after an update equal those of a fresh ensemble with the new weights, not the stale ones."""
+    size, n_class = 32, 3
+    spec = so.GeneratorSpec(size, 512, 8, 2)
+    sd = so.perturb_zero_params(so.init_state_dict(spec, seed=0), seed=1234)
+    g = Generator(size, 512, 8)
+    g.load_state_dict(sd)
+    g = g.to(cuda_device).eval()
+    torch.manual_seed(3)
+    with torch.no_grad():
+        _, acts = g([torch.randn(2, 512, device=cuda_device)], return_intermediate_activations=True)
+    feat = sum(t.shape[1] for t in acts.values())
+    old_states = [dg.init_classifier_state(feat, n_class, seed=60 + i, base_seed=59) for i in range(2)]
+    new_states = [dg.init_classifier_state(feat, n_class, seed=70 + i, base_seed=69) for i in range(2)]
+    ens = build_ensemble(old_states, n_class, feat)
+    before = ens.predict_label_images(acts, size)[0].clone()
+    nets = list(ens.get_networks().values())
+    nets[0].load_state_dict(new_states[0])                       # in-place copy into the existing tensors
+    with torch.no_grad():
+        for k, v in new_states[1].items():
+            nets[1].state_dict()[k].copy_(v)                     # raw in-place update
+    after = ens.predict_label_images(acts, size)[0]
+    fresh = build_ensemble(new_states, n_class, feat).predict_label_images(acts, size)[0]
+    assert torch.equal(after, fresh)
+    assert not torch.equal(after, before)

@@ -117,3 +117,23 @@ def test_upfirdn2d_autograd(cuda_device):
     yr = so.upfirdn2d(xr, k.cpu(), up=2, down=1, pad=(2, 1))
     yr.square().sum().backward()
     torch.testing.assert_close(x.grad.cpu(), xr.grad, rtol=1e-4, atol=1e-4)
+
+
+def test_ops_first_and_second_order_gradients_fp64(cuda_device):
+    """Both drop-in ops are differentiable to any order through one self-adjoint Function each: finite-difference
+    checks of the first and second derivatives in float64 (the kernels dispatch on dtype like the reference's)."""
+    from torch.autograd import gradcheck, gradgradcheck
+    torch.manual_seed(0)
+    x = torch.randn(2, 3, 5, 5, device=cuda_device, dtype=torch.float64)
+    x = (x + 0.3 * x.sign()).requires_grad_(True)          # keep away from the kink at 0
+    b = torch.randn(3, device=cuda_device, dtype=torch.float64, requires_grad=True)
+    with torch.no_grad():
+        shifted = x + b.view(1, -1, 1, 1)
+        x.sub_(torch.where(shifted.abs() < 0.1, shifted, torch.zeros_like(shifted)) * 2)
+    assert gradcheck(lambda a, c: fused_leaky_relu(a, c), (x, b), eps=1e-6, atol=1e-6)
+    assert gradgradcheck(lambda a, c: fused_leaky_relu(a, c) ** 2, (x, b), eps=1e-6, atol=1e-5)
+    k = (so.make_kernel([1, 3, 3, 1]) * 4).to(cuda_device, torch.float64)
+    for up, down, pad in ((2, 1, (2, 1)), (1, 2, (1, 1)), (1, 1, (1, 1)), (2, 3, (0, 2))):
+        xi = torch.randn(1, 2, 7, 6, device=cuda_device, dtype=torch.float64, requires_grad=True)
+        assert gradcheck(lambda a: upfirdn2d(a, k, up=up, down=down, pad=pad), (xi,), eps=1e-6, atol=1e-6), (up, down, pad)
+        assert gradgradcheck(lambda a: upfirdn2d(a, k, up=up, down=down, pad=pad) ** 2, (xi,), eps=1e-6, atol=1e-5), (up, down, pad)

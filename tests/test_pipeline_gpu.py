@@ -50,7 +50,8 @@ def test_pipeline_matches_oracle_on_same_seeds(cuda_device, precision):
     total = agree = 0
     for layer in layers:
         ids_want, margin = lo.predict_with_margin(want_acts[int(layer)], cents[layer])
-        ids_got = seg.catalog[layer].predict(got.activations[int(layer)]).cpu()
+        ids_got = got.ids[layer].cpu().long()           # the in-forward label job's own id map (the timed kernels)
+        assert torch.equal(seg.catalog[layer].predict(got.activations[int(layer)]).cpu()[margin > 1e-3], ids_want[margin > 1e-3])
         safe = margin > 1e-3
         assert torch.equal(ids_got[safe], ids_want[safe]), (layer, int((ids_got[safe] != ids_want[safe]).sum()))
         total += ids_want.numel(); agree += int((ids_got == ids_want).sum())
@@ -61,25 +62,40 @@ def test_pipeline_matches_oracle_on_same_seeds(cuda_device, precision):
     assert agree / total >= 0.999
 
 
-def test_sharded_run_equals_single_stream(cuda_device):
+@pytest.mark.parametrize('replay', [False, True])
+def test_sharded_run_equals_single_stream(cuda_device, replay):
+    """Rank shards reproduce the single-process stream bit for bit: by replaying every draw (`replay=True`) and by
+    addressing the streams positionally (default on CUDA: Philox offset jumps for the device noise, one positional CPU
+    draw per round for the latents)."""
     layers = ['4', '5', '6', '7']
     spec, sd, g, seg, cents = make_setup(32, layers, cuda_device)
     cfg = {'batch_size': 3, 'latent_size': 512}
     single = []
-    for i, b in zip(range(4), dc.LabelledPairGenerator(g, seg, cfg, seed=1)):
+    for i, b in zip(range(6), dc.LabelledPairGenerator(g, seg, cfg, seed=1)):
         single.append(b)
+    it0 = dc.sharded_latent_stream(g, cfg, 1, 1, 3, replay=replay)
+    idx, lat = next(it0)
+    idx2, lat2 = next(it0)
+    ref = list(zip(range(5), dc.build_latent_and_noise_generator(g, cfg, seed=1)))
+    assert (idx, idx2) == (1, 4)
+    for got, want in ((lat, ref[1][1]), (lat2, ref[4][1])):
+        assert torch.equal(got.latent, want.latent)
+        assert all(torch.equal(a, b) for a, b in zip(got.noise, want.noise))
     for rank in range(2):
         pipe = dc.LabelledPairGenerator(g, seg, cfg, seed=1, rank=rank, world_size=2, capture_only_labelled=True)
-        for i, b in zip(range(2), pipe):
-            ref = single[b.batch_index]
+        if replay:
+            pipe.replay_stream = True
+        for i, b in zip(range(3), pipe):
+            ref_b = single[b.batch_index]
             assert b.batch_index % 2 == rank
-            assert torch.equal(b.image, ref.image)
+            assert torch.equal(b.image, ref_b.image)
             assert sorted(b.activations) == [0, 4, 5, 6, 7]
             for layer in layers:
+                assert torch.equal(b.ids[layer], ref_b.ids[layer])
                 for cn in NAMES:
-                    assert torch.equal(b.masks[layer][cn], ref.masks[layer][cn])
+                    assert torch.equal(b.masks[layer][cn], ref_b.masks[layer][cn])
         vec = pipe.stats_vector()
-        assert int(vec[-2]) == 6 and int(vec[-1]) == 2
+        assert int(vec[-2]) == 9 and int(vec[-1]) == 3
 
 
 def test_full_size_properties(cuda_device):
