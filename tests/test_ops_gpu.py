@@ -135,5 +135,8 @@ def test_ops_first_and_second_order_gradients_fp64(cuda_device):
     k = (so.make_kernel([1, 3, 3, 1]) * 4).to(cuda_device, torch.float64)
     for up, down, pad in ((2, 1, (2, 1)), (1, 2, (1, 1)), (1, 1, (1, 1)), (2, 3, (0, 2))):
         xi = torch.randn(1, 2, 7, 6, device=cuda_device, dtype=torch.float64, requires_grad=True)
-        assert gradcheck(lambda a: upfirdn2d(a, k, up=up, down=down, pad=pad), (xi,), eps=1e-6, atol=1e-6), (up, down, pad)
-        assert gradgradcheck(lambda a: upfirdn2d(a, k, up=up, down=down, pad=pad) ** 2, (xi,), eps=1e-6, atol=1e-5), (up, down, pad)
+        # like the reference's kernel (upfirdn2d_kernel.cu:56-57 stages input and taps in `float` shared memory) the fp64
+        # path has fp32 products: the op is linear (its square quadratic), so central differences are exact for any step
+        # and a large step keeps the fp32 rounding out of the quotient
+        assert gradcheck(lambda a: upfirdn2d(a, k, up=up, down=down, pad=pad), (xi,), eps=1e-1, atol=1e-4, rtol=1e-3), (up, down, pad)
+        assert gradgradcheck(lambda a: upfirdn2d(a, k, up=up, down=down, pad=pad) ** 2, (xi,), eps=1e-1, atol=1e-3, rtol=1e-3), (up, down, pad)
