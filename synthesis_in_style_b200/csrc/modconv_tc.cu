@@ -36,8 +36,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+// Every single-lane operation of the warp-specialised roles takes a lane predicate `pred` and predicates the instruction
+// INSIDE the asm block.  The producer / MMA loops are executed by the WHOLE warp with warp-uniform control flow and
+// operands; only the instruction itself is issued by one lane.  (Wrapping the loop in `if (lane == 0)` makes every
+// descriptor a per-thread value: the compiler then emits an ELECT + 5 x R2UR.BROADCAST + BRA.U.ANY "waterfall" around
+// every UTCHMMA / UTMALDG, ~95 clk per MMA whatever its shape -- measured: N = 64 layers at 32 % tensor-active, N = 32 at
+// 17 %, N = 128 at 63 %.)
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes, uint32_t pred = 1u) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
+                 ::"r"(smem_u32(bar)), "r"(bytes), "r"(pred) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -64,15 +71,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
     }
 }
 
-__device__ __forceinline__ void tma_load_4d(const void* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+__device__ __forceinline__ void tma_load_4d(const void* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, uint32_t pred = 1u) {
     asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+        "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(pred) : "memory");
 }
-__device__ __forceinline__ void tma_load_3d(const void* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_3d(const void* map, uint64_t* bar, void* dst, int c0, int c1, int c2, uint32_t pred = 1u) {
     asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+        "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+        "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(pred) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const void* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
@@ -81,15 +90,18 @@ __device__ __forceinline__ void tma_prefetch_desc(const void* map) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                          uint32_t pred = 1u) {
     asm volatile(
-        "{\n\t.reg .pred p;\n\t"
+        "{\n\t.reg .pred p, q;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(pred) : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+__device__ __forceinline__ void umma_commit(uint64_t* bar, uint32_t pred = 1u) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+                 "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)), "r"(pred) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -123,6 +135,7 @@ struct TcSubProblem {
     int ntaps;
     short dy[9], dx[9];         // tap offsets (may carry a sub-problem origin: border strips of the transposed conv)
     signed char widx[9];
+    signed char phase[9];       // 4-phase halo mode (transposed conv, Cout <= 64): output phase py*2+px of every tap
     int oh, ow;                 // extent of this sub-problem's output grid
     int ostride, ooff_y, ooff_x;
     int tiles_y, tiles_x;       // tiled A mode: spatial tiles of the box
@@ -244,67 +257,76 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-pair bit of a shared::cluster address -> even CTA
 
 template <int CG>
-__device__ __forceinline__ void tma_load_4d_cg(const void* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+__device__ __forceinline__ void tma_load_4d_cg(const void* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3, uint32_t pred = 1u) {
     if (CG == 1) {
-        tma_load_4d(map, bar, dst, c0, c1, c2, c3);
+        tma_load_4d(map, bar, dst, c0, c1, c2, c3, pred);
     } else {
         asm volatile(
-            "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-            ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+            "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+            "@q cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n\t}"
+            ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(pred) : "memory");
     }
 }
 // TMA im2col mode: 128 consecutive pixels (W fastest, then H, then N) of the traversal box starting at the base pixel
 // (c1, c2, c3), each shifted by the filter offset (off_w, off_h); pixels outside the tensor are zero-filled.
 template <int CG>
 __device__ __forceinline__ void tma_load_im2col_cg(const void* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3,
-                                                   unsigned short off_w, unsigned short off_h) {
+                                                   unsigned short off_w, unsigned short off_h, uint32_t pred = 1u) {
     if (CG == 1) {
         asm volatile(
-            "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
-            ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(off_w), "h"(off_h) : "memory");
+            "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %9, 0;\n\t"
+            "@q cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};\n\t}"
+            ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(off_w), "h"(off_h), "r"(pred) : "memory");
     } else {
         asm volatile(
-            "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
-            ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(off_w), "h"(off_h) : "memory");
+            "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %9, 0;\n\t"
+            "@q cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};\n\t}"
+            ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(off_w), "h"(off_h), "r"(pred) : "memory");
     }
 }
 template <int CG>
-__device__ __forceinline__ void tma_load_3d_cg(const void* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+__device__ __forceinline__ void tma_load_3d_cg(const void* map, uint64_t* bar, void* dst, int c0, int c1, int c2, uint32_t pred = 1u) {
     if (CG == 1) {
-        tma_load_3d(map, bar, dst, c0, c1, c2);
+        tma_load_3d(map, bar, dst, c0, c1, c2, pred);
     } else {
         asm volatile(
-            "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-            ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2) : "memory");
+            "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+            "@q cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n\t}"
+            ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2), "r"(pred) : "memory");
     }
 }
 template <int CG>
-__device__ __forceinline__ void umma_bf16_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+__device__ __forceinline__ void umma_bf16_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate,
+                                             uint32_t pred = 1u) {
     if (CG == 1) {
-        umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);
+        umma_bf16(tmem_d, adesc, bdesc, idesc, accumulate, pred);
     } else {
         asm volatile(
-            "{\n\t.reg .pred p;\n\t"
+            "{\n\t.reg .pred p, q;\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+            "setp.ne.b32 q, %5, 0;\n\t"
+            "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(pred) : "memory");
     }
 }
 // tcgen05.commit: arrive on `bar` when all previously issued MMAs retire; CG = 2 arrives on the barrier at the same
 // offset in BOTH CTAs of the pair.
 template <int CG>
-__device__ __forceinline__ void umma_commit_cg(uint64_t* bar) {
+__device__ __forceinline__ void umma_commit_cg(uint64_t* bar, uint32_t pred = 1u) {
     if (CG == 1) {
-        umma_commit(bar);
+        umma_commit(bar, pred);
     } else {
-        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                     ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+        asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t"
+                     "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}"
+                     ::"r"(smem_u32(bar)), "h"((uint16_t)3), "r"(pred) : "memory");
     }
 }
 
 // Epilogue warps (2..9): TMEM accumulator -> demodulate [-> noise + bias + lrelu] -> fp32 capture (+ the next conv's
 // pre-scaled bf16 hi/lo planes), shared by the per-tap and the halo kernels.
-template <int BN, int TH, int TW, int TB, int CG>
+// UP4: the accumulator holds the FOUR output phases of a transposed conv side by side (4 x BN columns; phase p of pixel
+// (yy, xx) goes to scratch position (2yy + py, 2xx + px); the py = 1 / px = 1 phases are one row / column shorter).
+template <int BN, int TH, int TW, int TB, int CG, bool UP4 = false>
 __device__ __forceinline__ void tc_epilogue(const TcKernelArgs& a, uint64_t* tfull_bar, uint64_t* tempty_bar, uint32_t tmem_base,
                                             int rank, int warp, int lane, int unit0, int unit_stride) {
         // ============================== epilogue (warps 2..9) ==============================
@@ -325,25 +347,30 @@ __device__ __forceinline__ void tc_epilogue(const TcKernelArgs& a, uint64_t* tfu
             } else {
                 b = c.b0 + tb; yy = c.y0 + th; xx = c.x0 + tw;
             }
-            const bool valid = !c.dummy && b < a.batch && yy < s.oh && xx < s.ow;
-            const int oy = yy * s.ostride + s.ooff_y, ox = xx * s.ostride + s.ooff_x;
+            const bool valid0 = !c.dummy && b < a.batch && yy < s.oh && xx < s.ow;
+            const int oy0 = yy * s.ostride + s.ooff_y, ox0 = xx * s.ostride + s.ooff_x;
             mbar_wait(&tfull_bar[acc], acc_phase, a.error, 0x400 + acc);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-            const float* dm = a.demod + (int64_t)(valid ? b : 0) * a.cout + c.n0;
+            constexpr int ACC_COLS = (UP4 ? 4 : 1) * BN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS);
+            const float* dm = a.demod + (int64_t)(valid0 ? b : 0) * a.cout + c.n0;
             float nz = 0.0f;
-            if (a.mode == 0 && valid && a.noise) nz = __fmul_rn(a.noise_w, a.noise[(int64_t)b * a.noise_bstride + (int64_t)oy * a.out_w + ox]);
+            if (!UP4 && a.mode == 0 && valid0 && a.noise) nz = __fmul_rn(a.noise_w, a.noise[(int64_t)b * a.noise_bstride + (int64_t)oy0 * a.out_w + ox0]);
             const int cstep = (blockDim.x / 32 - 2) * 8;      // 4 epilogue warps: 32, 8: 64
 #pragma unroll 1
-            for (int c0 = chalf * 32; c0 < BN; c0 += cstep) {
+            for (int call = chalf * 32; call < ACC_COLS; call += cstep) {
+                const int ph = UP4 ? call / BN : 0;
+                const int c0 = UP4 ? call - ph * BN : call;
+                const bool valid = UP4 ? (valid0 && yy < s.oh - (ph >> 1) && xx < s.ow - (ph & 1)) : valid0;
+                const int oy = UP4 ? oy0 + (ph >> 1) : oy0, ox = UP4 ? ox0 + (ph & 1) : ox0;
                 uint32_t r[32];
-                tmem_ld_32x32(taddr + (uint32_t)c0, r);
+                tmem_ld_32x32(taddr + (uint32_t)call, r);
                 tmem_ld_wait();
                 if (valid) {
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __fmul_rn(__uint_as_float(r[j]), __ldg(dm + c0 + j));
-                    if (a.mode == 0) {
+                    if (!UP4 && a.mode == 0) {
                         // NoiseInjection + FusedLeakyReLU (model.py:292, fused_bias_act_kernel.cu:26-47)
                         const int64_t plane = (int64_t)a.out_h * a.out_w;
                         float* dst = a.out_f32 + ((int64_t)b * a.cout + c.n0 + c0) * plane + (int64_t)oy * a.out_w + ox;
@@ -358,7 +385,7 @@ __device__ __forceinline__ void tc_epilogue(const TcKernelArgs& a, uint64_t* tfu
                         if (a.s_next) {
                             const float* sn = a.s_next + (int64_t)b * a.cout + c.n0 + c0;
                             const int64_t off = (((int64_t)b * a.out_h + oy) * a.out_w + ox) * a.cout + c.n0 + c0;
-                            uint4* ph = reinterpret_cast<uint4*>(a.next_hi + off);
+                            uint4* ph_ = reinterpret_cast<uint4*>(a.next_hi + off);
                             uint4* pl = reinterpret_cast<uint4*>(a.next_lo + off);
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
@@ -373,7 +400,7 @@ __device__ __forceinline__ void tc_epilogue(const TcKernelArgs& a, uint64_t* tfu
                                     wh[e] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
                                     wl[e] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
                                 }
-                                ph[q] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+                                ph_[q] = make_uint4(wh[0], wh[1], wh[2], wh[3]);
                                 pl[q] = make_uint4(wl[0], wl[1], wl[2], wl[3]);
                             }
                         }
@@ -413,7 +440,8 @@ modconv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ T
     uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]       (CG = 2: only the even CTA's are used)
     uint32_t* tmem_ptr_smem = (uint32_t*)(bars + 2 * STAGES + 4);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
+    const uint32_t one = lane == 0;                 // the lane that issues the single-thread instructions of its warp's role
     const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
     const bool leader = rank == 0;
     const int unit0 = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // first tile (pair) of this CTA
@@ -441,8 +469,8 @@ modconv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ T
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == 0) {
-        // ============================== TMA producer (both CTAs of a pair) ==============================
-        if (lane == 0) {
+        // ============================== TMA producer (both CTAs of a pair; whole warp, lane 0 issues) ==============================
+        {
             int stage = 0; uint32_t phase = 0;
             for (int t = unit0; t < a.total_tiles; t += unit_stride) {
                 const TileCoord c = decode_tile<BN, TH, TW, TB, CG>(a, t, rank);
@@ -458,24 +486,24 @@ modconv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ T
                         mbar_wait(&empty_bar[stage], phase ^ 1, a.error, 0x100 + stage);
                         uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
                         // one arming per stage: the even CTA expects the bytes of BOTH CTAs on its barrier
-                        if (leader) mbar_expect_tx(&full_bar[stage], CG * Cfg::STAGE_BYTES);
+                        mbar_expect_tx(&full_bar[stage], CG * Cfg::STAGE_BYTES, one & (uint32_t)leader);
                         if (a.im2col) {
-                            tma_load_im2col_cg<CG>(ma_hi, &full_bar[stage], st, kc * BK, c.x0 + s.base_dx, c.y0 + s.base_dy, c.b0, ow_, oh_);
-                            tma_load_im2col_cg<CG>(ma_lo, &full_bar[stage], st + A_TILE_BYTES, kc * BK, c.x0 + s.base_dx, c.y0 + s.base_dy, c.b0, ow_, oh_);
+                            tma_load_im2col_cg<CG>(ma_hi, &full_bar[stage], st, kc * BK, c.x0 + s.base_dx, c.y0 + s.base_dy, c.b0, ow_, oh_, one);
+                            tma_load_im2col_cg<CG>(ma_lo, &full_bar[stage], st + A_TILE_BYTES, kc * BK, c.x0 + s.base_dx, c.y0 + s.base_dy, c.b0, ow_, oh_, one);
                         } else {
-                            tma_load_4d_cg<CG>(ma_hi, &full_bar[stage], st, kc * BK, ax, ay, c.b0);
-                            tma_load_4d_cg<CG>(ma_lo, &full_bar[stage], st + A_TILE_BYTES, kc * BK, ax, ay, c.b0);
+                            tma_load_4d_cg<CG>(ma_hi, &full_bar[stage], st, kc * BK, ax, ay, c.b0, one);
+                            tma_load_4d_cg<CG>(ma_lo, &full_bar[stage], st + A_TILE_BYTES, kc * BK, ax, ay, c.b0, one);
                         }
-                        tma_load_3d_cg<CG>(&maps.w[0], &full_bar[stage], st + 2 * A_TILE_BYTES, kc * BK, wrow, wi);
-                        tma_load_3d_cg<CG>(&maps.w[1], &full_bar[stage], st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES, kc * BK, wrow, wi);
+                        tma_load_3d_cg<CG>(&maps.w[0], &full_bar[stage], st + 2 * A_TILE_BYTES, kc * BK, wrow, wi, one);
+                        tma_load_3d_cg<CG>(&maps.w[1], &full_bar[stage], st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES, kc * BK, wrow, wi, one);
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ============================== MMA issuer (even CTA of a pair only) ==============================
-        if (lane == 0 && leader) {
+        // ============================== MMA issuer (even CTA of a pair only; whole warp, lane 0 issues) ==============================
+        if (leader) {
             // instruction descriptor: D=f32, A=B=bf16, both K-major, N=BN, M=128*CG
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
             int stage = 0; uint32_t phase = 0;
@@ -497,14 +525,14 @@ modconv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ T
 #pragma unroll
                     for (int k = 0; k < BK / UMMA_K; ++k) {
                         const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B per K step inside the swizzle row
-                        umma_bf16_cg<CG>(d_tmem, d_ah + koff, d_bh + koff, idesc, (kb | k) ? 1u : 0u);
-                        umma_bf16_cg<CG>(d_tmem, d_ah + koff, d_bl + koff, idesc, 1u);
-                        umma_bf16_cg<CG>(d_tmem, d_al + koff, d_bh + koff, idesc, 1u);
+                        umma_bf16_cg<CG>(d_tmem, d_ah + koff, d_bh + koff, idesc, (kb | k) ? 1u : 0u, one);
+                        umma_bf16_cg<CG>(d_tmem, d_ah + koff, d_bl + koff, idesc, 1u, one);
+                        umma_bf16_cg<CG>(d_tmem, d_al + koff, d_bh + koff, idesc, 1u, one);
                     }
-                    umma_commit_cg<CG>(&empty_bar[stage]);     // frees this smem stage (in both CTAs) when the MMAs retire
+                    umma_commit_cg<CG>(&empty_bar[stage], one);     // frees this smem stage (in both CTAs) when the MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit_cg<CG>(&tfull_bar[acc]);           // accumulator complete -> epilogue (both CTAs)
+                umma_commit_cg<CG>(&tfull_bar[acc], one);           // accumulator complete -> epilogue (both CTAs)
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -532,38 +560,48 @@ modconv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ T
 // verifies this on the B200).  A traffic drops from 9 x 32 KB to 45 KB per K chunk; the weights stream per tap through
 // their own ring.  With Cout = 128 that takes the L2 -> SM fill from ~62 to ~27 B/clk/SM, i.e. back under the tensor pipe.
 constexpr int HALO_TH = 16, HALO_TW = 8, HALO_W = HALO_TW + 2, HALO_H = HALO_TH + 2;
-template <int BN, int CG> struct TcHaloCfg {
-    static constexpr int BK = 64;
-    static constexpr int A_BYTES = HALO_H * HALO_W * BK * 2;                 // 23040: bytes one halo load delivers
-    static constexpr int A_PAD = (A_BYTES + 1023) / 1024 * 1024;             // 23552: hi / lo planes stay 1024 B aligned
+// BK = 64: 128 B operand rows (SWIZZLE_128B); BK = 32 (layers with 32 input channels): 64 B rows (SWIZZLE_64B), as the
+// transposed halo kernel below uses them.
+// UP4 (transposed conv with Cout <= 64): the 9 taps of a stride-2 transposed conv fall into 4 output phases with 4/2/2/1
+// taps whose offsets are all in {-1, 0}: one halo per K chunk serves ALL FOUR phases of the spatial tile, each phase
+// accumulating into its own BN columns of a 4 x BN accumulator (double-buffered: 8 x BN <= 512 TMEM columns).  The
+// per-tap kernel re-fetches an A tile per (phase, tap, K chunk): with N <= 64 that is ~85 B/clk/SM of L2 -> SM fill for
+// MMAs that need 40-48 clk each, i.e. fill-bound at about half the MMA rate.
+template <int BN, int CG, int BK = 64, bool UP4 = false> struct TcHaloCfg {
+    static constexpr int ROW = BK * 2;
+    static constexpr int A_BYTES = HALO_H * HALO_W * ROW;                    // 23040 (BK 64): bytes one halo load delivers
+    static constexpr int A_PAD = (A_BYTES + 1023) / 1024 * 1024;             // hi / lo planes stay 1024 B aligned
     static constexpr int A_STAGE = 2 * A_PAD;
     static constexpr int NA = 2;
     static constexpr int B_ROWS = BN / CG;
-    static constexpr int B_TILE_BYTES = B_ROWS * BK * 2;
+    static constexpr int B_TILE_BYTES = B_ROWS * ROW;
     static constexpr int B_STAGE = 2 * B_TILE_BYTES;
     static constexpr int BUDGET = 227 * 1024 - 1024 - 512;
     static constexpr int NB_RAW = (BUDGET - NA * A_STAGE) / B_STAGE;
     static constexpr int NB = NB_RAW > 8 ? 8 : NB_RAW;
     static constexpr int SMEM_BYTES = NA * A_STAGE + NB * B_STAGE + 1024 /*align*/ + 512 /*barriers*/;
-    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    static constexpr int ACC_COLS = (UP4 ? 4 : 1) * BN;
+    static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
     static_assert(NB >= 2, "weight ring too shallow");
+    static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
 };
 
+template <int ROW>
 __device__ __forceinline__ uint64_t make_halo_desc(uint32_t saddr) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr >> 4) & 0x3FFF);
     d |= (uint64_t)1 << 16;
-    d |= (uint64_t)((HALO_W * 128) >> 4) << 32;         // 8-pixel row groups are one halo row apart
+    d |= (uint64_t)((HALO_W * ROW) >> 4) << 32;         // 8-pixel row groups are one halo row apart
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B, base_offset 0
+    d |= (uint64_t)(ROW == 128 ? 2 : 4) << 61;          // SWIZZLE_128B / SWIZZLE_64B, base_offset 0
     return d;
 }
 
-template <int BN, int CG>
+template <int BN, int CG, int BK, bool UP4>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 modconv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcKernelArgs a) {
-    using Cfg = TcHaloCfg<BN, CG>;
-    constexpr int NA = Cfg::NA, BK = Cfg::BK;
+    using Cfg = TcHaloCfg<BN, CG, BK, UP4>;
+    constexpr int NA = Cfg::NA, ROW = Cfg::ROW;
     const int NB = a.stages > 0 && a.stages < Cfg::NB ? a.stages : Cfg::NB;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -577,7 +615,8 @@ modconv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const __grid_constan
     uint64_t* tempty_bar = tfull_bar + 2;            // [2]
     uint32_t* tmem_ptr_smem = (uint32_t*)(tempty_bar + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
+    const uint32_t one = lane == 0;                 // the lane that issues the single-thread instructions of its warp's role
     const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
     const bool leader = rank == 0;
     const int unit0 = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -607,8 +646,8 @@ modconv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const __grid_constan
     const TcSubProblem& s = a.sub[0];
 
     if (warp == 0) {
-        // ============================== TMA producer (both CTAs of a pair) ==============================
-        if (lane == 0) {
+        // ============================== TMA producer (both CTAs of a pair; whole warp, lane 0 issues) ==============================
+        {
             int as = 0; uint32_t aphase = 0;
             int bs = 0; uint32_t bphase = 0;
             for (int t = unit0; t < a.total_tiles; t += unit_stride) {
@@ -617,24 +656,24 @@ modconv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const __grid_constan
                 for (int kc = 0; kc < a.kchunks; ++kc) {
                     mbar_wait(&aempty_bar[as], aphase ^ 1, a.error, 0x500 + as);
                     uint8_t* sa = smem + as * Cfg::A_STAGE;
-                    if (leader) mbar_expect_tx(&afull_bar[as], CG * 2 * Cfg::A_BYTES);
-                    tma_load_4d_cg<CG>(&maps.a[0][0], &afull_bar[as], sa, kc * BK, c.x0 - 1, c.y0 - 1, c.b0);
-                    tma_load_4d_cg<CG>(&maps.a[0][1], &afull_bar[as], sa + Cfg::A_PAD, kc * BK, c.x0 - 1, c.y0 - 1, c.b0);
+                    mbar_expect_tx(&afull_bar[as], CG * 2 * Cfg::A_BYTES, one & (uint32_t)leader);
+                    tma_load_4d_cg<CG>(&maps.a[0][0], &afull_bar[as], sa, kc * BK, c.x0 - 1, c.y0 - 1, c.b0, one);
+                    tma_load_4d_cg<CG>(&maps.a[0][1], &afull_bar[as], sa + Cfg::A_PAD, kc * BK, c.x0 - 1, c.y0 - 1, c.b0, one);
                     if (++as == NA) { as = 0; aphase ^= 1; }
                     for (int tap = 0; tap < s.ntaps; ++tap) {
                         mbar_wait(&empty_bar[bs], bphase ^ 1, a.error, 0x100 + bs);
                         uint8_t* sb = smem_b + bs * Cfg::B_STAGE;
-                        if (leader) mbar_expect_tx(&full_bar[bs], CG * Cfg::B_STAGE);
-                        tma_load_3d_cg<CG>(&maps.w[0], &full_bar[bs], sb, kc * BK, wrow, s.widx[tap]);
-                        tma_load_3d_cg<CG>(&maps.w[1], &full_bar[bs], sb + Cfg::B_TILE_BYTES, kc * BK, wrow, s.widx[tap]);
+                        mbar_expect_tx(&full_bar[bs], CG * Cfg::B_STAGE, one & (uint32_t)leader);
+                        tma_load_3d_cg<CG>(&maps.w[0], &full_bar[bs], sb, kc * BK, wrow, s.widx[tap], one);
+                        tma_load_3d_cg<CG>(&maps.w[1], &full_bar[bs], sb + Cfg::B_TILE_BYTES, kc * BK, wrow, s.widx[tap], one);
                         if (++bs == NB) { bs = 0; bphase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ============================== MMA issuer (even CTA of a pair only) ==============================
-        if (lane == 0 && leader) {
+        // ============================== MMA issuer (even CTA of a pair only; whole warp, lane 0 issues) ==============================
+        if (leader) {
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
             int as = 0; uint32_t aphase = 0;
             int bs = 0; uint32_t bphase = 0;
@@ -642,36 +681,41 @@ modconv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const __grid_constan
             for (int t = unit0; t < a.total_tiles; t += unit_stride) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1, a.error, 0x200 + acc);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                const uint32_t d_tile = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS);
+                uint32_t started = 0;                       // UP4: phases whose accumulator has been written in this tile
                 for (int kc = 0; kc < a.kchunks; ++kc) {
                     mbar_wait(&afull_bar[as], aphase, a.error, 0x600 + as);
                     const uint32_t sa = smem_u32(smem + as * Cfg::A_STAGE);
                     for (int tap = 0; tap < s.ntaps; ++tap) {
                         mbar_wait(&full_bar[bs], bphase, a.error, 0x300 + bs);
                         tc_fence_after();
-                        const uint32_t aoff = (uint32_t)(((s.dy[tap] + 1) * HALO_W + (s.dx[tap] + 1)) * (BK * 2));
-                        const uint64_t d_ah = make_halo_desc(sa + aoff), d_al = make_halo_desc(sa + Cfg::A_PAD + aoff);
+                        const uint32_t aoff = (uint32_t)(((s.dy[tap] + 1) * HALO_W + (s.dx[tap] + 1)) * ROW);
+                        const uint64_t d_ah = make_halo_desc<ROW>(sa + aoff), d_al = make_halo_desc<ROW>(sa + Cfg::A_PAD + aoff);
                         const uint32_t sb = smem_u32(smem_b + bs * Cfg::B_STAGE);
-                        const uint64_t d_bh = make_smem_desc<BK * 2>(sb), d_bl = make_smem_desc<BK * 2>(sb + Cfg::B_TILE_BYTES);
+                        const uint64_t d_bh = make_smem_desc<ROW>(sb), d_bl = make_smem_desc<ROW>(sb + Cfg::B_TILE_BYTES);
+                        const int ph = UP4 ? s.phase[tap] : 0;
+                        const uint32_t d_tmem = d_tile + (uint32_t)(ph * BN);
+                        const uint32_t fresh = UP4 ? (((started >> ph) & 1u) ^ 1u) : ((kc | tap) ? 0u : 1u);
+                        started |= 1u << ph;
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
                             const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
-                            umma_bf16_cg<CG>(d_tmem, d_ah + koff, d_bh + koff, idesc, (kc | tap | k) ? 1u : 0u);
-                            umma_bf16_cg<CG>(d_tmem, d_ah + koff, d_bl + koff, idesc, 1u);
-                            umma_bf16_cg<CG>(d_tmem, d_al + koff, d_bh + koff, idesc, 1u);
+                            umma_bf16_cg<CG>(d_tmem, d_ah + koff, d_bh + koff, idesc, (fresh && k == 0) ? 0u : 1u, one);
+                            umma_bf16_cg<CG>(d_tmem, d_ah + koff, d_bl + koff, idesc, 1u, one);
+                            umma_bf16_cg<CG>(d_tmem, d_al + koff, d_bh + koff, idesc, 1u, one);
                         }
-                        umma_commit_cg<CG>(&empty_bar[bs]);
+                        umma_commit_cg<CG>(&empty_bar[bs], one);
                         if (++bs == NB) { bs = 0; bphase ^= 1; }
                     }
-                    umma_commit_cg<CG>(&aempty_bar[as]);            // halo stage free (in both CTAs) once its 9 taps retire
+                    umma_commit_cg<CG>(&aempty_bar[as], one);       // halo stage free (in both CTAs) once its taps retire
                     if (++as == NA) { as = 0; aphase ^= 1; }
                 }
-                umma_commit_cg<CG>(&tfull_bar[acc]);
+                umma_commit_cg<CG>(&tfull_bar[acc], one);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
-        tc_epilogue<BN, HALO_TH, HALO_TW, 1, CG>(a, tfull_bar, tempty_bar, tmem_base, rank, warp, lane, unit0, unit_stride);
+        tc_epilogue<BN, HALO_TH, HALO_TW, 1, CG, UP4>(a, tfull_bar, tempty_bar, tmem_base, rank, warp, lane, unit0, unit_stride);
     }
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();
@@ -736,7 +780,8 @@ modconv_tc_halo_t_kernel(const __grid_constant__ TcMaps maps, const __grid_const
     uint64_t* tempty_bar = tfull_bar + 2;            // [2]
     uint32_t* tmem_ptr_smem = (uint32_t*)(tempty_bar + 2);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
+    const uint32_t one = lane == 0;                 // the lane that issues the single-thread instructions of its warp's role
     const int n_epi_warps = (int)(blockDim.x / 32) - 2;
     // tiles: n-tile slowest, then spatial tile, then (transposed conv) the 4 output phases, rotated by the spatial index so
     // that a CTA's static stride (148 = 4 * 37) does not lock onto one phase (they have 4 / 2 / 2 / 1 taps)
@@ -762,8 +807,8 @@ modconv_tc_halo_t_kernel(const __grid_constant__ TcMaps maps, const __grid_const
     const uint32_t tmem_base = *tmem_ptr_smem;
 
     if (warp == 0) {
-        // ============================== TMA producer ==============================
-        if (lane == 0) {
+        // ============================== TMA producer (whole warp, lane 0 issues) ==============================
+        {
             int as = 0; uint32_t aphase = 0;
             int ws = 0; uint32_t wphase = 0;
             for (int t = blockIdx.x; t < a.total_tiles; t += gridDim.x) {
@@ -774,24 +819,24 @@ modconv_tc_halo_t_kernel(const __grid_constant__ TcMaps maps, const __grid_const
                 for (int kc = 0; kc < a.kchunks; ++kc) {
                     mbar_wait(&aempty_bar[as], aphase ^ 1, a.error, 0x500 + as);
                     uint8_t* sa = smem + as * Cfg::A_STAGE;
-                    mbar_expect_tx(&afull_bar[as], 2 * Cfg::A_BYTES);
-                    tma_load_4d(&maps.a[0][0], &afull_bar[as], sa, kc * BK, x0 - 1, y0 - 1, b);
-                    tma_load_4d(&maps.a[0][1], &afull_bar[as], sa + Cfg::A_PAD, kc * BK, x0 - 1, y0 - 1, b);
+                    mbar_expect_tx(&afull_bar[as], 2 * Cfg::A_BYTES, one);
+                    tma_load_4d(&maps.a[0][0], &afull_bar[as], sa, kc * BK, x0 - 1, y0 - 1, b, one);
+                    tma_load_4d(&maps.a[0][1], &afull_bar[as], sa + Cfg::A_PAD, kc * BK, x0 - 1, y0 - 1, b, one);
                     if (++as == NA) { as = 0; aphase ^= 1; }
                     for (int tap = 0; tap < s.ntaps; ++tap) {
                         mbar_wait(&empty_bar[ws], wphase ^ 1, a.error, 0x100 + ws);
                         uint8_t* sw = smem_w + ws * Cfg::W_STAGE;
-                        mbar_expect_tx(&full_bar[ws], Cfg::W_STAGE);
-                        tma_load_3d(&maps.w[0], &full_bar[ws], sw, kc * BK, n0, s.widx[tap]);
-                        tma_load_3d(&maps.w[1], &full_bar[ws], sw + Cfg::W_TILE_BYTES, kc * BK, n0, s.widx[tap]);
+                        mbar_expect_tx(&full_bar[ws], Cfg::W_STAGE, one);
+                        tma_load_3d(&maps.w[0], &full_bar[ws], sw, kc * BK, n0, s.widx[tap], one);
+                        tma_load_3d(&maps.w[1], &full_bar[ws], sw + Cfg::W_TILE_BYTES, kc * BK, n0, s.widx[tap], one);
                         if (++ws == NW) { ws = 0; wphase ^= 1; }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ============================== MMA issuer ==============================
-        if (lane == 0) {
+        // ============================== MMA issuer (whole warp, lane 0 issues) ==============================
+        {
             // D[128 channels][256 pixels] = W[128][K] . X[256][K]^T : A = weights, B = pixels, both K-major
             constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(HT_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             int as = 0; uint32_t aphase = 0;
@@ -816,17 +861,17 @@ modconv_tc_halo_t_kernel(const __grid_constant__ TcMaps maps, const __grid_const
 #pragma unroll
                         for (int k = 0; k < BK / UMMA_K; ++k) {
                             const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
-                            umma_bf16(d_tmem, d_wh + koff, d_xh + koff, idesc, (kc | tap | k) ? 1u : 0u);
-                            umma_bf16(d_tmem, d_wl + koff, d_xh + koff, idesc, 1u);
-                            umma_bf16(d_tmem, d_wh + koff, d_xl + koff, idesc, 1u);
+                            umma_bf16(d_tmem, d_wh + koff, d_xh + koff, idesc, (kc | tap | k) ? 1u : 0u, one);
+                            umma_bf16(d_tmem, d_wl + koff, d_xh + koff, idesc, 1u, one);
+                            umma_bf16(d_tmem, d_wh + koff, d_xl + koff, idesc, 1u, one);
                         }
-                        umma_commit(&empty_bar[ws]);
+                        umma_commit(&empty_bar[ws], one);
                         if (++ws == NW) { ws = 0; wphase ^= 1; }
                     }
-                    umma_commit(&aempty_bar[as]);
+                    umma_commit(&aempty_bar[as], one);
                     if (++as == NA) { as = 0; aphase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);
+                umma_commit(&tfull_bar[acc], one);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -1441,10 +1486,10 @@ static int launch_tc(const TcMaps& maps, const TcKernelArgs& a, cudaStream_t str
     return SIS_OK;
 }
 
-template <int BN, int CG>
+template <int BN, int CG, int BK, bool UP4>
 static int launch_tc_halo(const TcMaps& maps, const TcKernelArgs& a, cudaStream_t stream) {
-    using Cfg = TcHaloCfg<BN, CG>;
-    auto kern = modconv_tc_halo_kernel<BN, CG>;
+    using Cfg = TcHaloCfg<BN, CG, BK, UP4>;
+    auto kern = modconv_tc_halo_kernel<BN, CG, BK, UP4>;
     static bool configured = false;
     if (!configured) {
         SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
@@ -1479,11 +1524,24 @@ static int launch_tc_halo_t(const TcMaps& maps, const TcKernelArgs& a, cudaStrea
 }
 
 template <int CG>
-static int launch_tc_halo_any(int BN, const TcMaps& maps, const TcKernelArgs& a, cudaStream_t stream) {
-    if (BN == 256) return launch_tc_halo<256, CG>(maps, a, stream);
-    if (BN == 128) return launch_tc_halo<128, CG>(maps, a, stream);
-    if (BN == 64) return launch_tc_halo<64, CG>(maps, a, stream);
-    return launch_tc_halo<32, CG>(maps, a, stream);
+static int launch_tc_halo_any(int BN, int BK, const TcMaps& maps, const TcKernelArgs& a, cudaStream_t stream) {
+    if (BK == 32) {          // 32-channel K chunks are only built for the narrow layers that have them
+        if (BN == 64) return launch_tc_halo<64, CG, 32, false>(maps, a, stream);
+        return launch_tc_halo<32, CG, 32, false>(maps, a, stream);
+    }
+    if (BN == 256) return launch_tc_halo<256, CG, 64, false>(maps, a, stream);
+    if (BN == 128) return launch_tc_halo<128, CG, 64, false>(maps, a, stream);
+    if (BN == 64) return launch_tc_halo<64, CG, 64, false>(maps, a, stream);
+    return launch_tc_halo<32, CG, 64, false>(maps, a, stream);
+}
+
+// 4-phase halo kernel of the transposed conv with Cout <= 64 (BN = Cout)
+static int launch_tc_halo_up4(int BN, int BK, int CG, const TcMaps& maps, const TcKernelArgs& a, cudaStream_t stream) {
+    if (BN == 64) {
+        if (CG == 2) return BK == 64 ? launch_tc_halo<64, 2, 64, true>(maps, a, stream) : launch_tc_halo<64, 2, 32, true>(maps, a, stream);
+        return BK == 64 ? launch_tc_halo<64, 1, 64, true>(maps, a, stream) : launch_tc_halo<64, 1, 32, true>(maps, a, stream);
+    }
+    return BK == 64 ? launch_tc_halo<32, 1, 64, true>(maps, a, stream) : launch_tc_halo<32, 1, 32, true>(maps, a, stream);
 }
 
 template <int BN, int BK, int CG>
@@ -1670,10 +1728,54 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
         }
         return tc_blur_after_upconv(ws, call, stream);
     }
-    // halo reuse: plain 3x3 layers whose image holds whole 16 x 8 tiles and whose K chunks are 64 wide
-    const bool halo = halo_env && !call.up && call.res_in >= HALO_TH && call.res_in % HALO_TH == 0 && call.cin % 64 == 0;
+    // Cout <= 64 up-convs (the 512^2 / 1024^2 models): all four output phases of a spatial tile from ONE halo per K chunk
+    static int up4_env = env_int("SIS_TC_UP4", 1) != 0;
+    if (up4_env && halo_env && call.up && (call.cout == 64 || call.cout == 32) && call.cin % 32 == 0 && call.res_in >= 8) {
+        SIS_REQUIRE(w.hi && w.cin == call.cin && w.cout == call.cout, "tc_modconv: weights not packed for this layer");
+        const int B = call.batch, H = call.res_in, BN = call.cout, BK = call.cin % 64 == 0 ? 64 : 32;
+        TcKernelArgs a;
+        memset(&a, 0, sizeof(a));
+        a.batch = B; a.cin = call.cin; a.cout = call.cout; a.kchunks = call.cin / BK;
+        a.b_tiles = B; a.n_tiles = 1;
+        a.demod = call.demod; a.error = ws.d_error; a.mode = 1; a.nsub = 1;
+        TcSubProblem& s = a.sub[0];
+        s.ntaps = 0;
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px)
+                for (int ky = py; ky < 3; ky += 2)
+                    for (int kx = px; kx < 3; kx += 2) {
+                        s.dy[s.ntaps] = (short)(-(ky / 2)); s.dx[s.ntaps] = (short)(-(kx / 2));
+                        s.widx[s.ntaps] = (signed char)(ky * 3 + kx); s.phase[s.ntaps] = (signed char)(py * 2 + px); s.ntaps++;
+                    }
+        // tiles cover the (H+1)^2 grid of the py = px = 0 phase; the other phases' last row / column is masked in the epilogue
+        s.oh = H + 1; s.ow = H + 1; s.ostride = 2; s.ooff_y = 0; s.ooff_x = 0;
+        s.tiles_y = ceil_div(H + 1, HALO_TH); s.tiles_x = ceil_div(H + 1, HALO_TW); s.tile_begin = 0;
+        const int64_t m_tiles = (int64_t)B * s.tiles_y * s.tiles_x;
+        const int CG = (cg_env == 2 && BN == 64 && m_tiles >= 2 * kNumSMs) ? 2 : 1;
+        a.total_tiles = (int)ceil_div64(m_tiles, CG);
+        a.out_f32 = call.upconv_tmp; a.out_h = 2 * H + 1; a.out_w = 2 * H + 1;
+        TcMaps maps;
+        memset(&maps, 0, sizeof(maps));
+        const uint64_t adims[4] = {(uint64_t)call.cin, (uint64_t)H, (uint64_t)H, (uint64_t)B};
+        const uint32_t abox[4] = {(uint32_t)BK, (uint32_t)HALO_W, (uint32_t)HALO_H, 1};
+        SIS_PROPAGATE(make_map(&maps.a[0][0], ws.a_hi[call.in_slot], 4, adims, abox, BK * 2));
+        SIS_PROPAGATE(make_map(&maps.a[0][1], ws.a_lo[call.in_slot], 4, adims, abox, BK * 2));
+        const uint64_t wdims[3] = {(uint64_t)call.cin, (uint64_t)call.cout, 9};
+        const uint32_t wbox[3] = {(uint32_t)BK, (uint32_t)(BN / CG), 1};
+        SIS_PROPAGATE(make_map(&maps.w[0], w.hi, 3, wdims, wbox, BK * 2));
+        SIS_PROPAGATE(make_map(&maps.w[1], w.lo, 3, wdims, wbox, BK * 2));
+        {
+            ProfScope prof(conv_cat, stream);
+            SIS_PROPAGATE(launch_tc_halo_up4(BN, BK, CG, maps, a, stream));
+        }
+        return tc_blur_after_upconv(ws, call, stream);
+    }
+    // halo reuse: plain 3x3 layers whose image holds whole 16 x 8 tiles; K chunks of 64 channels (128 B rows), or of 32
+    // (64 B rows) for the narrow layers with 32 input channels
+    const bool halo = halo_env && !call.up && call.res_in >= HALO_TH && call.res_in % HALO_TH == 0 &&
+                      (call.cin % 64 == 0 || (call.cin % 32 == 0 && call.cout <= 64));
     const bool im2col = im2col_env != 0 && !halo;
-    const int BK = halo ? 64 : (call.cin % 64 == 0) ? bk_env : 32;
+    const int BK = halo ? (call.cin % 64 == 0 ? 64 : 32) : (call.cin % 64 == 0) ? bk_env : 32;
     SIS_REQUIRE(call.cin % BK == 0, "tc_modconv: Cin must be a multiple of 32 (got %d)", call.cin);
     SIS_REQUIRE(call.cout % 32 == 0, "tc_modconv: Cout must be a multiple of 32 (got %d)", call.cout);
     SIS_REQUIRE(w.hi && w.cin == call.cin && w.cout == call.cout, "tc_modconv: weights not packed for this layer");
@@ -1800,7 +1902,7 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
     int st;
     {
         ProfScope prof(conv_cat, stream);
-        if (halo) st = (CG == 2) ? launch_tc_halo_any<2>(BN, maps, a, stream) : launch_tc_halo_any<1>(BN, maps, a, stream);
+        if (halo) st = (CG == 2) ? launch_tc_halo_any<2>(BN, BK, maps, a, stream) : launch_tc_halo_any<1>(BN, BK, maps, a, stream);
         else if (CG == 2) st = (BK == 64) ? launch_tc_any<64, 2>(BN, th, tw, tb, maps, a, stream) : launch_tc_any<32, 2>(BN, th, tw, tb, maps, a, stream);
         else st = (BK == 64) ? launch_tc_any<64, 1>(BN, th, tw, tb, maps, a, stream) : launch_tc_any<32, 1>(BN, th, tw, tb, maps, a, stream);
     }
