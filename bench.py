@@ -673,7 +673,8 @@ def measure(wl, args, dev, rank, world, steps, warmup, profile_steps, with_e2e=T
         return float(ms.item())
 
     # ---------------------------------------------------------------- value: inputs resident in HBM
-    run_steps(0, warmup)
+    run_steps(0, warmup, keep_first=True)     # the first warm-up batch is held like the first timed one will be, then released:
+    first_timed.clear()                       # the allocator's cache then already holds blocks of those sizes
     sampler = ClockSampler(dev)
     if rank == 0:
         sampler.start()

@@ -33,15 +33,24 @@ using bf16 = __nv_bfloat16;
 // ------------------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// One lane of a converged warp (PTX elect.sync).  A branch on this predicate is a pattern the compiler knows: inside it
+// the single-thread tcgen05 / TMA instructions are issued once with warp-uniform operands, without a per-lane loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-// Every single-lane operation of the warp-specialised roles takes a lane predicate `pred` and predicates the instruction
-// INSIDE the asm block.  The producer / MMA loops are executed by the WHOLE warp with warp-uniform control flow and
-// operands; only the instruction itself is issued by one lane.  (Wrapping the loop in `if (lane == 0)` makes every
-// descriptor a per-thread value: the compiler then emits an ELECT + 5 x R2UR.BROADCAST + BRA.U.ANY "waterfall" around
-// every UTCHMMA / UTMALDG, ~95 clk per MMA whatever its shape -- measured: N = 64 layers at 32 % tensor-active, N = 32 at
-// 17 %, N = 128 at 63 %.)
+// The producer / MMA loops of the warp-specialised kernels are executed by the WHOLE warp with warp-uniform control flow
+// and operands; the single-thread instructions sit in `if (elect_one())` blocks, so their descriptors live in uniform
+// registers and the UTCHMMA / UTMALDG instructions issue back to back.  (Wrapping the whole loop in `if (lane == 0)`
+// makes every descriptor a per-thread value: the compiler then emits an ELECT + 5 x R2UR.BROADCAST + BRA.U.ANY
+// "waterfall" around every UTCHMMA, ~95 clk per MMA whatever its shape -- measured: N = 64 layers at 32 % tensor-active,
+// N = 32 at 17 %, N = 128 at 63 %.  A lane predicate inside the asm block (`pred`, kept for single call sites) still
+// costs an ELECT loop per instruction: 42 % / 17 % / 78 %.)
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes, uint32_t pred = 1u) {
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}"
                  ::"r"(smem_u32(bar)), "r"(bytes), "r"(pred) : "memory");
@@ -324,6 +333,20 @@ __device__ __forceinline__ void umma_commit_cg(uint64_t* bar, uint32_t pred = 1u
 
 // Epilogue warps (2..9): TMEM accumulator -> demodulate [-> noise + bias + lrelu] -> fp32 capture (+ the next conv's
 // pre-scaled bf16 hi/lo planes), shared by the per-tap and the halo kernels.
+// 32 consecutive per-channel constants (demodulation factors, bias, next style) as 8 x 128-bit loads when aligned
+__device__ __forceinline__ void load32(const float* p, float (&o)[32]) {
+    if ((reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(p) + q);
+            o[4 * q] = v.x; o[4 * q + 1] = v.y; o[4 * q + 2] = v.z; o[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = __ldg(p + j);
+    }
+}
+
 // UP4: the accumulator holds the FOUR output phases of a transposed conv side by side (4 x BN columns; phase p of pixel
 // (yy, xx) goes to scratch position (2yy + py, 2xx + px); the py = 1 / px = 1 phases are one row / column shorter).
 template <int BN, int TH, int TW, int TB, int CG, bool UP4 = false>
@@ -367,23 +390,26 @@ __device__ __forceinline__ void tc_epilogue(const TcKernelArgs& a, uint64_t* tfu
                 tmem_ld_32x32(taddr + (uint32_t)call, r);
                 tmem_ld_wait();
                 if (valid) {
-                    float v[32];
+                    float v[32], cst[32];
+                    load32(dm + c0, cst);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = __fmul_rn(__uint_as_float(r[j]), __ldg(dm + c0 + j));
+                    for (int j = 0; j < 32; ++j) v[j] = __fmul_rn(__uint_as_float(r[j]), cst[j]);
                     if (!UP4 && a.mode == 0) {
                         // NoiseInjection + FusedLeakyReLU (model.py:292, fused_bias_act_kernel.cu:26-47)
                         const int64_t plane = (int64_t)a.out_h * a.out_w;
                         float* dst = a.out_f32 + ((int64_t)b * a.cout + c.n0 + c0) * plane + (int64_t)oy * a.out_w + ox;
+                        if (a.bias) load32(a.bias + c.n0 + c0, cst);
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             float x = __fadd_rn(v[j], nz);
-                            if (a.bias) x = __fadd_rn(x, __ldg(a.bias + c.n0 + c0 + j));
+                            if (a.bias) x = __fadd_rn(x, cst[j]);
                             if (a.act) x = lrelu_scale(x, 0.2f, 1.41421356237309504880f);
                             v[j] = x;
                             dst[(int64_t)j * plane] = x;       // lanes = consecutive x: coalesced per channel
                         }
                         if (a.s_next) {
-                            const float* sn = a.s_next + (int64_t)b * a.cout + c.n0 + c0;
+                            load32(a.s_next + (int64_t)b * a.cout + c.n0 + c0, cst);
+                            const float* sn = cst;
                             const int64_t off = (((int64_t)b * a.out_h + oy) * a.out_w + ox) * a.cout + c.n0 + c0;
                             uint4* ph_ = reinterpret_cast<uint4*>(a.next_hi + off);
                             uint4* pl = reinterpret_cast<uint4*>(a.next_lo + off);
@@ -393,7 +419,7 @@ __device__ __forceinline__ void tc_epilogue(const TcKernelArgs& a, uint64_t* tfu
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
                                     const int j = q * 8 + e * 2;
-                                    const float x0 = __fmul_rn(v[j], __ldg(sn + j)), x1 = __fmul_rn(v[j + 1], __ldg(sn + j + 1));
+                                    const float x0 = __fmul_rn(v[j], sn[j]), x1 = __fmul_rn(v[j + 1], sn[j + 1]);
                                     const bf16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
                                     const bf16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
                                     const bf16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
@@ -441,7 +467,6 @@ modconv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ T
     uint32_t* tmem_ptr_smem = (uint32_t*)(bars + 2 * STAGES + 4);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
-    const uint32_t one = lane == 0;                 // the lane that issues the single-thread instructions of its warp's role
     const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
     const bool leader = rank == 0;
     const int unit0 = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;        // first tile (pair) of this CTA
@@ -485,17 +510,20 @@ modconv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ T
                     for (int kc = 0; kc < a.kchunks; ++kc) {
                         mbar_wait(&empty_bar[stage], phase ^ 1, a.error, 0x100 + stage);
                         uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
-                        // one arming per stage: the even CTA expects the bytes of BOTH CTAs on its barrier
-                        mbar_expect_tx(&full_bar[stage], CG * Cfg::STAGE_BYTES, one & (uint32_t)leader);
-                        if (a.im2col) {
-                            tma_load_im2col_cg<CG>(ma_hi, &full_bar[stage], st, kc * BK, c.x0 + s.base_dx, c.y0 + s.base_dy, c.b0, ow_, oh_, one);
-                            tma_load_im2col_cg<CG>(ma_lo, &full_bar[stage], st + A_TILE_BYTES, kc * BK, c.x0 + s.base_dx, c.y0 + s.base_dy, c.b0, ow_, oh_, one);
-                        } else {
-                            tma_load_4d_cg<CG>(ma_hi, &full_bar[stage], st, kc * BK, ax, ay, c.b0, one);
-                            tma_load_4d_cg<CG>(ma_lo, &full_bar[stage], st + A_TILE_BYTES, kc * BK, ax, ay, c.b0, one);
+                        if (elect_one()) {
+                            // one arming per stage: the even CTA expects the bytes of BOTH CTAs on its barrier
+                            if (leader) mbar_expect_tx(&full_bar[stage], CG * Cfg::STAGE_BYTES);
+                            if (a.im2col) {
+                                tma_load_im2col_cg<CG>(ma_hi, &full_bar[stage], st, kc * BK, c.x0 + s.base_dx, c.y0 + s.base_dy, c.b0, ow_, oh_);
+                                tma_load_im2col_cg<CG>(ma_lo, &full_bar[stage], st + A_TILE_BYTES, kc * BK, c.x0 + s.base_dx, c.y0 + s.base_dy, c.b0, ow_, oh_);
+                            } else {
+                                tma_load_4d_cg<CG>(ma_hi, &full_bar[stage], st, kc * BK, ax, ay, c.b0);
+                                tma_load_4d_cg<CG>(ma_lo, &full_bar[stage], st + A_TILE_BYTES, kc * BK, ax, ay, c.b0);
+                            }
+                            tma_load_3d_cg<CG>(&maps.w[0], &full_bar[stage], st + 2 * A_TILE_BYTES, kc * BK, wrow, wi);
+                            tma_load_3d_cg<CG>(&maps.w[1], &full_bar[stage], st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES, kc * BK, wrow, wi);
                         }
-                        tma_load_3d_cg<CG>(&maps.w[0], &full_bar[stage], st + 2 * A_TILE_BYTES, kc * BK, wrow, wi, one);
-                        tma_load_3d_cg<CG>(&maps.w[1], &full_bar[stage], st + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES, kc * BK, wrow, wi, one);
+                        __syncwarp();
                         if (++stage == STAGES) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -522,17 +550,20 @@ modconv_tc_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ T
                     const uint64_t d_ah = make_smem_desc<BK * 2>(sa), d_al = make_smem_desc<BK * 2>(sa + A_TILE_BYTES);
                     const uint64_t d_bh = make_smem_desc<BK * 2>(sa + 2 * A_TILE_BYTES);
                     const uint64_t d_bl = make_smem_desc<BK * 2>(sa + 2 * A_TILE_BYTES + Cfg::B_TILE_BYTES);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B per K step inside the swizzle row
-                        umma_bf16_cg<CG>(d_tmem, d_ah + koff, d_bh + koff, idesc, (kb | k) ? 1u : 0u, one);
-                        umma_bf16_cg<CG>(d_tmem, d_ah + koff, d_bl + koff, idesc, 1u, one);
-                        umma_bf16_cg<CG>(d_tmem, d_al + koff, d_bh + koff, idesc, 1u, one);
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // +32 B per K step inside the swizzle row
+                            umma_bf16_cg<CG>(d_tmem, d_ah + koff, d_bh + koff, idesc, (kb | k) ? 1u : 0u);
+                            umma_bf16_cg<CG>(d_tmem, d_ah + koff, d_bl + koff, idesc, 1u);
+                            umma_bf16_cg<CG>(d_tmem, d_al + koff, d_bh + koff, idesc, 1u);
+                        }
+                        umma_commit_cg<CG>(&empty_bar[stage]);      // frees this smem stage (in both CTAs) when the MMAs retire
+                        if (kb == kblocks - 1) umma_commit_cg<CG>(&tfull_bar[acc]);   // accumulator complete -> epilogue (both CTAs)
                     }
-                    umma_commit_cg<CG>(&empty_bar[stage], one);     // frees this smem stage (in both CTAs) when the MMAs retire
+                    __syncwarp();
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
-                umma_commit_cg<CG>(&tfull_bar[acc], one);           // accumulator complete -> epilogue (both CTAs)
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -616,7 +647,6 @@ modconv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const __grid_constan
     uint32_t* tmem_ptr_smem = (uint32_t*)(tempty_bar + 2);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
-    const uint32_t one = lane == 0;                 // the lane that issues the single-thread instructions of its warp's role
     const int rank = (CG == 2) ? (int)cluster_ctarank() : 0;
     const bool leader = rank == 0;
     const int unit0 = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
@@ -656,16 +686,22 @@ modconv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const __grid_constan
                 for (int kc = 0; kc < a.kchunks; ++kc) {
                     mbar_wait(&aempty_bar[as], aphase ^ 1, a.error, 0x500 + as);
                     uint8_t* sa = smem + as * Cfg::A_STAGE;
-                    mbar_expect_tx(&afull_bar[as], CG * 2 * Cfg::A_BYTES, one & (uint32_t)leader);
-                    tma_load_4d_cg<CG>(&maps.a[0][0], &afull_bar[as], sa, kc * BK, c.x0 - 1, c.y0 - 1, c.b0, one);
-                    tma_load_4d_cg<CG>(&maps.a[0][1], &afull_bar[as], sa + Cfg::A_PAD, kc * BK, c.x0 - 1, c.y0 - 1, c.b0, one);
+                    if (elect_one()) {
+                        if (leader) mbar_expect_tx(&afull_bar[as], CG * 2 * Cfg::A_BYTES);
+                        tma_load_4d_cg<CG>(&maps.a[0][0], &afull_bar[as], sa, kc * BK, c.x0 - 1, c.y0 - 1, c.b0);
+                        tma_load_4d_cg<CG>(&maps.a[0][1], &afull_bar[as], sa + Cfg::A_PAD, kc * BK, c.x0 - 1, c.y0 - 1, c.b0);
+                    }
+                    __syncwarp();
                     if (++as == NA) { as = 0; aphase ^= 1; }
                     for (int tap = 0; tap < s.ntaps; ++tap) {
                         mbar_wait(&empty_bar[bs], bphase ^ 1, a.error, 0x100 + bs);
                         uint8_t* sb = smem_b + bs * Cfg::B_STAGE;
-                        mbar_expect_tx(&full_bar[bs], CG * Cfg::B_STAGE, one & (uint32_t)leader);
-                        tma_load_3d_cg<CG>(&maps.w[0], &full_bar[bs], sb, kc * BK, wrow, s.widx[tap], one);
-                        tma_load_3d_cg<CG>(&maps.w[1], &full_bar[bs], sb + Cfg::B_TILE_BYTES, kc * BK, wrow, s.widx[tap], one);
+                        if (elect_one()) {
+                            if (leader) mbar_expect_tx(&full_bar[bs], CG * Cfg::B_STAGE);
+                            tma_load_3d_cg<CG>(&maps.w[0], &full_bar[bs], sb, kc * BK, wrow, s.widx[tap]);
+                            tma_load_3d_cg<CG>(&maps.w[1], &full_bar[bs], sb + Cfg::B_TILE_BYTES, kc * BK, wrow, s.widx[tap]);
+                        }
+                        __syncwarp();
                         if (++bs == NB) { bs = 0; bphase ^= 1; }
                     }
                 }
@@ -697,20 +733,25 @@ modconv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const __grid_constan
                         const uint32_t d_tmem = d_tile + (uint32_t)(ph * BN);
                         const uint32_t fresh = UP4 ? (((started >> ph) & 1u) ^ 1u) : ((kc | tap) ? 0u : 1u);
                         started |= 1u << ph;
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k) {
-                            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
-                            umma_bf16_cg<CG>(d_tmem, d_ah + koff, d_bh + koff, idesc, (fresh && k == 0) ? 0u : 1u, one);
-                            umma_bf16_cg<CG>(d_tmem, d_ah + koff, d_bl + koff, idesc, 1u, one);
-                            umma_bf16_cg<CG>(d_tmem, d_al + koff, d_bh + koff, idesc, 1u, one);
+                            for (int k = 0; k < BK / UMMA_K; ++k) {
+                                const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+                                umma_bf16_cg<CG>(d_tmem, d_ah + koff, d_bh + koff, idesc, (fresh && k == 0) ? 0u : 1u);
+                                umma_bf16_cg<CG>(d_tmem, d_ah + koff, d_bl + koff, idesc, 1u);
+                                umma_bf16_cg<CG>(d_tmem, d_al + koff, d_bh + koff, idesc, 1u);
+                            }
+                            umma_commit_cg<CG>(&empty_bar[bs]);
+                            if (tap == s.ntaps - 1) {
+                                umma_commit_cg<CG>(&aempty_bar[as]);    // halo stage free (in both CTAs) once its taps retire
+                                if (kc == a.kchunks - 1) umma_commit_cg<CG>(&tfull_bar[acc]);
+                            }
                         }
-                        umma_commit_cg<CG>(&empty_bar[bs], one);
+                        __syncwarp();
                         if (++bs == NB) { bs = 0; bphase ^= 1; }
                     }
-                    umma_commit_cg<CG>(&aempty_bar[as], one);       // halo stage free (in both CTAs) once its taps retire
                     if (++as == NA) { as = 0; aphase ^= 1; }
                 }
-                umma_commit_cg<CG>(&tfull_bar[acc], one);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -726,6 +767,142 @@ modconv_tc_halo_kernel(const __grid_constant__ TcMaps maps, const __grid_constan
             asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
         else
             asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------- halo kernel with resident weights
+// The 32-output-channel layers of the 1024^2 model (32 -> 32 plain, 64 -> 32 up): an MMA with N = 32 needs 40 clk of
+// operand fetch for 16 clk of math, a tap is only 6-12 of them, and a weight tile is 2-4 KB -- streaming the weights per
+// (tile, tap) through a barrier ring makes the producer and the per-tap barrier round trips the bottleneck (measured:
+// 83 clk per MMA).  Here all 9 taps of the (single) K chunk stay in shared memory for the life of the CTA (36-72 KB),
+// the producer only streams halos (ring of up to 4), and the MMA warp issues the 54-108 MMAs of a tile in ONE elected
+// block behind a single barrier wait.
+template <int BN, int BK, bool UP4> struct TcHaloRwCfg {
+    static constexpr int ROW = BK * 2;
+    static constexpr int A_BYTES = HALO_H * HALO_W * ROW;
+    static constexpr int A_PAD = (A_BYTES + 1023) / 1024 * 1024;
+    static constexpr int A_STAGE = 2 * A_PAD;
+    static constexpr int W_TILE = BN * ROW;                                  // one plane of one tap
+    static constexpr int W_TAP = 2 * W_TILE;
+    static constexpr int W_BYTES = 9 * W_TAP;
+    static constexpr int BUDGET = 227 * 1024 - 1024 - 512;
+    static constexpr int NA_RAW = (BUDGET - W_BYTES) / A_STAGE;
+    static constexpr int NA = NA_RAW > 4 ? 4 : NA_RAW;
+    static constexpr int SMEM_BYTES = W_BYTES + NA * A_STAGE + 1024 + 512;
+    static constexpr int ACC_COLS = (UP4 ? 4 : 1) * BN;
+    static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
+    static_assert(NA >= 2, "halo ring too shallow");
+    static_assert(W_TILE % 1024 == 0, "weight tiles must stay swizzle-aligned");
+};
+
+template <int BN, int BK, bool UP4>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+modconv_tc_halo_rw_kernel(const __grid_constant__ TcMaps maps, const __grid_constant__ TcKernelArgs a) {
+    using Cfg = TcHaloRwCfg<BN, BK, UP4>;
+    constexpr int NA = Cfg::NA, ROW = Cfg::ROW;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem_w = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem_a = smem_w + Cfg::W_BYTES;
+    uint64_t* bars = (uint64_t*)(smem_a + NA * Cfg::A_STAGE);
+    uint64_t* afull_bar = bars;                      // [NA]
+    uint64_t* aempty_bar = bars + NA;                // [NA]
+    uint64_t* tfull_bar = bars + 2 * NA;             // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;            // [2]
+    uint64_t* wfull_bar = tempty_bar + 2;            // [1]
+    uint32_t* tmem_ptr_smem = (uint32_t*)(wfull_bar + 1);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const int unit0 = (int)blockIdx.x, unit_stride = (int)gridDim.x;
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&maps.a[0][0]); tma_prefetch_desc(&maps.a[0][1]);
+        tma_prefetch_desc(&maps.w[0]); tma_prefetch_desc(&maps.w[1]);
+        for (int i = 0; i < NA; ++i) { mbar_init(&afull_bar[i], 1); mbar_init(&aempty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], blockDim.x / 32 - 2); }
+        mbar_init(wfull_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr_smem)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+    const TcSubProblem& s = a.sub[0];
+
+    if (warp == 0) {
+        // ============================== TMA producer (whole warp, one elected lane issues) ==============================
+        if (elect_one()) {
+            mbar_expect_tx(wfull_bar, Cfg::W_BYTES);
+            for (int tap = 0; tap < 9; ++tap) {
+                tma_load_3d(&maps.w[0], wfull_bar, smem_w + tap * Cfg::W_TAP, 0, 0, s.widx[tap]);
+                tma_load_3d(&maps.w[1], wfull_bar, smem_w + tap * Cfg::W_TAP + Cfg::W_TILE, 0, 0, s.widx[tap]);
+            }
+        }
+        __syncwarp();
+        int as = 0; uint32_t aphase = 0;
+        for (int t = unit0; t < a.total_tiles; t += unit_stride) {
+            const TileCoord c = decode_tile<BN, HALO_TH, HALO_TW, 1, 1>(a, t, 0);
+            mbar_wait(&aempty_bar[as], aphase ^ 1, a.error, 0x500 + as);
+            uint8_t* sa = smem_a + as * Cfg::A_STAGE;
+            if (elect_one()) {
+                mbar_expect_tx(&afull_bar[as], 2 * Cfg::A_BYTES);
+                tma_load_4d(&maps.a[0][0], &afull_bar[as], sa, 0, c.x0 - 1, c.y0 - 1, c.b0);
+                tma_load_4d(&maps.a[0][1], &afull_bar[as], sa + Cfg::A_PAD, 0, c.x0 - 1, c.y0 - 1, c.b0);
+            }
+            __syncwarp();
+            if (++as == NA) { as = 0; aphase ^= 1; }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer (whole warp, one elected lane issues) ==============================
+        constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        int as = 0; uint32_t aphase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
+        mbar_wait(wfull_bar, 0, a.error, 0x700);
+        const uint32_t sw0 = smem_u32(smem_w);
+        for (int t = unit0; t < a.total_tiles; t += unit_stride) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1, a.error, 0x200 + acc);
+            mbar_wait(&afull_bar[as], aphase, a.error, 0x600 + as);
+            tc_fence_after();
+            const uint32_t d_tile = tmem_base + (uint32_t)(acc * Cfg::ACC_COLS);
+            const uint32_t sa = smem_u32(smem_a + as * Cfg::A_STAGE);
+            if (elect_one()) {
+                uint32_t started = 0;
+#pragma unroll 1
+                for (int tap = 0; tap < 9; ++tap) {
+                    const uint32_t aoff = (uint32_t)(((s.dy[tap] + 1) * HALO_W + (s.dx[tap] + 1)) * ROW);
+                    const uint64_t d_ah = make_halo_desc<ROW>(sa + aoff), d_al = make_halo_desc<ROW>(sa + Cfg::A_PAD + aoff);
+                    const uint32_t sb = sw0 + (uint32_t)(tap * Cfg::W_TAP);
+                    const uint64_t d_bh = make_smem_desc<ROW>(sb), d_bl = make_smem_desc<ROW>(sb + Cfg::W_TILE);
+                    const int ph = UP4 ? s.phase[tap] : 0;
+                    const uint32_t d_tmem = d_tile + (uint32_t)(ph * BN);
+                    const uint32_t fresh = UP4 ? (((started >> ph) & 1u) ^ 1u) : (tap ? 0u : 1u);
+                    started |= 1u << ph;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+                        umma_bf16(d_tmem, d_ah + koff, d_bh + koff, idesc, (fresh && k == 0) ? 0u : 1u);
+                        umma_bf16(d_tmem, d_ah + koff, d_bl + koff, idesc, 1u);
+                        umma_bf16(d_tmem, d_al + koff, d_bh + koff, idesc, 1u);
+                    }
+                }
+                umma_commit(&aempty_bar[as]);
+                umma_commit(&tfull_bar[acc]);
+            }
+            __syncwarp();
+            if (++as == NA) { as = 0; aphase ^= 1; }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        tc_epilogue<BN, HALO_TH, HALO_TW, 1, 1, UP4>(a, tfull_bar, tempty_bar, tmem_base, 0, warp, lane, unit0, unit_stride);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
     }
 }
 
@@ -781,7 +958,6 @@ modconv_tc_halo_t_kernel(const __grid_constant__ TcMaps maps, const __grid_const
     uint32_t* tmem_ptr_smem = (uint32_t*)(tempty_bar + 2);
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // provably warp-uniform
-    const uint32_t one = lane == 0;                 // the lane that issues the single-thread instructions of its warp's role
     const int n_epi_warps = (int)(blockDim.x / 32) - 2;
     // tiles: n-tile slowest, then spatial tile, then (transposed conv) the 4 output phases, rotated by the spatial index so
     // that a CTA's static stride (148 = 4 * 37) does not lock onto one phase (they have 4 / 2 / 2 / 1 taps)
@@ -819,16 +995,22 @@ modconv_tc_halo_t_kernel(const __grid_constant__ TcMaps maps, const __grid_const
                 for (int kc = 0; kc < a.kchunks; ++kc) {
                     mbar_wait(&aempty_bar[as], aphase ^ 1, a.error, 0x500 + as);
                     uint8_t* sa = smem + as * Cfg::A_STAGE;
-                    mbar_expect_tx(&afull_bar[as], 2 * Cfg::A_BYTES, one);
-                    tma_load_4d(&maps.a[0][0], &afull_bar[as], sa, kc * BK, x0 - 1, y0 - 1, b, one);
-                    tma_load_4d(&maps.a[0][1], &afull_bar[as], sa + Cfg::A_PAD, kc * BK, x0 - 1, y0 - 1, b, one);
+                    if (elect_one()) {
+                        mbar_expect_tx(&afull_bar[as], 2 * Cfg::A_BYTES);
+                        tma_load_4d(&maps.a[0][0], &afull_bar[as], sa, kc * BK, x0 - 1, y0 - 1, b);
+                        tma_load_4d(&maps.a[0][1], &afull_bar[as], sa + Cfg::A_PAD, kc * BK, x0 - 1, y0 - 1, b);
+                    }
+                    __syncwarp();
                     if (++as == NA) { as = 0; aphase ^= 1; }
                     for (int tap = 0; tap < s.ntaps; ++tap) {
                         mbar_wait(&empty_bar[ws], wphase ^ 1, a.error, 0x100 + ws);
                         uint8_t* sw = smem_w + ws * Cfg::W_STAGE;
-                        mbar_expect_tx(&full_bar[ws], Cfg::W_STAGE, one);
-                        tma_load_3d(&maps.w[0], &full_bar[ws], sw, kc * BK, n0, s.widx[tap], one);
-                        tma_load_3d(&maps.w[1], &full_bar[ws], sw + Cfg::W_TILE_BYTES, kc * BK, n0, s.widx[tap], one);
+                        if (elect_one()) {
+                            mbar_expect_tx(&full_bar[ws], Cfg::W_STAGE);
+                            tma_load_3d(&maps.w[0], &full_bar[ws], sw, kc * BK, n0, s.widx[tap]);
+                            tma_load_3d(&maps.w[1], &full_bar[ws], sw + Cfg::W_TILE_BYTES, kc * BK, n0, s.widx[tap]);
+                        }
+                        __syncwarp();
                         if (++ws == NW) { ws = 0; wphase ^= 1; }
                     }
                 }
@@ -858,20 +1040,25 @@ modconv_tc_halo_t_kernel(const __grid_constant__ TcMaps maps, const __grid_const
                         const uint64_t d_xh = make_halo_t_desc(sa + xoff), d_xl = make_halo_t_desc(sa + Cfg::A_PAD + xoff);
                         const uint32_t sw = smem_u32(smem_w + ws * Cfg::W_STAGE);
                         const uint64_t d_wh = make_smem_desc<Cfg::ROW>(sw), d_wl = make_smem_desc<Cfg::ROW>(sw + Cfg::W_TILE_BYTES);
+                        if (elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < BK / UMMA_K; ++k) {
-                            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
-                            umma_bf16(d_tmem, d_wh + koff, d_xh + koff, idesc, (kc | tap | k) ? 1u : 0u, one);
-                            umma_bf16(d_tmem, d_wl + koff, d_xh + koff, idesc, 1u, one);
-                            umma_bf16(d_tmem, d_wh + koff, d_xl + koff, idesc, 1u, one);
+                            for (int k = 0; k < BK / UMMA_K; ++k) {
+                                const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+                                umma_bf16(d_tmem, d_wh + koff, d_xh + koff, idesc, (kc | tap | k) ? 1u : 0u);
+                                umma_bf16(d_tmem, d_wl + koff, d_xh + koff, idesc, 1u);
+                                umma_bf16(d_tmem, d_wh + koff, d_xl + koff, idesc, 1u);
+                            }
+                            umma_commit(&empty_bar[ws]);
+                            if (tap == s.ntaps - 1) {
+                                umma_commit(&aempty_bar[as]);
+                                if (kc == a.kchunks - 1) umma_commit(&tfull_bar[acc]);
+                            }
                         }
-                        umma_commit(&empty_bar[ws], one);
+                        __syncwarp();
                         if (++ws == NW) { ws = 0; wphase ^= 1; }
                     }
-                    umma_commit(&aempty_bar[as], one);
                     if (++as == NA) { as = 0; aphase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc], one);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -979,10 +1166,19 @@ struct BlurSplitArgs {
     const float* s_next; bf16* next_hi; bf16* next_lo;   // [B][OH][OW][C]
     int act;                              // apply lrelu(0.2)*sqrt2 (StyledConv) or blur only (bare ModulatedConv2d)
 };
-constexpr int BS_TH = 8, BS_TW = 16, BS_C = 64;
-constexpr int BS_IH = BS_TH + 3, BS_IW = BS_TW + 3;
-constexpr int BS_OPITCH = BS_TH * BS_TW + 1;                      // 129: transposing writes are 2-way conflicted at worst
-constexpr int BS_SMEM = BS_IH * BS_IW * BS_C * 4;                 // 53,504 B
+// Tile geometry by channel block CB: 64 channels -> 8 x 16 output pixels, a warp owns one column pair (32 lanes x 2
+// channels); 32 channels (the 1024^2 layer) -> 8 x 32 output pixels, a warp owns TWO column pairs (16 lanes x 2 channels
+// each), so no lane idles and the NCHW capture is written as full 128 B rows.
+constexpr int BS_TH = 8, BS_IH = BS_TH + 3;
+template <int CB> struct BlurGeo {
+    static constexpr int LPG = CB / 2;                       // lanes per column-pair group
+    static constexpr int GROUPS = 32 / LPG;                  // column pairs per warp
+    static constexpr int TW = 8 * GROUPS * 2;                // 16 / 32 output columns per block (8 warps)
+    static constexpr int IW = TW + 3;
+    static constexpr int OPITCH = BS_TH * TW + 1;            // transposing writes are 2-way conflicted at worst
+    static constexpr int SMEM = BS_IH * IW * CB * 4;         // 53,504 B (CB 64) / 49,280 B (CB 32)
+    static_assert(CB * OPITCH * 4 <= SMEM, "the transposed output must fit in the input tile");
+};
 
 __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
@@ -1008,31 +1204,34 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
 }
 __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
 
-// Block = 8x16 output pixels x 64 channels, 8 warps; lane = 2 channels (LDS.64, packed fp32x2 math, 32-bit bf16x2
-// stores).  The 11x19x64 fp32 input tile is staged with 16-byte cp.async (all chunks in flight at once).  Warp w owns
-// the output column pair (2w, 2w+1) and walks down the rows, sharing the 5 input columns the pair needs.  Separable
-// taps (the reference's [1,3,3,1] outer product always is): a horizontal 4-tap pass per input row, then a vertical
-// 4-tap pass over a sliding register window = 8 FMAs per output instead of 16; a non-separable `blur.kernel` takes the
-// generic 16-tap path.  The bf16 hi/lo NHWC planes are written straight from registers (128 B per pixel per plane);
-// the fp32 NCHW capture goes through a shared-memory transpose that re-uses the input tile's storage.  All index
-// arithmetic is hoisted out of the per-element loops: the kernel is HBM-bound only if its instruction count is small.
-// TMA = true: the input tile comes from ONE TMA box load (fp32 NHWC scratch, out-of-bounds rows / columns / channels are
-// zero-filled by the tensor map) into a two-deep ring, issued a tile ahead by thread 0: no per-thread staging
-// instructions (11 % of the kernel's issue slots) and the load of tile i+1 overlaps the math and stores of tile i.
-template <bool SEP, int RING>     // RING: 0 = cp.async staging, 1 / 2 = TMA ring depth
+// Block = 8 x TW output pixels x CB channels, 8 warps; lane = 2 channels (LDS.64, packed fp32x2 math, 32-bit bf16x2
+// stores).  A column-pair group of lanes owns the output columns (px, px+1) and walks down the rows, sharing the 5 input
+// columns the pair needs.  Separable taps (the reference's [1,3,3,1] outer product always is): a horizontal 4-tap pass per
+// input row, then a vertical 4-tap pass over a sliding register window = 8 FMAs per output instead of 16; a non-separable
+// `blur.kernel` takes the generic 16-tap path.  The bf16 hi/lo NHWC planes are written straight from registers; the fp32
+// NCHW capture goes through a shared-memory transpose that re-uses the input tile's storage.  All index arithmetic is
+// hoisted out of the per-element loops: the kernel is HBM-bound only if its instruction count is small.
+// RING > 0: the input tile comes from ONE TMA box load (fp32 NHWC scratch, out-of-bounds rows / columns / channels are
+// zero-filled by the tensor map) into a ring, issued a tile ahead by thread 0: no per-thread staging instructions and the
+// load of tile i+1 overlaps the math and stores of tile i.  RING = 0 (cp.async staging) exists for CB = 64 only.
+template <bool SEP, int RING, int CB>     // RING: 0 = cp.async staging, 1 / 2 = TMA ring depth
 __global__ void __launch_bounds__(256, RING == 2 ? 2 : 3) blur_act_split_kernel(BlurSplitArgs a, const __grid_constant__ CUtensorMap in_map) {
+    using G = BlurGeo<CB>;
     constexpr bool TMA = RING > 0;
-    extern __shared__ __align__(128) float stile_raw[];    // [11*19][64] fp32 (x2 with TMA); re-used as sout[64][129]
+    constexpr int TW = G::TW, IW = G::IW, LPG = G::LPG, OPITCH = G::OPITCH, TILE_BYTES = G::SMEM;
+    static_assert(TMA || CB == 64, "cp.async staging is only written for 64-channel blocks");
+    extern __shared__ __align__(128) float stile_raw[];    // [11*IW][CB] fp32 (x2 with TMA); re-used as sout[CB][OPITCH]
     __shared__ float sk[16], skx[4], sky[4];
-    __shared__ float snz[BS_TH * BS_TW];
+    __shared__ float snz[BS_TH * TW];
     __shared__ uint64_t tma_bar[2];
     float* stile = TMA ? (float*)(((uintptr_t)stile_raw + 127) & ~(uintptr_t)127) : stile_raw;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int grp = lane / LPG, cl = lane - grp * LPG;      // column-pair group of this lane, channel pair inside the block
     if (tid < 16) sk[tid] = a.blur_k[(3 - tid / 4) * 4 + (3 - tid % 4)];   // flipped taps
     __syncthreads();
     if (tid < 4) { sky[tid] = sk[tid * 4]; skx[tid] = SEP ? sk[tid] / sk[0] : 0.0f; }   // k[i][j] = sky[i] * skx[j]
-    const int tiles_x = (a.OW + BS_TW - 1) / BS_TW, tiles_y = (a.OH + BS_TH - 1) / BS_TH;
-    const int cgroups = (a.C + BS_C - 1) / BS_C;     // C = 32 (1024^2 layers): half of the lanes idle
+    const int tiles_x = (a.OW + TW - 1) / TW, tiles_y = (a.OH + BS_TH - 1) / BS_TH;
+    const int cgroups = (a.C + CB - 1) / CB;
     const int64_t total = (int64_t)a.batch * tiles_y * tiles_x * cgroups;
     const int part = tid & 15;
     float* const ring0 = stile;
@@ -1041,7 +1240,7 @@ __global__ void __launch_bounds__(256, RING == 2 ? 2 : 3) blur_act_split_kernel(
         int64_t r = tile / cgroups;
         const int tx = (int)(r % tiles_x); r /= tiles_x;
         const int ty = (int)(r % tiles_y);
-        b = (int)(r / tiles_y); y0 = ty * BS_TH; x0 = tx * BS_TW; c0 = cg * BS_C;
+        b = (int)(r / tiles_y); y0 = ty * BS_TH; x0 = tx * TW; c0 = cg * CB;
     };
     if (TMA) {
         if (tid == 0) {
@@ -1050,7 +1249,7 @@ __global__ void __launch_bounds__(256, RING == 2 ? 2 : 3) blur_act_split_kernel(
             if (RING == 2 && (int64_t)blockIdx.x < total) {
                 int b, y0, x0, c0;
                 tile_coords(blockIdx.x, b, y0, x0, c0);
-                mbar_expect_tx(&tma_bar[0], BS_SMEM);
+                mbar_expect_tx(&tma_bar[0], TILE_BYTES);
                 tma_load_4d(&in_map, &tma_bar[0], ring0, c0, x0 - 1, y0 - 1, b);
             }
         }
@@ -1059,9 +1258,9 @@ __global__ void __launch_bounds__(256, RING == 2 ? 2 : 3) blur_act_split_kernel(
     for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
         int b, y0, x0, c0;
         tile_coords(tile, b, y0, x0, c0);
-        if (RING == 2) stile = ring0 + (it & 1) * (BS_SMEM / 4);
+        if (RING == 2) stile = ring0 + (it & 1) * (TILE_BYTES / 4);
         const uint32_t stile_u32 = smem_u32(stile);
-        const float2* st2 = reinterpret_cast<const float2*>(stile);    // [pix][32 lanes]
+        const float2* st2 = reinterpret_cast<const float2*>(stile);    // [pix][CB / 2 lanes]
         __syncthreads();     // previous tile's transpose reads are done (and the tap tables are visible)
         if (TMA) {
             // the other ring slot held the previous tile (its transposed output was just consumed): refill it a tile ahead
@@ -1069,16 +1268,16 @@ __global__ void __launch_bounds__(256, RING == 2 ? 2 : 3) blur_act_split_kernel(
                 int nb, ny0, nx0, nc0;
                 tile_coords(tile + gridDim.x, nb, ny0, nx0, nc0);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy accesses of that slot are done
-                mbar_expect_tx(&tma_bar[(it + 1) & 1], BS_SMEM);
-                tma_load_4d(&in_map, &tma_bar[(it + 1) & 1], ring0 + ((it + 1) & 1) * (BS_SMEM / 4), nc0, nx0 - 1, ny0 - 1, nb);
+                mbar_expect_tx(&tma_bar[(it + 1) & 1], TILE_BYTES);
+                tma_load_4d(&in_map, &tma_bar[(it + 1) & 1], ring0 + ((it + 1) & 1) * (TILE_BYTES / 4), nc0, nx0 - 1, ny0 - 1, nb);
             }
             if (RING == 1 && tid == 0) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(&tma_bar[0], BS_SMEM);
+                mbar_expect_tx(&tma_bar[0], TILE_BYTES);
                 tma_load_4d(&in_map, &tma_bar[0], ring0, c0, x0 - 1, y0 - 1, b);
             }
-            if (tid < BS_TH * BS_TW) {
-                const int oy = y0 + (tid >> 4), ox = x0 + (tid & 15);
+            if (tid < BS_TH * TW) {
+                const int oy = y0 + tid / TW, ox = x0 + tid % TW;
                 snz[tid] = (a.noise && oy < a.OH && ox < a.OW) ? a.noise_w * __ldg(a.noise + (int64_t)b * a.noise_bstride + (int64_t)oy * a.OW + ox) : 0.0f;
             }
             if (RING == 2) mbar_wait(&tma_bar[it & 1], (uint32_t)((it >> 1) & 1), nullptr, 0);
@@ -1088,17 +1287,17 @@ __global__ void __launch_bounds__(256, RING == 2 ? 2 : 3) blur_act_split_kernel(
         {
             const float* src_base = a.in + (int64_t)b * a.IH * a.IW * a.C + c0 + part * 4;
 #pragma unroll 2
-            for (int pi = tid >> 4; pi < BS_IH * BS_IW; pi += 16) {
-                const int ry = pi / BS_IW, rx = pi - ry * BS_IW;
+            for (int pi = tid >> 4; pi < BS_IH * IW; pi += 16) {
+                const int ry = pi / IW, rx = pi - ry * IW;
                 const int iy = y0 + ry - 1, ix = x0 + rx - 1;
-                const uint32_t dst = stile_u32 + (uint32_t)(pi * BS_C + part * 4) * 4u;
+                const uint32_t dst = stile_u32 + (uint32_t)(pi * CB + part * 4) * 4u;
                 if ((unsigned)iy < (unsigned)a.IH && (unsigned)ix < (unsigned)a.IW && c0 + part * 4 < a.C)
                     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src_base + (int64_t)(iy * a.IW + ix) * a.C) : "memory");
                 else
                     asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "f"(0.0f) : "memory");
             }
-            if (tid < BS_TH * BS_TW) {
-                const int oy = y0 + (tid >> 4), ox = x0 + (tid & 15);
+            if (tid < BS_TH * TW) {
+                const int oy = y0 + tid / TW, ox = x0 + tid % TW;
                 snz[tid] = (a.noise && oy < a.OH && ox < a.OW) ? a.noise_w * __ldg(a.noise + (int64_t)b * a.noise_bstride + (int64_t)oy * a.OW + ox) : 0.0f;
             }
         }
@@ -1108,21 +1307,21 @@ __global__ void __launch_bounds__(256, RING == 2 ? 2 : 3) blur_act_split_kernel(
 
         // ---- blur: column pair (px, px+1), rows top to bottom
         float2 res[2][BS_TH];
+        const int px = (warp * G::GROUPS + grp) * 2;
         {
-            const int px = warp * 2;
-            const bool chok = c0 + 2 * lane < a.C;
-            const float2 bias = (chok && a.bias) ? *reinterpret_cast<const float2*>(a.bias + c0 + 2 * lane) : make_float2(0.f, 0.f);
-            const float2 sn = (a.s_next && chok) ? *reinterpret_cast<const float2*>(a.s_next + (int64_t)b * a.C + c0 + 2 * lane) : make_float2(0.f, 0.f);
+            const bool chok = c0 + 2 * cl < a.C;
+            const float2 bias = (chok && a.bias) ? *reinterpret_cast<const float2*>(a.bias + c0 + 2 * cl) : make_float2(0.f, 0.f);
+            const float2 sn = (a.s_next && chok) ? *reinterpret_cast<const float2*>(a.s_next + (int64_t)b * a.C + c0 + 2 * cl) : make_float2(0.f, 0.f);
             const bool colok0 = chok && x0 + px < a.OW, colok1 = chok && x0 + px + 1 < a.OW;
-            // NHWC element offset of (b, y0, x0+px, c0+2*lane); advances by OW*C per row, C per column
-            const int64_t off0 = (((int64_t)b * a.OH + y0) * a.OW + x0 + px) * a.C + c0 + 2 * lane;
+            // NHWC element offset of (b, y0, x0+px, c0+2*cl); advances by OW*C per row, C per column
+            const int64_t off0 = (((int64_t)b * a.OH + y0) * a.OW + x0 + px) * a.C + c0 + 2 * cl;
             const int64_t row_stride = (int64_t)a.OW * a.C;
             float2 win[2][4][SEP ? 1 : 4];
 #pragma unroll
             for (int rr = 0; rr < BS_IH; ++rr) {
                 float2 in5[5];
 #pragma unroll
-                for (int j = 0; j < 5; ++j) in5[j] = st2[(rr * BS_IW + px + j) * 32 + lane];
+                for (int j = 0; j < 5; ++j) in5[j] = st2[(rr * IW + px + j) * LPG + cl];
 #pragma unroll
                 for (int cx = 0; cx < 2; ++cx) {
 #pragma unroll
@@ -1154,7 +1353,7 @@ __global__ void __launch_bounds__(256, RING == 2 ? 2 : 3) blur_act_split_kernel(
 #pragma unroll
                                 for (int kx = 0; kx < 4; ++kx) v = ffma2(win[cx][ky][kx], splat2(sk[ky * 4 + kx]), v);
                         }
-                        v = fadd2(fadd2(v, splat2(snz[py * BS_TW + px + cx])), bias);
+                        v = fadd2(fadd2(v, splat2(snz[py * TW + px + cx])), bias);
                         // lrelu(x)*sqrt2 = max(x*sqrt2, x*0.2*sqrt2)
                         if (a.act) {
                             const float2 p = fmul2(v, splat2(1.41421356237309504880f)), q = fmul2(v, splat2(0.2f * 1.41421356237309504880f));
@@ -1175,33 +1374,34 @@ __global__ void __launch_bounds__(256, RING == 2 ? 2 : 3) blur_act_split_kernel(
             }
         }
         __syncthreads();     // everyone is done reading the input tile
-        float* sout = stile; // [64][129]
+        float* sout = stile; // [CB][OPITCH]
         {
-            float* w0 = sout + (2 * lane) * BS_OPITCH + warp * 2;
+            float* w0 = sout + (2 * cl) * OPITCH + px;
 #pragma unroll
             for (int cx = 0; cx < 2; ++cx)
 #pragma unroll
                 for (int py = 0; py < BS_TH; ++py) {
-                    w0[py * BS_TW + cx] = res[cx][py].x;
-                    w0[BS_OPITCH + py * BS_TW + cx] = res[cx][py].y;
+                    w0[py * TW + cx] = res[cx][py].x;
+                    w0[OPITCH + py * TW + cx] = res[cx][py].y;
                 }
         }
         __syncthreads();
-        // ---- NCHW capture: warp -> channels warp, warp+8, ...; lanes -> 2 rows x 16 pixels, 4 row pairs
+        // ---- NCHW capture: warp -> channels warp, warp+8, ...; a pass of the 32 lanes covers 32 / TW rows of TW pixels
         {
-            const int ox = x0 + (lane & 15), oyb = y0 + (lane >> 4);
+            constexpr int RPP = 32 / TW;                    // rows per pass: 2 (TW 16) or 1 (TW 32)
+            const int ox = x0 + (lane % TW), oyb = y0 + lane / TW;
             const bool colok = ox < a.OW;
             const int64_t plane = (int64_t)a.OH * a.OW;
             float* dst = a.out_f32 + ((int64_t)b * a.C + c0 + warp) * plane + (int64_t)oyb * a.OW + ox;
-            const float* sp = sout + warp * BS_OPITCH + lane;
+            const float* sp = sout + warp * OPITCH + lane;
 #pragma unroll
-            for (int j = 0; j < BS_C / 8; ++j) {
+            for (int j = 0; j < CB / 8; ++j) {
                 if (c0 + warp + 8 * j >= a.C) break;
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (colok && oyb + 2 * i < a.OH) dst[(int64_t)(2 * i) * a.OW] = sp[32 * i];
+                for (int i = 0; i < BS_TH / RPP; ++i)
+                    if (colok && oyb + RPP * i < a.OH) dst[(int64_t)(RPP * i) * a.OW] = sp[32 * i];
                 dst += 8 * plane;
-                sp += 8 * BS_OPITCH;
+                sp += 8 * OPITCH;
             }
         }
     }
@@ -1510,6 +1710,21 @@ static int launch_tc_halo(const TcMaps& maps, const TcKernelArgs& a, cudaStream_
     return SIS_OK;
 }
 
+template <int BN, int BK, bool UP4>
+static int launch_tc_halo_rw(const TcMaps& maps, const TcKernelArgs& a, cudaStream_t stream) {
+    using Cfg = TcHaloRwCfg<BN, BK, UP4>;
+    auto kern = modconv_tc_halo_rw_kernel<BN, BK, UP4>;
+    static bool configured = false;
+    if (!configured) {
+        SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    const int grid = a.total_tiles < kNumSMs ? a.total_tiles : kNumSMs;
+    kern<<<grid, tc_threads(), Cfg::SMEM_BYTES, stream>>>(maps, a);
+    SIS_CHECK_LAUNCH();
+    return SIS_OK;
+}
+
 static int launch_tc_halo_t(const TcMaps& maps, const TcKernelArgs& a, cudaStream_t stream) {
     using Cfg = TcHaloTCfg;
     static bool configured = false;
@@ -1562,6 +1777,38 @@ static int launch_tc_any(int BN, int th, int tw, int tb, const TcMaps& maps, con
 }
 
 // Second half of an up-sampling layer: Blur(4x4, pad 1) + noise + bias + lrelu over the fp32 NHWC scratch.
+template <int CB>
+static int launch_blur_split(const BlurSplitArgs& bs, int ring, bool sep, cudaStream_t stream) {
+    using G = BlurGeo<CB>;
+    if (CB != 64 && ring == 0) ring = 2;                   // cp.async staging exists for 64-channel blocks only
+    static int blocks_per_sm[6] = {0, 0, 0, 0, 0, 0};
+    const int variant = (sep ? 1 : 0) + 2 * ring;
+    const size_t smem = ring == 2 ? 2 * (size_t)G::SMEM + 128 : ring == 1 ? (size_t)G::SMEM + 128 : (size_t)G::SMEM;
+    void (*kern)(BlurSplitArgs, const CUtensorMap);
+    if (CB == 64 && ring == 0) kern = sep ? blur_act_split_kernel<true, 0, 64> : blur_act_split_kernel<false, 0, 64>;
+    else if (ring == 1) kern = sep ? blur_act_split_kernel<true, 1, CB> : blur_act_split_kernel<false, 1, CB>;
+    else kern = sep ? blur_act_split_kernel<true, 2, CB> : blur_act_split_kernel<false, 2, CB>;
+    if (!blocks_per_sm[variant]) {
+        SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        SIS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[variant], kern, 256, smem));
+        if (blocks_per_sm[variant] < 1) blocks_per_sm[variant] = 1;
+    }
+    CUtensorMap in_map;
+    memset(&in_map, 0, sizeof(in_map));
+    if (ring > 0) {
+        const uint64_t dims[4] = {(uint64_t)bs.C, (uint64_t)bs.IW, (uint64_t)bs.IH, (uint64_t)bs.batch};
+        const uint32_t box[4] = {(uint32_t)CB, (uint32_t)G::IW, (uint32_t)BS_IH, 1};
+        SIS_PROPAGATE(make_map_f32(&in_map, bs.in, 4, dims, box));
+    }
+    const int64_t total = (int64_t)bs.batch * ceil_div(bs.OH, BS_TH) * ceil_div(bs.OW, G::TW) * ceil_div(bs.C, CB);
+    const int grid = (int)std::min<int64_t>(total, (int64_t)kNumSMs * blocks_per_sm[variant]);   // exactly one resident wave
+    ProfScope prof(PROF_BLUR_SPLIT, stream);
+    kern<<<grid, 256, smem, stream>>>(bs, in_map);
+    SIS_CHECK_LAUNCH();
+    return SIS_OK;
+}
+
+// Second half of an up-sampling layer: Blur(4x4, pad 1) + noise + bias + lrelu over the fp32 NHWC scratch.
 static int tc_blur_after_upconv(TcWorkspace& ws, const TcConvCall& call, cudaStream_t stream) {
     const int B = call.batch, H = call.res_in;
     BlurSplitArgs bs;
@@ -1573,32 +1820,9 @@ static int tc_blur_after_upconv(TcWorkspace& ws, const TcConvCall& call, cudaStr
     SIS_REQUIRE(bs.C % 32 == 0, "tc_modconv: the blur pass needs Cout %% 32 == 0 (got %d)", bs.C);
     static int ring_env = env_int("SIS_BLUR_TMA", 2);      // 0: cp.async, 1: TMA single buffer (3 blocks/SM), 2: TMA ring of 2
     const int ring = (bs.C * 4) % 16 == 0 ? (ring_env < 0 ? 0 : ring_env > 2 ? 2 : ring_env) : 0;
-    const bool tma = ring > 0;
-    static int blocks_per_sm[6] = {0, 0, 0, 0, 0, 0};
-    const int sep = call.blur_separable ? 1 : 0;
-    const int variant = sep + 2 * ring;
-    const size_t smem = ring == 2 ? 2 * (size_t)BS_SMEM + 128 : ring == 1 ? (size_t)BS_SMEM + 128 : (size_t)BS_SMEM;
-    auto kern = ring == 2 ? (sep ? blur_act_split_kernel<true, 2> : blur_act_split_kernel<false, 2>)
-              : ring == 1 ? (sep ? blur_act_split_kernel<true, 1> : blur_act_split_kernel<false, 1>)
-                          : (sep ? blur_act_split_kernel<true, 0> : blur_act_split_kernel<false, 0>);
-    if (!blocks_per_sm[variant]) {
-        SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        SIS_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[variant], kern, 256, smem));
-        if (blocks_per_sm[variant] < 1) blocks_per_sm[variant] = 1;
-    }
-    CUtensorMap in_map;
-    memset(&in_map, 0, sizeof(in_map));
-    if (tma) {
-        const uint64_t dims[4] = {(uint64_t)bs.C, (uint64_t)bs.IW, (uint64_t)bs.IH, (uint64_t)B};
-        const uint32_t box[4] = {(uint32_t)BS_C, (uint32_t)BS_IW, (uint32_t)BS_IH, 1};
-        SIS_PROPAGATE(make_map_f32(&in_map, bs.in, 4, dims, box));
-    }
-    const int64_t total = (int64_t)B * ceil_div(bs.OH, BS_TH) * ceil_div(bs.OW, BS_TW) * ceil_div(bs.C, BS_C);
-    const int grid = (int)std::min<int64_t>(total, (int64_t)kNumSMs * blocks_per_sm[variant]);   // exactly one resident wave
-    ProfScope prof(PROF_BLUR_SPLIT, stream);
-    kern<<<grid, 256, smem, stream>>>(bs, in_map);
-    SIS_CHECK_LAUNCH();
-    return SIS_OK;
+    // 32-channel blocks when the channel count is an odd multiple of 32 (the 1024^2 layer): no idle lanes
+    if (bs.C % 64 != 0 && bs.OW >= 32) return launch_blur_split<32>(bs, ring, call.blur_separable, stream);
+    return launch_blur_split<64>(bs, ring, call.blur_separable, stream);
 }
 
 int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, cudaStream_t stream) {
@@ -1752,6 +1976,9 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
         s.tiles_y = ceil_div(H + 1, HALO_TH); s.tiles_x = ceil_div(H + 1, HALO_TW); s.tile_begin = 0;
         const int64_t m_tiles = (int64_t)B * s.tiles_y * s.tiles_x;
         const int CG = (cg_env == 2 && BN == 64 && m_tiles >= 2 * kNumSMs) ? 2 : 1;
+        // 64 -> 32: all nine weight tiles stay resident in shared memory (SIS_TC_RW=0 streams them per tap)
+        static int rw_env = env_int("SIS_TC_RW", 1) != 0;
+        const bool rw = rw_env && BN == 32 && BK == 64 && a.kchunks == 1;
         a.total_tiles = (int)ceil_div64(m_tiles, CG);
         a.out_f32 = call.upconv_tmp; a.out_h = 2 * H + 1; a.out_w = 2 * H + 1;
         TcMaps maps;
@@ -1766,7 +1993,8 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
         SIS_PROPAGATE(make_map(&maps.w[1], w.lo, 3, wdims, wbox, BK * 2));
         {
             ProfScope prof(conv_cat, stream);
-            SIS_PROPAGATE(launch_tc_halo_up4(BN, BK, CG, maps, a, stream));
+            if (rw) SIS_PROPAGATE((launch_tc_halo_rw<32, 64, true>(maps, a, stream)));
+            else SIS_PROPAGATE(launch_tc_halo_up4(BN, BK, CG, maps, a, stream));
         }
         return tc_blur_after_upconv(ws, call, stream);
     }
@@ -1902,7 +2130,9 @@ int tc_modconv(TcWorkspace& ws, const TcConvWeights& w, const TcConvCall& call, 
     int st;
     {
         ProfScope prof(conv_cat, stream);
-        if (halo) st = (CG == 2) ? launch_tc_halo_any<2>(BN, BK, maps, a, stream) : launch_tc_halo_any<1>(BN, BK, maps, a, stream);
+        static int rw_env = env_int("SIS_TC_RW", 1) != 0;
+        if (halo && rw_env && BN == 32 && BK == 32 && CG == 1 && a.kchunks == 1 && n_tiles == 1) st = launch_tc_halo_rw<32, 32, false>(maps, a, stream);
+        else if (halo) st = (CG == 2) ? launch_tc_halo_any<2>(BN, BK, maps, a, stream) : launch_tc_halo_any<1>(BN, BK, maps, a, stream);
         else if (CG == 2) st = (BK == 64) ? launch_tc_any<64, 2>(BN, th, tw, tb, maps, a, stream) : launch_tc_any<32, 2>(BN, th, tw, tb, maps, a, stream);
         else st = (BK == 64) ? launch_tc_any<64, 1>(BN, th, tw, tb, maps, a, stream) : launch_tc_any<32, 1>(BN, th, tw, tb, maps, a, stream);
     }
