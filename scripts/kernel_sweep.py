@@ -20,8 +20,13 @@ def peak():
     return json.load(open(p))['hbm_gbs'] if os.path.exists(p) else 6650.0
 
 
+NCU = os.environ.get('SIS_SWEEP_NCU') == '1'      # under ncu: one launch per case, so launch order = case order
+
+
 def time_op(fn, inputs, iters=10, warm=3):
     """fn(*inputs[i % len(inputs)]); distinct buffers rotate so that every iteration misses L2."""
+    if NCU:
+        iters, warm = 1, 0
     for i in range(warm):
         fn(*inputs[i % len(inputs)])
     torch.cuda.synchronize()

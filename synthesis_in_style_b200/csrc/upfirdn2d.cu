@@ -323,7 +323,11 @@ extern "C" int sis_upfirdn2d(void* d_out, const void* d_x, const void* d_kernel,
     SIS_REQUIRE(d_x || (int64_t)in_h * in_w * minor * major == 0, "upfirdn2d: input must be a CUDA tensor (null pointer)");
 
     bool done = false;
-    if (dtype == SIS_F32 && minor == 1 && up_x == up_y && down_x == down_y && in_h > 0 && in_w > 0) {
+    // Small planes (the 4^2 ... 16^2 maps): a 64-wide tile per plane pair would leave most of a block idle and the op is
+    // latency-bound; the one-thread-per-output kernel below (same y-outer / x-inner FMA chain over the real taps, i.e. the
+    // same bits) keeps every lane busy.
+    const bool small_plane = (int64_t)p.out_h * p.out_w <= 32 * 32;
+    if (dtype == SIS_F32 && minor == 1 && up_x == up_y && down_x == down_y && in_h > 0 && in_w > 0 && !small_plane) {
         float* o = (float*)d_out; const float* x = (const float*)d_x; const float* k = (const float*)d_kernel;
         const int kmax = kernel_h > kernel_w ? kernel_h : kernel_w;
         done = true;
