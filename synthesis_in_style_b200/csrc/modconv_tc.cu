@@ -1203,6 +1203,20 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
     return d;
 }
 __device__ __forceinline__ float2 splat2(float v) { return make_float2(v, v); }
+// explicit shared-space accesses by 32-bit address: the tile pointer is picked from a ring at run time, and through a
+// generic pointer every access becomes LD.E / ST.E with 64-bit address arithmetic (measured: ~250 extra integer instructions
+// per tile and generic-path loads in a kernel that is co-limited by issue)
+__device__ __forceinline__ float2 lds_f2(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float lds_f1(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f1(uint32_t addr, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory"); }
 
 // Block = 8 x TW output pixels x CB channels, 8 warps; lane = 2 channels (LDS.64, packed fp32x2 math, 32-bit bf16x2
 // stores).  A column-pair group of lanes owns the output columns (px, px+1) and walks down the rows, sharing the 5 input
@@ -1259,8 +1273,7 @@ __global__ void __launch_bounds__(256, RING == 2 ? 2 : 3) blur_act_split_kernel(
         int b, y0, x0, c0;
         tile_coords(tile, b, y0, x0, c0);
         if (RING == 2) stile = ring0 + (it & 1) * (TILE_BYTES / 4);
-        const uint32_t stile_u32 = smem_u32(stile);
-        const float2* st2 = reinterpret_cast<const float2*>(stile);    // [pix][CB / 2 lanes]
+        const uint32_t stile_u32 = smem_u32(stile);                    // tile: [pix][CB / 2 lanes] float2
         __syncthreads();     // previous tile's transpose reads are done (and the tap tables are visible)
         if (TMA) {
             // the other ring slot held the previous tile (its transposed output was just consumed): refill it a tile ahead
@@ -1308,6 +1321,7 @@ __global__ void __launch_bounds__(256, RING == 2 ? 2 : 3) blur_act_split_kernel(
         // ---- blur: column pair (px, px+1), rows top to bottom
         float2 res[2][BS_TH];
         const int px = (warp * G::GROUPS + grp) * 2;
+        const uint32_t in_base = stile_u32 + (uint32_t)(px * LPG + cl) * 8u;
         {
             const bool chok = c0 + 2 * cl < a.C;
             const float2 bias = (chok && a.bias) ? *reinterpret_cast<const float2*>(a.bias + c0 + 2 * cl) : make_float2(0.f, 0.f);
@@ -1315,13 +1329,19 @@ __global__ void __launch_bounds__(256, RING == 2 ? 2 : 3) blur_act_split_kernel(
             const bool colok0 = chok && x0 + px < a.OW, colok1 = chok && x0 + px + 1 < a.OW;
             // NHWC element offset of (b, y0, x0+px, c0+2*cl); advances by OW*C per row, C per column
             const int64_t off0 = (((int64_t)b * a.OH + y0) * a.OW + x0 + px) * a.C + c0 + 2 * cl;
-            const int64_t row_stride = (int64_t)a.OW * a.C;
+            // plane pointers of this lane's first pixel, in bf16x2 units: + C/2 per column, + OW*C/2 per row.  (Only
+            // dereferenced when the planes are wanted; the stores below are predicated, not branched around.)
+            __nv_bfloat162* ph = reinterpret_cast<__nv_bfloat162*>(a.next_hi + off0);
+            __nv_bfloat162* pl = reinterpret_cast<__nv_bfloat162*>(a.next_lo + off0);
+            const int c2 = a.C >> 1;
+            const int64_t rs2 = ((int64_t)a.OW * a.C) >> 1;
+            const bool st0 = a.s_next != nullptr && colok0, st1 = a.s_next != nullptr && colok1;
             float2 win[2][4][SEP ? 1 : 4];
 #pragma unroll
             for (int rr = 0; rr < BS_IH; ++rr) {
                 float2 in5[5];
 #pragma unroll
-                for (int j = 0; j < 5; ++j) in5[j] = st2[(rr * IW + px + j) * LPG + cl];
+                for (int j = 0; j < 5; ++j) in5[j] = lds_f2(in_base + (uint32_t)((rr * IW + j) * LPG) * 8u);
 #pragma unroll
                 for (int cx = 0; cx < 2; ++cx) {
 #pragma unroll
@@ -1360,29 +1380,30 @@ __global__ void __launch_bounds__(256, RING == 2 ? 2 : 3) blur_act_split_kernel(
                             v = make_float2(fmaxf(p.x, q.x), fmaxf(p.y, q.y));
                         }
                         res[cx][py] = v;
-                        if (a.s_next && rowok && (cx ? colok1 : colok0)) {
-                            const float2 xs = fmul2(v, sn);
-                            const __nv_bfloat162 h = __floats2bfloat162_rn(xs.x, xs.y);
-                            const float2 hf = __bfloat1622float2(h);
-                            const __nv_bfloat162 l = __floats2bfloat162_rn(xs.x - hf.x, xs.y - hf.y);
-                            const int64_t off = off0 + py * row_stride + cx * a.C;
-                            *reinterpret_cast<__nv_bfloat162*>(a.next_hi + off) = h;
-                            *reinterpret_cast<__nv_bfloat162*>(a.next_lo + off) = l;
+                        const float2 xs = fmul2(v, sn);
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(xs.x, xs.y);
+                        const float2 hf = __bfloat1622float2(h);
+                        const __nv_bfloat162 l = __floats2bfloat162_rn(xs.x - hf.x, xs.y - hf.y);
+                        if (rowok && (cx ? st1 : st0)) {
+                            ph[cx * c2] = h;
+                            pl[cx * c2] = l;
                         }
                     }
+                    ph += rs2;
+                    pl += rs2;
                 }
             }
         }
         __syncthreads();     // everyone is done reading the input tile
-        float* sout = stile; // [CB][OPITCH]
+        // sout = the tile's storage again, [CB][OPITCH] fp32
         {
-            float* w0 = sout + (2 * cl) * OPITCH + px;
+            const uint32_t w0 = stile_u32 + (uint32_t)((2 * cl) * OPITCH + px) * 4u;
 #pragma unroll
             for (int cx = 0; cx < 2; ++cx)
 #pragma unroll
                 for (int py = 0; py < BS_TH; ++py) {
-                    w0[py * TW + cx] = res[cx][py].x;
-                    w0[OPITCH + py * TW + cx] = res[cx][py].y;
+                    sts_f1(w0 + (uint32_t)(py * TW + cx) * 4u, res[cx][py].x);
+                    sts_f1(w0 + (uint32_t)(OPITCH + py * TW + cx) * 4u, res[cx][py].y);
                 }
         }
         __syncthreads();
@@ -1393,15 +1414,15 @@ __global__ void __launch_bounds__(256, RING == 2 ? 2 : 3) blur_act_split_kernel(
             const bool colok = ox < a.OW;
             const int64_t plane = (int64_t)a.OH * a.OW;
             float* dst = a.out_f32 + ((int64_t)b * a.C + c0 + warp) * plane + (int64_t)oyb * a.OW + ox;
-            const float* sp = sout + warp * OPITCH + lane;
+            uint32_t sp = stile_u32 + (uint32_t)(warp * OPITCH + lane) * 4u;
 #pragma unroll
             for (int j = 0; j < CB / 8; ++j) {
                 if (c0 + warp + 8 * j >= a.C) break;
 #pragma unroll
                 for (int i = 0; i < BS_TH / RPP; ++i)
-                    if (colok && oyb + RPP * i < a.OH) dst[(int64_t)(RPP * i) * a.OW] = sp[32 * i];
+                    if (colok && oyb + RPP * i < a.OH) dst[(int64_t)(RPP * i) * a.OW] = lds_f1(sp + (uint32_t)(32 * i) * 4u);
                 dst += 8 * plane;
-                sp += 8 * OPITCH;
+                sp += (uint32_t)(8 * OPITCH) * 4u;
             }
         }
     }

@@ -89,6 +89,86 @@ __global__ void __launch_bounds__(256) upfirdn2d_generic_kernel(T* __restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------ small planes
+// Planes of at most 32 x 32 outputs (the 4^2 ... 32^2 maps; minor == 1, fp32, any up / down / taps).  A 64-wide tile per
+// plane pair would leave most of a block idle there, and one thread per output straight from global memory is bound by
+// its 64-bit index arithmetic and per-tap bounds checks (measured: 0.3 TB/s at 32^2).  Here a block owns PB consecutive
+// planes: their inputs are ONE contiguous span of global memory (coalesced loads) scattered into zero-padded planes in
+// shared memory, so the tap loops carry no bounds checks and all index arithmetic is 32-bit; the outputs of the PB planes
+// are one contiguous span again.  Same FMA chain per output as the generic kernel (real taps only, y outer, x inner).
+struct SmallPlaneGeom {
+    int px0, py0, pw, ph;        // padded input window: columns px0 .. px0+pw-1, rows py0 .. py0+ph-1 (zero outside the plane)
+    int planes_per_block;
+};
+
+__global__ void __launch_bounds__(256) upfirdn2d_small_plane_kernel(float* __restrict__ out, const float* __restrict__ in,
+                                                                   const float* __restrict__ kernel, UpfirdnParams p,
+                                                                   SmallPlaneGeom g) {
+    extern __shared__ float sp_smem[];
+    float* sk = sp_smem;                                   // [kernel_h][kernel_w], flipped
+    float* sin = sp_smem + p.kernel_h * p.kernel_w;        // [PB][ph][pw]
+    const int tid = threadIdx.x;
+    const int plane_in = p.in_h * p.in_w, plane_pad = g.ph * g.pw, plane_out = p.out_h * p.out_w;
+    for (int t = tid; t < p.kernel_h * p.kernel_w; t += 256) {
+        int ky = t / p.kernel_w, kx = t - ky * p.kernel_w;
+        sk[t] = kernel[(p.kernel_h - 1 - ky) * p.kernel_w + (p.kernel_w - 1 - kx)];
+    }
+    const int64_t groups = (p.major + g.planes_per_block - 1) / g.planes_per_block;
+    for (int64_t grp = blockIdx.x; grp < groups; grp += gridDim.x) {
+        const int64_t plane0 = grp * g.planes_per_block;
+        const int np = (int)(p.major - plane0 < g.planes_per_block ? p.major - plane0 : g.planes_per_block);
+        __syncthreads();                                   // previous group's reads are done
+        for (int i = tid; i < np * plane_pad; i += 256) sin[i] = 0.0f;
+        __syncthreads();
+        const float* src = in + plane0 * plane_in;
+        for (int i = tid; i < np * plane_in; i += 256) {
+            const int pl = i / plane_in, r = i - pl * plane_in;
+            const int iy = r / p.in_w, ix = r - iy * p.in_w;
+            const int sy = iy - g.py0, sx = ix - g.px0;
+            if (sy >= 0 && sy < g.ph && sx >= 0 && sx < g.pw) sin[pl * plane_pad + sy * g.pw + sx] = src[i];
+        }
+        __syncthreads();
+        float* dst = out + plane0 * plane_out;
+        for (int o = tid; o < np * plane_out; o += 256) {
+            const int pl = o / plane_out, r = o - pl * plane_out;
+            const int oy = r / p.out_w, ox = r - oy * p.out_w;
+            const int mid_x = ox * p.down_x + p.up_x - 1 - p.pad_x0, mid_y = oy * p.down_y + p.up_y - 1 - p.pad_y0;
+            const int in_x0 = floor_div(mid_x, p.up_x), in_y0 = floor_div(mid_y, p.up_y);
+            const int kx0 = (in_x0 + 1) * p.up_x - mid_x - 1, ky0 = (in_y0 + 1) * p.up_y - mid_y - 1;
+            const float* row = sin + pl * plane_pad + (in_y0 - g.py0) * g.pw + (in_x0 - g.px0);
+            float v = 0.0f;
+            for (int ky = ky0; ky < p.kernel_h; ky += p.up_y, row += g.pw) {
+                const float* a = row;
+                const float* kr = sk + ky * p.kernel_w;
+                for (int kx = kx0; kx < p.kernel_w; kx += p.up_x, ++a) v = __fmaf_rn(*a, kr[kx], v);
+            }
+            dst[o] = v;
+        }
+    }
+}
+
+// false when the padded planes do not fit (the caller falls through to the other paths)
+static bool launch_small_plane(float* out, const float* in, const float* kernel, const UpfirdnParams& p, cudaStream_t stream) {
+    auto first = [](int o, int down, int up, int pad0) { return floor_div(o * down + up - 1 - pad0, up); };
+    SmallPlaneGeom g;
+    g.px0 = first(0, p.down_x, p.up_x, p.pad_x0);
+    g.py0 = first(0, p.down_y, p.up_y, p.pad_y0);
+    g.pw = first(p.out_w - 1, p.down_x, p.up_x, p.pad_x0) + ceil_div(p.kernel_w, p.up_x) - g.px0;
+    g.ph = first(p.out_h - 1, p.down_y, p.up_y, p.pad_y0) + ceil_div(p.kernel_h, p.up_y) - g.py0;
+    const int64_t plane_bytes = (int64_t)g.pw * g.ph * 4, budget = 40 * 1024;
+    if (plane_bytes > budget) return false;
+    int64_t ppb = budget / plane_bytes;
+    const int64_t want_blocks = (int64_t)kNumSMs * 4;       // keep every SM busy before growing the groups
+    if (ppb * want_blocks > p.major) ppb = p.major / want_blocks;
+    if (ppb < 1) ppb = 1;
+    g.planes_per_block = (int)ppb;
+    const int64_t groups = (p.major + ppb - 1) / ppb;
+    const int64_t cap = (int64_t)kNumSMs * 5;
+    const int smem = (int)(p.kernel_h * p.kernel_w * 4 + ppb * plane_bytes);
+    upfirdn2d_small_plane_kernel<<<(int)(groups < cap ? groups : cap), 256, smem, stream>>>(out, in, kernel, p, g);
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------------ tiled
 // One block = one TH x 64 output tile of TWO planes (minor == 1), interleaved in shared memory as float2 so that every
 // shared-memory access is an LDS.64 and every multiply-add is a packed FFMA2 (two planes per instruction).  K = padded
@@ -323,11 +403,12 @@ extern "C" int sis_upfirdn2d(void* d_out, const void* d_x, const void* d_kernel,
     SIS_REQUIRE(d_x || (int64_t)in_h * in_w * minor * major == 0, "upfirdn2d: input must be a CUDA tensor (null pointer)");
 
     bool done = false;
-    // Small planes (the 4^2 ... 16^2 maps): a 64-wide tile per plane pair would leave most of a block idle and the op is
-    // latency-bound; the one-thread-per-output kernel below (same y-outer / x-inner FMA chain over the real taps, i.e. the
-    // same bits) keeps every lane busy.
+    // Small planes (the 4^2 ... 32^2 maps): a 64-wide tile per plane pair would leave most of a block idle; they take the
+    // shared-memory plane-group kernel (same y-outer / x-inner FMA chain over the real taps, i.e. the same bits).
     const bool small_plane = (int64_t)p.out_h * p.out_w <= 32 * 32;
-    if (dtype == SIS_F32 && minor == 1 && up_x == up_y && down_x == down_y && in_h > 0 && in_w > 0 && !small_plane) {
+    if (small_plane && dtype == SIS_F32 && minor == 1 && in_h > 0 && in_w > 0)
+        done = launch_small_plane((float*)d_out, (const float*)d_x, (const float*)d_kernel, p, stream);
+    if (!done && dtype == SIS_F32 && minor == 1 && up_x == up_y && down_x == down_y && in_h > 0 && in_w > 0 && !small_plane) {
         float* o = (float*)d_out; const float* x = (const float*)d_x; const float* k = (const float*)d_kernel;
         const int kmax = kernel_h > kernel_w ? kernel_h : kernel_w;
         done = true;

@@ -39,7 +39,10 @@ def test_fused_bias_act_equals_reference_kernel(cuda_device, shape, code):
 @pytest.mark.parametrize('cfg', [
     # (major, H, W, up, down, pad, k)  the reference's six modes
     (64, 65, 65, 1, 1, (1, 1), 4), (7, 33, 20, 1, 1, (1, 1), 3), (6, 32, 32, 2, 1, (2, 1), 4),
-    (6, 16, 16, 2, 1, (1, 0), 2), (5, 64, 64, 1, 2, (1, 1), 4), (5, 32, 32, 1, 2, (0, 0), 2)])
+    (6, 16, 16, 2, 1, (1, 0), 2), (5, 64, 64, 1, 2, (1, 1), 4), (5, 32, 32, 1, 2, (0, 0), 2),
+    # planes of <= 32 x 32 outputs: the plane-group kernel (several planes per block, ragged last group, cropping pads)
+    (300, 8, 8, 1, 1, (1, 1), 4), (64, 33, 33, 1, 1, (1, 1), 4), (1301, 4, 4, 2, 1, (2, 1), 4), (50, 8, 8, 2, 1, (2, 1), 4),
+    (40, 16, 16, 1, 2, (1, 1), 4), (9, 20, 12, 1, 1, (-1, 2), 3), (33, 9, 9, 1, 1, (2, 2), 4)])
 def test_upfirdn2d_equals_reference_kernel(cuda_device, cfg):
     ref = load_ref('ref_upfirdn2d')
     major, h, w, up, down, pad, ks = cfg
