@@ -215,6 +215,36 @@ SIS_API int sis_or_u8(uint8_t* d_dst, const uint8_t* d_src, int64_t n, void* str
 SIS_API int sis_make_image_u8(const float* d_image, int batch, int size, uint8_t* d_out, void* stream);
 
 /* -----------------------------------------------------------------------------------------------------------
+ * Contour stage on the device: class masks -> colour label images + drop decision.
+ * Replaces the host loop of BlackWhiteHandwrittenPrintedTextDatasetSegmenter.create_segmentation_image
+ *   scf/segmentation/black_white_handwritten_printed_text_segmenter.py:42-99   (extract_text_regions, drop rule, driver)
+ *   scf/segmentation/base_cluster_based_dataset_segmenter.py:148-450           (cluster_image_to_contours, contour_overlap,
+ *       merge_contours*, merge_finegrained_segmentation, classify_fine_grained_contours, drop_too_small_contours,
+ *       render_segmentation_image)
+ *   scf/segmentation/base_dataset_segmenter.py:52-57                           (dilate_image)
+ * from the merged, image-size uint8 masks on (what prepare_image_segmentation + merge_sub_images produce).
+ *
+ * d_det_masks  : HOST array of n_det_keys*n_classes device pointers, entry [k*n_classes + c] = mask [batch,S,S] of class c
+ *                (classes = class_to_color_map without 'background', in its order) under keys_for_class_determination[k]
+ * d_fine_masks : HOST array of n_fine_keys device pointers: mask [batch,S,S] of the fine-grained class
+ *                ('printed_text') under keys_for_finegrained_segmentation[k]; the last one is also the ink mask of the
+ *                rendering step
+ * colors_rgb   : HOST, (1 + n_classes) * 3 bytes: background colour, then the classes
+ * render_rank  : HOST, n_classes ints: position of each class in the mask dict the reference's renderer iterates
+ *                (a later class overwrites an earlier one)
+ * d_label_rgb  : uint8 [batch,S,S,3];  d_flags: int32 [batch]: 0 keep, 1 drop, 2 = take this image through the host path
+ *                (the reference's drop rule reads the FIRST contour of a class; the device does not order contours and
+ *                only decides when the order cannot matter; also set for the whole batch when a capacity is exceeded)
+ * info         : HOST, 3 ints or NULL: shapes found, fixpoint rounds, reason the batch was handed to the host (0 none)
+ * The call synchronises the stream a few times (fixpoint control) and returns with the last kernels enqueued. */
+SIS_API int sis_contour_stage_workspace_bytes(int batch, int size, int n_classes, int n_det_keys, int n_fine_keys, int64_t* bytes);
+SIS_API int sis_contour_stage(const uint8_t* const* d_det_masks, const uint8_t* const* d_fine_masks, int batch, int size,
+                      int n_classes, int n_det_keys, int n_fine_keys, int fine_class, int only_keep_overlapping,
+                      double min_class_contour_area, const uint8_t* colors_rgb, const int* render_rank,
+                      void* d_workspace, int64_t workspace_bytes, uint8_t* d_label_rgb, int32_t* d_flags, int32_t* info,
+                      void* stream);
+
+/* -----------------------------------------------------------------------------------------------------------
  * DatasetGAN labeller (the other `segmenter_type`): every capture -> ensemble of per-pixel MLP classifiers -> labels.
  * Replaces DatasetGANSegmenter.create_segmentation_image's device work
  *   scf/segmentation/dataset_gan_segmenter.py:34-60  (predict_labels, label_images_to_color_images)

@@ -5,7 +5,7 @@ missing, `load()` raises and every op fails loudly.
 """
 import ctypes
 import os
-from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int64, c_uint8, c_uint32, c_uint64, c_void_p)
+from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_uint8, c_uint32, c_uint64, c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libsis_b200.so')
@@ -82,6 +82,9 @@ _SIGNATURES = {
     'sis_nearest_resize_u8': (c_int, [c_void_p, c_int64, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     'sis_or_u8': (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     'sis_make_image_u8': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    'sis_contour_stage_workspace_bytes': (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int64)]),
+    'sis_contour_stage': (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double,
+                                  c_char_p, POINTER(c_int), c_void_p, c_int64, c_void_p, c_void_p, POINTER(c_int), c_void_p]),
     'sis_pixel_ensemble_create': (c_int, [POINTER(c_void_p), c_int, c_int, c_int]),
     'sis_pixel_ensemble_destroy': (None, [c_void_p]),
     'sis_pixel_ensemble_set_param': (c_int, [c_void_p, c_int, c_char_p, c_void_p, c_int64]),

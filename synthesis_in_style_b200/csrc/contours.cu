@@ -1,0 +1,612 @@
+// Contour stage on the device: class masks -> colour label image + drop decision, per batch.
+// Replaces the host loop of BlackWhiteHandwrittenPrintedTextDatasetSegmenter.create_segmentation_image
+//   scf/segmentation/black_white_handwritten_printed_text_segmenter.py:42-99
+//   scf/segmentation/base_cluster_based_dataset_segmenter.py:148-450   (contours, overlap, merge, classify, render)
+//   scf/segmentation/base_dataset_segmenter.py:52-57                   (3x3 cross dilation)
+// which works on cv2 polygons.  Nothing here traces a polygon; the same results come from label maps:
+//
+//   * drawContours(FILLED) of an external contour of an 8-connected component = the component plus everything it
+//     encloses = one 8-connected component of the complement of the OUTSIDE background (background 4-connected to the
+//     image border).  Two union-find labellings per plane (background/4, then filled foreground/8) give every filled
+//     shape; its root is its smallest linear index = the first point findContours reports.
+//   * contourArea (Green's formula over the chain) = pixels - L/2 - 1, where L = number of chain points = boundary
+//     cracks minus convex corners, both local 3x3 counts (Pick's theorem; a single pixel gives L = 0, area 0).
+//   * boundingRect = min / max of the shape's pixels.
+//   * merge_contours' result SET does not depend on its merge order: "strict bounding-box test and a common pixel" only
+//     becomes true as shapes grow, so the set is the closure of that relation.  It is computed as a fixpoint: pixel-wise
+//     pair detection -> union-find over shapes -> group bounding boxes -> for every merged group the holes of its union
+//     (flood fill of the group's bounding-box window held as a bitmask in shared memory: the reference re-traces the
+//     union's outer contour, which fills them) -> repeat while anything changed.
+//   * classification = per-pixel overlap histogram (fine group, region class), rendering = per-pixel lookup.
+//
+// The ORDER of the merged contours (which the reference's drop rule reads: width and height of the FIRST contour of a
+// class, segmentation_utils.py:60-64 + black_white...:61-75) is not reproduced.  The kernel decides the drop flag when it
+// does not depend on the order (no contour of the class exceeds the limit, or all of them do) and otherwise marks the
+// image for the host path (flag 2), as it does when a capacity is exceeded.  tests/test_contours_gpu.py compares label
+// images and flags with synthesis_in_style_b200/contours.py (the polygon implementation pinned by the reference's goldens).
+#include <limits.h>
+#include "common.cuh"
+
+namespace sis {
+
+constexpr int CT_MAX_PLANE_TYPES = 32;
+constexpr int CT_MAX_KEYS = 4;
+constexpr int CT_MAX_CLASSES = 7;
+enum { CTR_SHAPES = 0, CTR_OVERFLOW = 1, CTR_CHANGED = 2, CTR_GLIST = 3, CTR_FILL_NEW = 4, CTR_NUM = 8 };
+
+struct CtGeom {
+    int B, S, n_cls, n_det, n_fine, fine_cls, px;
+    int only_keep_overlapping, limit;
+    double min_area2;                                   // 2 * min_class_contour_area
+    const uint8_t* planes[CT_MAX_PLANE_TYPES];          // [B, S, S] each: det (key k, class c) at k*n_cls+c, then fine key k
+    uint8_t colors[(CT_MAX_CLASSES + 1) * 3];           // background, then the classes
+    int render_rank[CT_MAX_CLASSES];                    // later rank overwrites earlier (mask-dict order of the last fine key)
+    __host__ __device__ int n_plane_types() const { return n_cls * n_det + n_fine; }
+    __host__ __device__ int n_seg_types() const { return n_cls + 1; }
+    // segment type st: 0..n_cls-1 = class-determination shapes of class st, n_cls = fine-grained shapes of fine_cls
+    __host__ __device__ int keys_of(int st) const { return st < n_cls ? n_det : n_fine; }
+    __host__ __device__ int plane_type(int st, int k) const { return st < n_cls ? k * n_cls + st : n_cls * n_det + k; }
+};
+
+struct CtWs {
+    int32_t *lab, *aux, *fillmap, *key_count;
+    uint8_t* fmask;
+    int cap;
+    int32_t *sh_seg, *sh_cnt, *sh_L, *sh_x0, *sh_y0, *sh_x1, *sh_y1, *parent;
+    int32_t *g_x0, *g_y0, *g_x1, *g_y1, *g_members, *g_filled, *g_cnt, *g_L, *g_kept, *g_cls, *score, *glist;
+    int32_t *ctr, *img_kept, *img_huge;
+};
+
+// ------------------------------------------------------------------------------------------------ union-find
+__device__ __forceinline__ int uf_find(const int32_t* parent, int i) {
+    while (true) {
+        const int p = ((const volatile int32_t*)parent)[i];
+        if (p == i) return i;
+        i = p;
+    }
+}
+// links the larger root under the smaller one; true when this call joined two sets
+__device__ __forceinline__ bool uf_unite(int32_t* parent, int a, int b) {
+    while (true) {
+        a = uf_find(parent, a);
+        b = uf_find(parent, b);
+        if (a == b) return false;
+        if (a > b) { const int t = a; a = b; b = t; }
+        const int old = atomicMin(&parent[b], a);
+        if (old == b) return true;
+        b = old;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ shapes of a plane
+// pass 1: dilated mask; background pixels start their own sets, foreground = -1
+__global__ void __launch_bounds__(256) ct_bg_init_kernel(CtGeom G, CtWs W) {
+    const int64_t total = (int64_t)G.n_plane_types() * G.B * G.px;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int plane = (int)(i / G.px), p = (int)(i - (int64_t)plane * G.px);
+        const int t = plane / G.B, b = plane - t * G.B;
+        const uint8_t* m = G.planes[t] + (int64_t)b * G.px;
+        const int y = p / G.S, x = p - y * G.S;
+        bool d = m[p] != 0;                                     // 3x3 cross (base_dataset_segmenter.py:52-57)
+        if (!d && y > 0) d = m[p - G.S] != 0;
+        if (!d && y < G.S - 1) d = m[p + G.S] != 0;
+        if (!d && x > 0) d = m[p - 1] != 0;
+        if (!d && x < G.S - 1) d = m[p + 1] != 0;
+        W.lab[i] = d ? -1 : p;
+        W.aux[i] = 0;
+    }
+}
+// background, 4-connectivity: join with the left and upper neighbour
+__global__ void __launch_bounds__(256) ct_bg_merge_kernel(CtGeom G, CtWs W) {
+    const int64_t total = (int64_t)G.n_plane_types() * G.B * G.px;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int plane = (int)(i / G.px), p = (int)(i - (int64_t)plane * G.px);
+        int32_t* lab = W.lab + (int64_t)plane * G.px;
+        if (lab[p] < 0) continue;
+        const int y = p / G.S, x = p - y * G.S;
+        if (x > 0 && lab[p - 1] >= 0) uf_unite(lab, p, p - 1);
+        if (y > 0 && lab[p - G.S] >= 0) uf_unite(lab, p, p - G.S);
+    }
+}
+// background sets that reach the image border are the outside (marked at their roots, once the sets are final)
+__global__ void __launch_bounds__(256) ct_bg_touch_kernel(CtGeom G, CtWs W) {
+    const int64_t total = (int64_t)G.n_plane_types() * G.B * 4 * G.S;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int plane = (int)(i / (4 * G.S)), j = (int)(i - (int64_t)plane * 4 * G.S), side = j / G.S, t = j - side * G.S;
+        const int p = side == 0 ? t : side == 1 ? (G.S - 1) * G.S + t : side == 2 ? t * G.S : t * G.S + G.S - 1;
+        const int32_t* lab = W.lab + (int64_t)plane * G.px;
+        if (lab[p] >= 0) W.aux[(int64_t)plane * G.px + uf_find(lab, p)] = 1;
+    }
+}
+// filled foreground = dilated mask + background that does not reach the border
+__global__ void __launch_bounds__(256) ct_fmask_kernel(CtGeom G, CtWs W) {
+    const int64_t total = (int64_t)G.n_plane_types() * G.B * G.px;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int plane = (int)(i / G.px), p = (int)(i - (int64_t)plane * G.px);
+        const int32_t* lab = W.lab + (int64_t)plane * G.px;
+        W.fmask[i] = (lab[p] < 0 || W.aux[(int64_t)plane * G.px + uf_find(lab, p)] == 0) ? 1 : 0;
+    }
+}
+__global__ void __launch_bounds__(256) ct_fg_init_kernel(CtGeom G, CtWs W) {
+    const int64_t total = (int64_t)G.n_plane_types() * G.B * G.px;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int p = (int)(i % G.px);
+        W.lab[i] = W.fmask[i] ? p : -1;
+    }
+}
+// filled foreground, 8-connectivity: join with W, NW, N, NE
+__global__ void __launch_bounds__(256) ct_fg_merge_kernel(CtGeom G, CtWs W) {
+    const int64_t total = (int64_t)G.n_plane_types() * G.B * G.px;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        if (!W.fmask[i]) continue;
+        const int plane = (int)(i / G.px), p = (int)(i - (int64_t)plane * G.px);
+        int32_t* lab = W.lab + (int64_t)plane * G.px;
+        const uint8_t* f = W.fmask + (int64_t)plane * G.px;
+        const int y = p / G.S, x = p - y * G.S;
+        if (x > 0 && f[p - 1]) uf_unite(lab, p, p - 1);
+        if (y > 0) {
+            if (f[p - G.S]) uf_unite(lab, p, p - G.S);
+            else {      // with N set, NW and NE are already joined through it
+                if (x > 0 && f[p - G.S - 1]) uf_unite(lab, p, p - G.S - 1);
+                if (x < G.S - 1 && f[p - G.S + 1]) uf_unite(lab, p, p - G.S + 1);
+            }
+        }
+    }
+}
+// roots get a compact shape id (aux[root]); every pixel's label becomes its root
+__global__ void __launch_bounds__(256) ct_fg_ids_kernel(CtGeom G, CtWs W) {
+    const int64_t total = (int64_t)G.n_plane_types() * G.B * G.px;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        if (!W.fmask[i]) continue;
+        const int plane = (int)(i / G.px), p = (int)(i - (int64_t)plane * G.px);
+        int32_t* lab = W.lab + (int64_t)plane * G.px;
+        const int r = uf_find(lab, p);
+        if (r != p) { lab[p] = r; continue; }
+        const int id = atomicAdd(&W.ctr[CTR_SHAPES], 1);
+        if (id >= W.cap) { W.ctr[CTR_OVERFLOW] = 1; W.aux[i] = -1; continue; }
+        W.aux[i] = id;
+        const int t = plane / G.B, b = plane - t * G.B;
+        const int st = t < G.n_cls * G.n_det ? t % G.n_cls : G.n_cls;
+        W.sh_seg[id] = st * G.B + b;
+        W.sh_cnt[id] = 0; W.sh_L[id] = 0;
+        W.sh_x0[id] = INT_MAX; W.sh_y0[id] = INT_MAX; W.sh_x1[id] = -1; W.sh_y1[id] = -1;
+        W.parent[id] = id;
+        W.g_filled[id] = 0; W.g_kept[id] = 0; W.g_cls[id] = -1;
+        for (int c = 0; c < G.n_cls; ++c) W.score[(int64_t)id * G.n_cls + c] = 0;
+        atomicAdd(&W.key_count[plane], 1);
+    }
+}
+// per-shape pixel count, chain length (cracks - convex corners) and bounding box; labels become shape ids
+__global__ void __launch_bounds__(256) ct_shape_stats_kernel(CtGeom G, CtWs W) {
+    const int64_t total = (int64_t)G.n_plane_types() * G.B * G.px;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        if (!W.fmask[i]) continue;
+        const int plane = (int)(i / G.px), p = (int)(i - (int64_t)plane * G.px);
+        const int64_t base = (int64_t)plane * G.px;
+        const int id = W.aux[base + W.lab[i]];
+        W.lab[i] = id;
+        if (id < 0) continue;
+        const uint8_t* f = W.fmask + base;
+        const int S = G.S, y = p / S, x = p - y * S;
+        const bool up = y == 0 || !f[p - S], dn = y == S - 1 || !f[p + S], lf = x == 0 || !f[p - 1], rt = x == S - 1 || !f[p + 1];
+        int L = (int)up + dn + lf + rt;
+        if (L) {
+            // a convex corner: both sides outside and the diagonal not part of the shape (a diagonal pixel would be a pinch)
+            if (up && lf && !(y > 0 && x > 0 && f[p - S - 1])) --L;
+            if (up && rt && !(y > 0 && x < S - 1 && f[p - S + 1])) --L;
+            if (dn && lf && !(y < S - 1 && x > 0 && f[p + S - 1])) --L;
+            if (dn && rt && !(y < S - 1 && x < S - 1 && f[p + S + 1])) --L;
+            if (L) atomicAdd(&W.sh_L[id], L);
+            if (lf) atomicMin(&W.sh_x0[id], x);
+            if (rt) atomicMax(&W.sh_x1[id], x);
+            if (up) atomicMin(&W.sh_y0[id], y);
+            if (dn) atomicMax(&W.sh_y1[id], y);
+        }
+        atomicAdd(&W.sh_cnt[id], 1);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ merge fixpoint
+__device__ __forceinline__ bool ct_strict(const CtWs& W, int a, int b) {
+    // BBox.is_overlapping_with (segmentation_utils.py:50-54): touching boxes do not overlap
+    return W.g_x0[a] < W.g_x1[b] && W.g_x1[a] > W.g_x0[b] && W.g_y0[a] < W.g_y1[b] && W.g_y1[a] > W.g_y0[b];
+}
+// the groups whose filled shape covers pixel p of segment (st, b): one per key plus the hole fill
+__device__ __forceinline__ int ct_cover(const CtGeom& G, const CtWs& W, int st, int b, int p, int* out) {
+    int n = 0;
+    const int nk = G.keys_of(st);
+    for (int k = 0; k <= nk; ++k) {
+        const int id = k < nk ? W.lab[((int64_t)G.plane_type(st, k) * G.B + b) * G.px + p]
+                              : W.fillmap[((int64_t)st * G.B + b) * G.px + p];
+        if (id < 0) continue;
+        const int r = uf_find(W.parent, id);
+        bool seen = false;
+        for (int j = 0; j < n; ++j) seen |= out[j] == r;
+        if (!seen) out[n++] = r;
+    }
+    return n;
+}
+__global__ void __launch_bounds__(256) ct_pairs_kernel(CtGeom G, CtWs W) {
+    const int64_t total = (int64_t)G.n_seg_types() * G.B * G.px;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int seg = (int)(i / G.px), p = (int)(i - (int64_t)seg * G.px);
+        const int st = seg / G.B, b = seg - st * G.B;
+        if (G.keys_of(st) < 2) continue;                 // a single key is never merged (base_cluster_based...:209)
+        int g[CT_MAX_KEYS + 1];
+        const int n = ct_cover(G, W, st, b, p, g);
+        for (int a = 0; a < n; ++a)
+            for (int c = a + 1; c < n; ++c)
+                if (ct_strict(W, g[a], g[c]) && uf_unite(W.parent, g[a], g[c])) W.ctr[CTR_CHANGED] = 1;
+    }
+}
+__global__ void __launch_bounds__(256) ct_group_reset_kernel(CtWs W) {
+    const int n = min(W.ctr[CTR_SHAPES], W.cap);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        W.g_x0[i] = INT_MAX; W.g_y0[i] = INT_MAX; W.g_x1[i] = -1; W.g_y1[i] = -1; W.g_members[i] = 0;
+    }
+}
+__global__ void __launch_bounds__(256) ct_group_accum_kernel(CtWs W) {
+    const int n = min(W.ctr[CTR_SHAPES], W.cap);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        const int r = uf_find(W.parent, i);
+        if (r != i) W.parent[i] = r;
+        atomicMin(&W.g_x0[r], W.sh_x0[i]); atomicMin(&W.g_y0[r], W.sh_y0[i]);
+        atomicMax(&W.g_x1[r], W.sh_x1[i]); atomicMax(&W.g_y1[r], W.sh_y1[i]);
+        atomicAdd(&W.g_members[r], 1);
+    }
+}
+__global__ void __launch_bounds__(256) ct_list_groups_kernel(CtWs W) {
+    const int n = min(W.ctr[CTR_SHAPES], W.cap);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
+        if (W.parent[i] == i && W.g_members[i] > 1 && W.g_filled[i] != W.g_members[i]) W.glist[atomicAdd(&W.ctr[CTR_GLIST], 1)] = i;
+}
+
+// occluded fill inside a word: bits of `s` spread through the runs of `f` (Kogge-Stone, both directions)
+__device__ __forceinline__ uint32_t ct_spread(uint32_t s, uint32_t f) {
+    uint32_t g = s, p = f;
+    g |= p & (g << 1); p &= p << 1;
+    g |= p & (g << 2); p &= p << 2;
+    g |= p & (g << 4); p &= p << 4;
+    g |= p & (g << 8); p &= p << 8;
+    g |= p & (g << 16);
+    uint32_t h = s; p = f;
+    h |= p & (h >> 1); p &= p >> 1;
+    h |= p & (h >> 2); p &= p >> 2;
+    h |= p & (h >> 4); p &= p >> 4;
+    h |= p & (h >> 8); p &= p >> 8;
+    h |= p & (h >> 16);
+    return g | h;
+}
+
+// One block per merged group: the union U of its members over the bounding box grown by one pixel, as a bitmask in shared
+// memory; flood of the free pixels from the window's rim; what the flood does not reach and U does not cover is hole.
+// Writes the holes to the fill map and the filled group's pixel count and chain length.
+__global__ void __launch_bounds__(256) ct_group_fill_kernel(CtGeom G, CtWs W) {
+    extern __shared__ uint32_t ct_sm[];
+    __shared__ int red[3];
+    const int g = W.glist[blockIdx.x], tid = threadIdx.x;
+    const int seg = W.sh_seg[g], st = seg / G.B, b = seg - st * G.B, nk = G.keys_of(st);
+    const int x0 = W.g_x0[g] - 1, y0 = W.g_y0[g] - 1;
+    const int ww = W.g_x1[g] - W.g_x0[g] + 3, hh = W.g_y1[g] - W.g_y0[g] + 3, wpr = (ww + 31) >> 5, words = hh * wpr;
+    uint32_t* U = ct_sm;
+    uint32_t* R = ct_sm + words;
+    if (tid < 3) red[tid] = 0;
+    for (int w = tid; w < words; w += 256) {
+        const int row = w / wpr, wc = w - row * wpr;
+        const int nbits = min(32, ww - wc * 32);
+        const uint32_t valid = nbits == 32 ? 0xffffffffu : ((1u << nbits) - 1u);
+        uint32_t u = 0, r = 0;
+        if (row == 0 || row == hh - 1) r = valid;
+        else {
+            if (wc == 0) r |= 1u;
+            if (wc == wpr - 1) r |= 1u << ((ww - 1) & 31);
+            const int y = y0 + row;
+            for (int i = 0; i < nbits; ++i) {
+                const int xw = wc * 32 + i;
+                if (xw == 0 || xw == ww - 1) continue;
+                const int p = y * G.S + x0 + xw;
+                bool in = false;
+                for (int k = 0; k < nk && !in; ++k) {
+                    const int id = W.lab[((int64_t)G.plane_type(st, k) * G.B + b) * G.px + p];
+                    in = id >= 0 && uf_find(W.parent, id) == g;
+                }
+                u |= (uint32_t)in << i;
+            }
+        }
+        U[w] = u;
+        R[w] = r;
+    }
+    __syncthreads();
+    int changed;
+    do {
+        changed = 0;
+        for (int w = tid; w < words; w += 256) {
+            const int row = w / wpr, wc = w - row * wpr;
+            const int nbits = min(32, ww - wc * 32);
+            const uint32_t valid = nbits == 32 ? 0xffffffffu : ((1u << nbits) - 1u);
+            const uint32_t f = ~U[w] & valid, r = ((volatile uint32_t*)R)[w];
+            uint32_t s = r | (r << 1) | (r >> 1);            // 4-connected: sideways only from this row's reach
+            if (wc > 0) s |= ((volatile uint32_t*)R)[w - 1] >> 31;
+            if (wc < wpr - 1) s |= ((volatile uint32_t*)R)[w + 1] << 31;
+            if (row > 0) s |= ((volatile uint32_t*)R)[w - wpr];
+            if (row < hh - 1) s |= ((volatile uint32_t*)R)[w + wpr];
+            s = ct_spread(s & f, f);
+            if (s != r) { ((volatile uint32_t*)R)[w] = s | r; changed = 1; }
+        }
+        changed = __syncthreads_or(changed);
+    } while (changed);
+    // filled shape F = everything the flood did not reach
+    int cnt = 0, L = 0, fresh = 0;
+    int32_t* fm = W.fillmap + (int64_t)seg * G.px;
+    auto Fw = [&](int row, int wc) -> uint32_t {
+        if (row < 0 || row >= hh || wc < 0 || wc >= wpr) return 0u;
+        const int nbits = min(32, ww - wc * 32);
+        const uint32_t valid = nbits == 32 ? 0xffffffffu : ((1u << nbits) - 1u);
+        return ~R[row * wpr + wc] & valid;
+    };
+    for (int w = tid; w < words; w += 256) {
+        const int row = w / wpr, wc = w - row * wpr;
+        const uint32_t F = Fw(row, wc);
+        if (!F) continue;
+        const uint32_t up = Fw(row - 1, wc), dn = Fw(row + 1, wc);
+        const uint32_t lf = (F << 1) | (Fw(row, wc - 1) >> 31), rt = (F >> 1) | (Fw(row, wc + 1) << 31);
+        const uint32_t ul = (up << 1) | (Fw(row - 1, wc - 1) >> 31), ur = (up >> 1) | (Fw(row - 1, wc + 1) << 31);
+        const uint32_t dl = (dn << 1) | (Fw(row + 1, wc - 1) >> 31), dr = (dn >> 1) | (Fw(row + 1, wc + 1) << 31);
+        cnt += __popc(F);
+        L += __popc(F & ~up) + __popc(F & ~dn) + __popc(F & ~lf) + __popc(F & ~rt);
+        L -= __popc(F & ~up & ~lf & ~ul) + __popc(F & ~up & ~rt & ~ur) + __popc(F & ~dn & ~lf & ~dl) + __popc(F & ~dn & ~rt & ~dr);
+        uint32_t hole = F & ~U[w];
+        while (hole) {
+            const int i = __ffs(hole) - 1;
+            hole &= hole - 1;
+            const int p = (y0 + row) * G.S + x0 + wc * 32 + i;
+            const int old = fm[p];
+            if (old < 0 || uf_find(W.parent, old) != g) ++fresh;
+            fm[p] = g;
+        }
+    }
+    atomicAdd(&red[0], cnt); atomicAdd(&red[1], L); atomicAdd(&red[2], fresh);
+    __syncthreads();
+    if (tid == 0) {
+        W.g_cnt[g] = red[0]; W.g_L[g] = red[1]; W.g_filled[g] = W.g_members[g];
+        if (red[2]) W.ctr[CTR_FILL_NEW] = 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ decisions
+// which groups survive merge_contours_of_same_class_from_different_images + drop_too_small_contours
+__global__ void __launch_bounds__(256) ct_finalize_kernel(CtGeom G, CtWs W) {
+    const int n = min(W.ctr[CTR_SHAPES], W.cap);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        if (W.parent[i] != i) continue;
+        const int seg = W.sh_seg[i], st = seg / G.B, b = seg - st * G.B, nk = G.keys_of(st);
+        bool valid = true;                                // a class with no contour in one of the keys is dropped (:241-245)
+        for (int k = 0; k < nk; ++k) valid &= W.key_count[G.plane_type(st, k) * G.B + b] > 0;
+        const int members = W.g_members[i];
+        if (members == 1) { W.g_cnt[i] = W.sh_cnt[i]; W.g_L[i] = W.sh_L[i]; }
+        const bool keep_overlap = st < G.n_cls ? G.only_keep_overlapping != 0 : true;     // fine-grained: always (:334-349)
+        const bool merged_ok = nk == 1 || members > 1 || !keep_overlap;
+        const bool big = (double)(2 * (int64_t)W.g_cnt[i] - W.g_L[i] - 2) >= G.min_area2;
+        W.g_kept[i] = st < G.n_cls ? (valid && merged_ok && big) : (valid && merged_ok);
+    }
+}
+// classify_fine_grained_contours' overlap sums: score[fine group][class] += 1 per common pixel with a kept region of the
+// class whose bounding box strictly overlaps the fine group's
+__global__ void __launch_bounds__(256) ct_classify_kernel(CtGeom G, CtWs W) {
+    const int64_t total = (int64_t)G.B * G.px;
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int b = (int)(i / G.px), p = (int)(i - (int64_t)b * G.px);
+        int fg[CT_MAX_KEYS + 1], rg[CT_MAX_KEYS + 1];
+        const int nf = ct_cover(G, W, G.n_cls, b, p, fg);
+        if (!nf) continue;
+        for (int c = 0; c < G.n_cls; ++c) {
+            const int nr = ct_cover(G, W, c, b, p, rg);
+            for (int a = 0; a < nf; ++a) {
+                if (!W.g_kept[fg[a]]) continue;
+                for (int r = 0; r < nr; ++r)
+                    if (W.g_kept[rg[r]] && ct_strict(W, fg[a], rg[r])) atomicAdd(&W.score[(int64_t)fg[a] * G.n_cls + c], 1);
+            }
+        }
+    }
+}
+__global__ void __launch_bounds__(256) ct_assign_kernel(CtGeom G, CtWs W) {
+    const int n = min(W.ctr[CTR_SHAPES], W.cap);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+        if (W.parent[i] != i || !W.g_kept[i]) continue;
+        const int seg = W.sh_seg[i], st = seg / G.B, b = seg - st * G.B;
+        if (st != G.n_cls) continue;
+        int best = -1, best_score = 0;                    // strict >: the first maximum in colour-map order wins (:371-384)
+        for (int c = 0; c < G.n_cls; ++c) {
+            const int s = W.score[(int64_t)i * G.n_cls + c];
+            if (s > best_score) { best = c; best_score = s; }
+        }
+        const bool big = (double)(2 * (int64_t)W.g_cnt[i] - W.g_L[i] - 2) >= G.min_area2;
+        if (best < 0 || !big) continue;
+        W.g_cls[i] = best;
+        atomicAdd(&W.img_kept[b * G.n_cls + best], 1);
+        if (W.g_x1[i] - W.g_x0[i] + 1 > G.limit && W.g_y1[i] - W.g_y0[i] + 1 > G.limit) atomicAdd(&W.img_huge[b * G.n_cls + best], 1);
+    }
+}
+// render_segmentation_image + determine_images_to_drop
+__global__ void __launch_bounds__(256) ct_render_kernel(CtGeom G, CtWs W, uint8_t* __restrict__ out, int32_t* __restrict__ flags) {
+    const int64_t total = (int64_t)G.B * G.px;
+    const uint8_t* ink_plane = G.planes[G.n_cls * G.n_det + G.n_fine - 1];
+    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+        const int b = (int)(i / G.px), p = (int)(i - (int64_t)b * G.px);
+        int cls = -1;
+        if (ink_plane[i]) {
+            int fg[CT_MAX_KEYS + 1];
+            const int nf = ct_cover(G, W, G.n_cls, b, p, fg);
+            for (int a = 0; a < nf; ++a) {
+                const int c = W.g_cls[fg[a]];
+                if (c >= 0 && (cls < 0 || G.render_rank[c] > G.render_rank[cls])) cls = c;
+            }
+        }
+        const uint8_t* col = G.colors + 3 * (cls + 1);
+        out[3 * i] = col[0]; out[3 * i + 1] = col[1]; out[3 * i + 2] = col[2];
+        if (p == 0) {
+            // the reference looks at the FIRST contour of each class: decided here when every contour of the class agrees
+            bool certain = false, undecided = false;
+            for (int c = 0; c < G.n_cls; ++c) {
+                const int huge = W.img_huge[b * G.n_cls + c], kept = W.img_kept[b * G.n_cls + c];
+                certain |= huge > 0 && huge == kept;
+                undecided |= huge > 0 && huge != kept;
+            }
+            flags[b] = certain ? 1 : undecided ? 2 : 0;       // a certain drop in one class decides the image
+        }
+    }
+}
+__global__ void ct_fill_flags_kernel(int32_t* flags, int n, int v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) flags[i] = v;
+}
+
+struct CtLayout {
+    int64_t lab, aux, fillmap, key_count, fmask, shapes, ctr, img, total;
+    int cap;
+};
+static CtLayout ct_layout(int B, int S, int n_cls, int n_det, int n_fine) {
+    CtLayout L;
+    const int64_t px = (int64_t)S * S, np = (int64_t)(n_cls * n_det + n_fine) * B, ns = (int64_t)(n_cls + 1) * B;
+    auto up = [](int64_t v) { return (v + 255) / 256 * 256; };
+    int64_t off = 0;
+    L.lab = off; off += up(np * px * 4);
+    L.aux = off; off += up(np * px * 4);
+    L.fillmap = off; off += up(ns * px * 4);
+    L.fmask = off; off += up(np * px);
+    L.key_count = off; off += up(np * 4);
+    // two shapes of a plane are never 8-adjacent, so a plane holds at most S^2/4; 16 k per plane is far above what masks
+    // produce (overflow marks the whole batch for the host path)
+    const int64_t per_plane = px / 4 < 16384 ? px / 4 : 16384;
+    L.cap = (int)(np * per_plane);
+    L.shapes = off; off += up((int64_t)L.cap * 4) * (20 + n_cls);
+    L.ctr = off; off += up(CTR_NUM * 4);
+    L.img = off; off += up((int64_t)B * n_cls * 4) * 2;
+    L.total = off;
+    return L;
+}
+
+}  // namespace sis
+
+using namespace sis;
+
+extern "C" int sis_contour_stage_workspace_bytes(int batch, int size, int n_classes, int n_det_keys, int n_fine_keys, int64_t* bytes) {
+    SIS_REQUIRE(bytes != nullptr, "contour stage: null output");
+    SIS_REQUIRE(batch > 0 && size > 0 && n_classes > 0 && n_det_keys > 0 && n_fine_keys > 0, "contour stage: sizes must be positive");
+    *bytes = ct_layout(batch, size, n_classes, n_det_keys, n_fine_keys).total;
+    return SIS_OK;
+}
+
+extern "C" int sis_contour_stage(const uint8_t* const* d_det_masks, const uint8_t* const* d_fine_masks, int batch, int size,
+                                 int n_classes, int n_det_keys, int n_fine_keys, int fine_class, int only_keep_overlapping,
+                                 double min_class_contour_area, const uint8_t* colors_rgb, const int* render_rank,
+                                 void* d_workspace, int64_t workspace_bytes, uint8_t* d_label_rgb, int32_t* d_flags,
+                                 int32_t* info, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    SIS_REQUIRE(batch > 0 && size > 0, "contour stage: batch and image size must be positive");
+    SIS_REQUIRE(n_classes >= 1 && n_classes <= CT_MAX_CLASSES, "contour stage: 1..%d classes besides the background (got %d)", CT_MAX_CLASSES, n_classes);
+    SIS_REQUIRE(n_det_keys >= 1 && n_det_keys <= CT_MAX_KEYS && n_fine_keys >= 1 && n_fine_keys <= CT_MAX_KEYS,
+                "contour stage: 1..%d keys per stage", CT_MAX_KEYS);
+    SIS_REQUIRE(n_classes * n_det_keys + n_fine_keys <= CT_MAX_PLANE_TYPES, "contour stage: too many mask planes");
+    SIS_REQUIRE(fine_class >= 0 && fine_class < n_classes, "contour stage: fine-grained class index out of range");
+    SIS_REQUIRE(d_det_masks && d_fine_masks && colors_rgb && render_rank && d_workspace && d_label_rgb && d_flags,
+                "contour stage: masks, outputs and workspace must be CUDA tensors (null pointer)");
+    const CtLayout L = ct_layout(batch, size, n_classes, n_det_keys, n_fine_keys);
+    SIS_REQUIRE(workspace_bytes >= L.total, "contour stage: workspace of %lld bytes, %lld needed", (long long)workspace_bytes, (long long)L.total);
+    CtGeom G;
+    G.B = batch; G.S = size; G.n_cls = n_classes; G.n_det = n_det_keys; G.n_fine = n_fine_keys; G.fine_cls = fine_class;
+    G.px = size * size; G.only_keep_overlapping = only_keep_overlapping; G.limit = (int)(size * 0.95);
+    G.min_area2 = 2.0 * min_class_contour_area;
+    for (int t = 0; t < n_classes * n_det_keys; ++t) {
+        SIS_REQUIRE(d_det_masks[t] != nullptr, "contour stage: null class-determination mask plane %d", t);
+        G.planes[t] = d_det_masks[t];
+    }
+    for (int k = 0; k < n_fine_keys; ++k) {
+        SIS_REQUIRE(d_fine_masks[k] != nullptr, "contour stage: null fine-grained mask plane %d", k);
+        G.planes[n_classes * n_det_keys + k] = d_fine_masks[k];
+    }
+    for (int i = 0; i < (n_classes + 1) * 3; ++i) G.colors[i] = colors_rgb[i];
+    for (int c = 0; c < n_classes; ++c) G.render_rank[c] = render_rank[c];
+
+    char* base = (char*)d_workspace;
+    CtWs W;
+    W.lab = (int32_t*)(base + L.lab); W.aux = (int32_t*)(base + L.aux); W.fillmap = (int32_t*)(base + L.fillmap);
+    W.fmask = (uint8_t*)(base + L.fmask); W.key_count = (int32_t*)(base + L.key_count);
+    W.cap = L.cap;
+    const int64_t stride = ((int64_t)L.cap * 4 + 255) / 256 * 256;
+    int32_t** fields[] = {&W.sh_seg, &W.sh_cnt, &W.sh_L, &W.sh_x0, &W.sh_y0, &W.sh_x1, &W.sh_y1, &W.parent, &W.g_x0, &W.g_y0,
+                          &W.g_x1, &W.g_y1, &W.g_members, &W.g_filled, &W.g_cnt, &W.g_L, &W.g_kept, &W.g_cls, &W.glist, &W.score};
+    for (int i = 0; i < 20; ++i) *fields[i] = (int32_t*)(base + L.shapes + stride * i);      // score takes slots 19 .. 19+n_cls
+    W.ctr = (int32_t*)(base + L.ctr);
+    W.img_kept = (int32_t*)(base + L.img);
+    W.img_huge = W.img_kept + ((int64_t)batch * n_classes * 4 + 255) / 256 * 64;
+
+    const int64_t np = (int64_t)G.n_plane_types() * batch, ns = (int64_t)G.n_seg_types() * batch;
+    const int wmax = size + 2, fill_smem = 2 * wmax * ((wmax + 31) / 32) * 4;
+    int host_ctr[CTR_NUM] = {0};
+    auto give_up = [&](int why) -> int {      // the whole batch goes to the host path
+        ct_fill_flags_kernel<<<ceil_div(batch, 128), 128, 0, stream>>>(d_flags, batch, 2);
+        SIS_CHECK_LAUNCH();
+        if (info) { info[0] = host_ctr[CTR_SHAPES]; info[1] = 0; info[2] = why; }
+        return SIS_OK;
+    };
+    if (fill_smem > 200 * 1024) return give_up(2);        // window bitmasks do not fit in shared memory (S > ~880)
+    static int fill_smem_set = 0;
+    if (fill_smem > fill_smem_set) {
+        SIS_CHECK_CUDA(cudaFuncSetAttribute(ct_group_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fill_smem));
+        fill_smem_set = fill_smem;
+    }
+    SIS_CHECK_CUDA(cudaMemsetAsync(W.fillmap, 0xff, ns * G.px * 4, stream));
+    SIS_CHECK_CUDA(cudaMemsetAsync(W.key_count, 0, np * 4, stream));
+    SIS_CHECK_CUDA(cudaMemsetAsync(W.ctr, 0, CTR_NUM * 4, stream));
+    SIS_CHECK_CUDA(cudaMemsetAsync(W.img_kept, 0, (char*)(base + L.total) - (char*)W.img_kept, stream));
+    const int grid_px = (int)min((int64_t)kNumSMs * 16, ceil_div64(np * G.px, 256));
+    const int grid_seg = (int)min((int64_t)kNumSMs * 16, ceil_div64(ns * G.px, 256));
+    const int grid_img = (int)min((int64_t)kNumSMs * 16, ceil_div64((int64_t)batch * G.px, 256));
+    ct_bg_init_kernel<<<grid_px, 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
+    ct_bg_merge_kernel<<<grid_px, 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
+    ct_bg_touch_kernel<<<(int)min((int64_t)kNumSMs * 8, ceil_div64(np * 4 * size, 256)), 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
+    ct_fmask_kernel<<<grid_px, 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
+    ct_fg_init_kernel<<<grid_px, 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
+    ct_fg_merge_kernel<<<grid_px, 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
+    ct_fg_ids_kernel<<<grid_px, 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
+    ct_shape_stats_kernel<<<grid_px, 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
+    auto read_ctr = [&]() -> cudaError_t {
+        cudaError_t e = cudaMemcpyAsync(host_ctr, W.ctr, sizeof(host_ctr), cudaMemcpyDeviceToHost, stream);
+        return e != cudaSuccess ? e : cudaStreamSynchronize(stream);
+    };
+    SIS_CHECK_CUDA(read_ctr());
+    if (host_ctr[CTR_OVERFLOW]) return give_up(1);
+    const int n_shapes = host_ctr[CTR_SHAPES];
+    const int grid_sh = max(1, min(kNumSMs * 8, ceil_div(n_shapes, 256)));
+    int rounds = 0;
+    const bool merging = n_det_keys > 1 || n_fine_keys > 1;
+    ct_group_reset_kernel<<<grid_sh, 256, 0, stream>>>(W); SIS_CHECK_LAUNCH();
+    ct_group_accum_kernel<<<grid_sh, 256, 0, stream>>>(W); SIS_CHECK_LAUNCH();
+    while (merging && n_shapes > 0) {
+        // pairs until the boxes stop growing
+        while (true) {
+            ++rounds;
+            SIS_CHECK_CUDA(cudaMemsetAsync(W.ctr + CTR_CHANGED, 0, 4, stream));
+            ct_pairs_kernel<<<grid_seg, 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
+            ct_group_reset_kernel<<<grid_sh, 256, 0, stream>>>(W); SIS_CHECK_LAUNCH();
+            ct_group_accum_kernel<<<grid_sh, 256, 0, stream>>>(W); SIS_CHECK_LAUNCH();
+            SIS_CHECK_CUDA(read_ctr());
+            if (!host_ctr[CTR_CHANGED]) break;
+            SIS_REQUIRE(rounds < 10000, "contour stage: merge fixpoint did not converge");
+        }
+        SIS_CHECK_CUDA(cudaMemsetAsync(W.ctr + CTR_GLIST, 0, 8, stream));       // list length and the new-hole flag
+        ct_list_groups_kernel<<<grid_sh, 256, 0, stream>>>(W); SIS_CHECK_LAUNCH();
+        SIS_CHECK_CUDA(read_ctr());
+        if (host_ctr[CTR_GLIST] == 0) break;
+        ct_group_fill_kernel<<<host_ctr[CTR_GLIST], 256, fill_smem, stream>>>(G, W); SIS_CHECK_LAUNCH();
+        SIS_CHECK_CUDA(read_ctr());
+        if (!host_ctr[CTR_FILL_NEW]) break;              // no pixel became covered: no new pair can appear
+    }
+    ct_finalize_kernel<<<grid_sh, 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
+    ct_classify_kernel<<<grid_img, 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
+    ct_assign_kernel<<<grid_sh, 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
+    ct_render_kernel<<<grid_img, 256, 0, stream>>>(G, W, d_label_rgb, d_flags); SIS_CHECK_LAUNCH();
+    if (info) { info[0] = n_shapes; info[1] = rounds; info[2] = 0; }
+    return SIS_OK;
+}

@@ -90,9 +90,9 @@ __global__ void __launch_bounds__(256) upfirdn2d_generic_kernel(T* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------ small planes
-// Planes of at most 32 x 32 outputs (the 4^2 ... 32^2 maps; minor == 1, fp32, any up / down / taps).  A 64-wide tile per
+// Planes of at most 16 x 16 outputs (the 4^2 ... 16^2 maps; minor == 1, fp32, any up / down / taps).  A 64-wide tile per
 // plane pair would leave most of a block idle there, and one thread per output straight from global memory is bound by
-// its 64-bit index arithmetic and per-tap bounds checks (measured: 0.3 TB/s at 32^2).  Here a block owns PB consecutive
+// its 64-bit index arithmetic and per-tap bounds checks.  Here a block owns PB consecutive
 // planes: their inputs are ONE contiguous span of global memory (coalesced loads) scattered into zero-padded planes in
 // shared memory, so the tap loops carry no bounds checks and all index arithmetic is 32-bit; the outputs of the PB planes
 // are one contiguous span again.  Same FMA chain per output as the generic kernel (real taps only, y outer, x inner).
@@ -403,9 +403,11 @@ extern "C" int sis_upfirdn2d(void* d_out, const void* d_x, const void* d_kernel,
     SIS_REQUIRE(d_x || (int64_t)in_h * in_w * minor * major == 0, "upfirdn2d: input must be a CUDA tensor (null pointer)");
 
     bool done = false;
-    // Small planes (the 4^2 ... 32^2 maps): a 64-wide tile per plane pair would leave most of a block idle; they take the
-    // shared-memory plane-group kernel (same y-outer / x-inner FMA chain over the real taps, i.e. the same bits).
-    const bool small_plane = (int64_t)p.out_h * p.out_w <= 32 * 32;
+    // Small planes (the 4^2 ... 16^2 maps): a 64-wide tile per plane pair would leave most of a block idle; they take the
+    // shared-memory plane-group kernel (same y-outer / x-inner FMA chain over the real taps, i.e. the same bits).  At 32^2
+    // the tiled kernel is still the faster one (measured 1.2 vs 0.45 TB/s: the plane-group kernel spends ~250 instructions
+    // per output on runtime-bounded loops and divisions).
+    const bool small_plane = (int64_t)p.out_h * p.out_w <= 16 * 16;
     if (small_plane && dtype == SIS_F32 && minor == 1 && in_h > 0 && in_w > 0)
         done = launch_small_plane((float*)d_out, (const float*)d_x, (const float*)d_kernel, p, stream);
     if (!done && dtype == SIS_F32 && minor == 1 && up_x == up_y && down_x == down_y && in_h > 0 && in_w > 0 && !small_plane) {
