@@ -488,6 +488,8 @@ def run_leg_dataset(args, dev, rank, world, out):
     cores = os.cpu_count() or 1
     per_rank = max(2, cores // world)
     n_contour, n_png = max(1, per_rank * 3 // 4), max(1, per_rank // 4)
+    if args.contours != 'host':          # contour stage on the device: the host cores go to the PNG encoder
+        n_contour, n_png = max(1, per_rank // 4), max(1, per_rank * 3 // 4)
     base = tempfile.mkdtemp(prefix=f'sis_dataset_r{rank}_', dir='/dev/shm' if os.path.isdir('/dev/shm') else None)
 
     def sync_max(seconds):
@@ -511,15 +513,36 @@ def run_leg_dataset(args, dev, rank, world, out):
             gpu_only = sync_max(time.perf_counter() - t0)
             del it, pipe
             # warm the worker processes, then the timed end-to-end run
+            device_contours = {'device': True, 'host': False, 'auto': None}[args.contours]
             warm = dc.LabelledPairGenerator(g, seg, cfg, seed=3, rank=rank, world_size=world, in_flight=args.in_flight)
-            dw.build_dataset(warm, os.path.join(base, 'warm'), 2 * B * world, cpool, wpool)
+            dw.build_dataset(warm, os.path.join(base, 'warm'), 2 * B * world, cpool, wpool, device_contours=device_contours)
             del warm
+            # the contour stage alone (device): one batch of this pipeline's masks, CUDA events around sis_contour_stage
+            contour_ms = None
+            if device_contours is not False:
+                from synthesis_in_style_b200 import contours_device as cd
+                probe = dc.LabelledPairGenerator(g, seg, cfg, seed=1, rank=rank, world_size=world)
+                jobs = seg.make_label_jobs(g, B)
+                batch0 = next(iter(probe))
+                stacked = {k: (list(v), torch.stack([m.view(torch.uint8) for m in v.values()])) for k, v in batch0.masks.items()}
+                stage = cd.DeviceContourStage(seg.contour_config())
+                stage.run(stacked)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(5):
+                    stage.run(stacked)
+                e1.record()
+                torch.cuda.synchronize()
+                contour_ms = e0.elapsed_time(e1) / 5
+                contour_info = {'ms_per_batch': round(contour_ms, 3), 'shapes': stage.last_info[0], 'fixpoint_rounds': stage.last_info[1]}
+                del probe, batch0, stacked, stage, jobs
             pipe = dc.LabelledPairGenerator(g, seg, cfg, seed=1, rank=rank, world_size=world, in_flight=args.in_flight)
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            stats = dw.build_dataset(pipe, os.path.join(base, 'run'), args.steps * B * world, cpool, wpool)
+            stats = dw.build_dataset(pipe, os.path.join(base, 'run'), args.steps * B * world, cpool, wpool, device_contours=device_contours)
             total = sync_max(time.perf_counter() - t0)
         generated = torch.tensor([stats['batches_this_rank'] * B], device=dev, dtype=torch.int64)
         if world > 1:
@@ -532,6 +555,8 @@ def run_leg_dataset(args, dev, rank, world, out):
                               'seconds': total, 'gpu_only_pairs_per_s': world * args.steps * B / gpu_only,
                               'fraction_of_gpu_rate': (n_gen / total) / (world * args.steps * B / gpu_only),
                               'host_cores': cores, 'contour_workers_per_rank': n_contour, 'png_threads_per_rank': n_png,
+                              'contours': args.contours, 'contour_stage': stats.get('contour_stage'),
+                              'device_contour_stage': contour_info if contour_ms is not None else None,
                               'scratch': 'tmpfs' if base.startswith('/dev/shm') else 'disk',
                               'note': 'wall clock, max over ranks; noise-like masks of a random-init generator (worst case for the contour stage)'}),
                   file=out, flush=True)
@@ -822,6 +847,8 @@ def main():
     ap.add_argument('--profile-steps', type=int, default=10)
     ap.add_argument('--in-flight', type=int, default=2, choices=[1, 2],
                     help='batches in flight on separate CUDA streams / generator workspaces (3 measured slower: do not)')
+    ap.add_argument('--contours', default='auto', choices=['auto', 'device', 'host'],
+                    help='--leg dataset: contour stage on the device (sis_contour_stage) or as host tasks')
     ap.add_argument('--leg', default='', choices=['', 'contours', 'dataset_gan', 'dataset'],
                     help='run one of the extra stage benchmarks (rows after the hot path) instead of the headline metric')
     args = ap.parse_args()

@@ -331,16 +331,116 @@ class LabelledPairGenerator:
             if len(in_flight) >= depth:
                 yield finish(in_flight.pop(0))
 
-    def iter_segmented(self, depth: int = 2, pool=None, lag: int = 1) -> Iterator[SegmentedBatch]:
-        """generate -> label (GPU) -> contour post-processing (host), pipelined: the per-image contour tasks of a batch
-        run on `pool` (a concurrent.futures executor; None = inline) while the GPU produces the next `lag` batches.
-        Yields what the reference's loop has after create_segmentation_image + make_image."""
+    def iter_segmented(self, depth: int = 2, pool=None, lag: int = 1, device_contours: Optional[bool] = None) -> Iterator[SegmentedBatch]:
+        """generate -> label -> contour post-processing, pipelined.  Yields what the reference's loop has after
+        create_segmentation_image + make_image (create_dataset_for_segmentation.py:132-140).
+
+        `device_contours` True: the contour stage runs on the GPU right behind the labelling kernels
+        (`contours_device.DeviceContourStage`); only the uint8 image, the uint8 label image and one flag per image
+        leave the device, and the few images whose drop decision depends on contour order go through the host path.
+        False: the masks are copied out and the per-image host tasks (`contours.segment_masks`) run on `pool` (a
+        concurrent.futures executor; None = inline) while the GPU produces the next `lag` batches.
+        None (default): the device when the configuration is one it handles."""
+        from . import contours_device
+        cfg = self.segmenter.contour_config()
+        if device_contours is None:
+            names = {layer: list(self.segmenter.class_label_map[layer].keys()) for layer in self.segmenter.catalog}
+            for dst in self.segmenter.keys_to_merge:
+                names[dst] = list(self.segmenter.class_to_color_map)
+            device_contours = contours_device.DeviceContourStage(cfg).supports(names) and self.generator.size <= 832
+        if device_contours:
+            yield from self._iter_segmented_device(depth, pool, lag, cfg)
+        else:
+            yield from self._iter_segmented_host(depth, pool, lag, cfg)
+
+    def _iter_segmented_device(self, depth, pool, lag, cfg) -> Iterator[SegmentedBatch]:
+        import collections
+        import contextlib
+
+        import numpy
+
+        from . import contours_device
+        device = self.generator.input.input.device
+        seg = self.segmenter
+        lanes = self._lanes(device)
+        stages = [contours_device.DeviceContourStage(cfg) for _ in lanes]      # one workspace per lane
+        B, S = self.config['batch_size'], self.generator.size
+        copy_stream = torch.cuda.Stream(device=device)
+        n_slots = max(depth, len(lanes)) + lag + 1
+        slots = [{'z': torch.empty(B, self.config['latent_size']).pin_memory(),
+                  'image': torch.empty(B, S, S, 3, dtype=torch.uint8).pin_memory(),
+                  'label': torch.empty(B, S, S, 3, dtype=torch.uint8).pin_memory(),
+                  'flags': torch.empty(B, dtype=torch.int32).pin_memory()} for _ in range(n_slots)]
+        keys = set(cfg.keys_for_class_determination) | set(cfg.keys_for_finegrained_segmentation)
+        pending = collections.deque()
+        self.contour_stats = {'images': 0, 'host_fallback': 0}
+
+        def finish(slot):
+            slot['done'].synchronize()
+            flags = slot['flags'].numpy()
+            images, labels = slot['image'].numpy().copy(), slot['label'].numpy().copy()
+            drop = [int(b) for b in numpy.flatnonzero(flags == contours_device.FLAG_DROP)]
+            undecided = [int(b) for b in numpy.flatnonzero(flags == contours_device.FLAG_HOST)]
+            self.contour_stats['images'] += len(flags)
+            self.contour_stats['host_fallback'] += len(undecided)
+            if undecided:
+                idx = torch.as_tensor(undecided, device=device)
+                host = {k: (n, m.index_select(1, idx).cpu().numpy()) for k, (n, m) in slot['stacked'].items() if k in keys}
+                tasks = [(pool.submit(contours_device.host_fallback, host, [j], cfg) if pool is not None
+                          else contours_device.host_fallback(host, [j], cfg)) for j in range(len(undecided))]
+                for j, b in enumerate(undecided):
+                    res = tasks[j].result() if hasattr(tasks[j], 'result') else tasks[j]
+                    labels[b] = res[j][0]
+                    if res[j][1]:
+                        drop.append(b)
+            slot['stacked'] = slot['keep'] = None
+            return SegmentedBatch(slot['index'], images, labels, sorted(drop))
+
+        n = 0
+        latent_stream = sharded_latent_stream(self.generator, self.config, self.seed, self.rank, self.world_size, self.replay_stream)
+        while True:
+            slot = slots[n % n_slots]
+            g, st = lanes[n % len(lanes)]
+            with (torch.cuda.stream(st) if st is not None else contextlib.nullcontext()):
+                idx, latents = next(latent_stream)
+                slot['z'].copy_(latents.latent)
+                lat = Latents(slot['z'].to(device, non_blocking=True), latents.noise)
+                if self.fused_labelling:
+                    jobs = seg.make_label_jobs(g, B)
+                    acts, image = generate_images(lat, g, device=device, mean_latent=self.mean_latent, capture_layers=self.capture_layers,
+                                                  label_jobs=jobs, mix_inject_index=self.mix_inject_index)
+                    stacked = seg.jobs_to_stacked(jobs)
+                else:
+                    acts, image = generate_images(lat, g, device=device, mean_latent=self.mean_latent, capture_layers=self.capture_layers,
+                                                  mix_inject_index=self.mix_inject_index)
+                    stacked = seg.label_layers_stacked(acts)
+                if seg.keys_to_merge:
+                    stacked = seg.merge_stacked(stacked)
+                image_u8 = make_image(image)
+                label_rgb, flags = stages[n % len(lanes)].run(stacked)
+                ready = torch.cuda.Event()
+                ready.record(torch.cuda.current_stream(device))
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ready)
+                slot['image'].copy_(image_u8, non_blocking=True)
+                slot['label'].copy_(label_rgb, non_blocking=True)
+                slot['flags'].copy_(flags, non_blocking=True)
+                slot['done'] = torch.cuda.Event()
+                slot['done'].record(copy_stream)
+            slot['keep'], slot['stacked'], slot['index'] = (image_u8, label_rgb, flags, lat, acts), stacked, idx
+            pending.append(slot)
+            self.stats['pairs'] += B
+            self.stats['batches'] += 1
+            n += 1
+            if len(pending) > max(lag, len(lanes) - 1):
+                yield finish(pending.popleft())
+
+    def _iter_segmented_host(self, depth, pool, lag, cfg) -> Iterator[SegmentedBatch]:
         import collections
 
         import numpy
 
         from . import contours
-        cfg = self.segmenter.contour_config()
         keys = set(cfg.keys_for_class_determination) | set(cfg.keys_for_finegrained_segmentation)
         pending = collections.deque()
 

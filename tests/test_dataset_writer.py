@@ -110,3 +110,18 @@ def test_has_class_flags_and_split(tmp_path):
     assert all(set(e) == {'file_name', 'has_printed_text', 'has_handwritten_text'} for e in t + v)
     by_name = {e['file_name']: e for e in t + v}
     assert by_name['0/0/0001.png']['has_printed_text'] and not by_name['0/0/0000.png']['has_printed_text']
+
+
+def test_png_encoders_decode_equal(tmp_path):
+    """The fast libpng writer and the reference's PIL call produce files that decode to the same pixels."""
+    from PIL import Image
+    rng = numpy.random.RandomState(3)
+    image = rng.randint(0, 256, size=(32, 64, 3)).astype(numpy.uint8)
+    a = dw.save_image(image, 7, tmp_path / 'cv2', '{id}.png', encoder='cv2')
+    b = dw.save_image(image, 7, tmp_path / 'pil', '{id}.png', encoder='pil')
+    assert numpy.array_equal(numpy.array(Image.open(a)), image) and numpy.array_equal(numpy.array(Image.open(b)), image)
+    gray = rng.randint(0, 256, size=(16, 16)).astype(numpy.uint8)
+    c = dw.save_image(gray, 8, tmp_path / 'cv2', '{id}.png', encoder='cv2')
+    assert numpy.array_equal(numpy.array(Image.open(c)), gray)
+    with pytest.raises(ValueError):
+        dw.save_image(image, 9, tmp_path, '{id}.png', encoder='bmp')

@@ -188,9 +188,10 @@ def test_create_segmentation_image_equals_oracle_contour_stage(cuda_device):
     assert (par_images == label_images).all() and sorted(par_drop) == sorted(drop)
 
 
-def test_build_dataset_writes_the_reference_layout(cuda_device, tmp_path):
-    """§8(f) rows 1+2 end to end: pipelined generate -> label -> contours -> PNG tree; every file is make_image || label
-    image of a kept sample, ids are the running count of kept images."""
+@pytest.mark.parametrize('device_contours,in_flight', [(True, 1), (True, 2), (False, 1)])
+def test_build_dataset_writes_the_reference_layout(cuda_device, tmp_path, device_contours, in_flight):
+    """§8(f) rows 1+2 end to end: pipelined generate -> label -> contours (device stage or host tasks) -> PNG tree; every
+    file is make_image || label image of a kept sample, ids are the running count of kept images."""
     import numpy
     from concurrent.futures import ThreadPoolExecutor
     from PIL import Image
@@ -200,7 +201,9 @@ def test_build_dataset_writes_the_reference_layout(cuda_device, tmp_path):
     spec, sd, g, seg, cents = make_setup(32, layers, cuda_device)
     cfg = {'batch_size': 4, 'latent_size': 512}
     with ThreadPoolExecutor(2) as cpool, ThreadPoolExecutor(2) as wpool:
-        stats = dw.build_dataset(dc.LabelledPairGenerator(g, seg, cfg, seed=1), tmp_path, 10, cpool, wpool)
+        stats = dw.build_dataset(dc.LabelledPairGenerator(g, seg, cfg, seed=1, in_flight=in_flight), tmp_path, 10, cpool, wpool,
+                                 device_contours=device_contours)
+    assert ('host' in stats['contour_stage']) == (not device_contours)
     files = sorted(tmp_path.glob('**/*.png'))
     assert stats['images_kept_all_ranks'] >= 10 and len(files) == stats['files_written_this_rank'] == stats['images_kept_all_ranks']
     # replay the stream without the pipeline
@@ -245,3 +248,21 @@ def test_two_batches_in_flight_equal_single_stream(cuda_device):
         assert h.batch_index == idx and torch.equal(h.image, image)
         for layer in layers:
             assert torch.equal(h.masks[layer], masks[layer])
+
+
+def test_segmented_stream_device_equals_host(cuda_device):
+    """The device contour stage inside the pipelined loop gives the host path's batches: same images, label images and
+    drop lists, batch for batch (256^2, the BASELINE layers, two lanes)."""
+    import itertools
+    import numpy
+    layers = ['8', '9', '12', '13']
+    spec, sd, g, seg, cents = make_setup(256, layers, cuda_device)
+    cfg = {'batch_size': 4, 'latent_size': 512}
+    host = list(itertools.islice(dc.LabelledPairGenerator(g, seg, cfg, seed=5).iter_segmented(device_contours=False), 3))
+    pipe = dc.LabelledPairGenerator(g, seg, cfg, seed=5, in_flight=2)
+    dev = list(itertools.islice(pipe.iter_segmented(device_contours=True), 3))
+    for h, d in zip(host, dev):
+        assert h.batch_index == d.batch_index
+        assert numpy.array_equal(h.images, d.images) and numpy.array_equal(h.label_images, d.label_images)
+        assert sorted(h.image_ids_to_drop) == sorted(d.image_ids_to_drop)
+    assert pipe.contour_stats['images'] >= 12
