@@ -500,7 +500,9 @@ def run_leg_dataset(args, dev, rank, world, out):
 
     try:
         spawn = multiprocessing.get_context('spawn')
-        with ProcessPoolExecutor(n_contour, mp_context=spawn) as cpool, ThreadPoolExecutor(n_png) as wpool:
+        # host contours: one process per worker (Python-heavy tasks); device contours: the rare fall-backs run on threads
+        with (ProcessPoolExecutor(n_contour, mp_context=spawn) if args.contours == 'host' else ThreadPoolExecutor(n_contour)) as cpool, \
+                ThreadPoolExecutor(n_png) as wpool:
             # GPU-only rate of the same pipeline (host buffers out, nothing downstream)
             pipe = dc.LabelledPairGenerator(g, seg, cfg, seed=1, rank=rank, world_size=world, in_flight=args.in_flight)
             it = pipe.iter_host(depth=2, image_u8=True)
@@ -555,7 +557,7 @@ def run_leg_dataset(args, dev, rank, world, out):
                               'seconds': total, 'gpu_only_pairs_per_s': world * args.steps * B / gpu_only,
                               'fraction_of_gpu_rate': (n_gen / total) / (world * args.steps * B / gpu_only),
                               'host_cores': cores, 'contour_workers_per_rank': n_contour, 'png_threads_per_rank': n_png,
-                              'contours': args.contours, 'contour_stage': stats.get('contour_stage'),
+                              'contours': args.contours, 'contour_stage': stats.get('contour_stage'), 'seconds_by_part': stats.get('seconds'),
                               'device_contour_stage': contour_info if contour_ms is not None else None,
                               'scratch': 'tmpfs' if base.startswith('/dev/shm') else 'disk',
                               'note': 'wall clock, max over ranks; noise-like masks of a random-init generator (worst case for the contour stage)'}),

@@ -366,35 +366,68 @@ class LabelledPairGenerator:
         stages = [contours_device.DeviceContourStage(cfg) for _ in lanes]      # one workspace per lane
         B, S = self.config['batch_size'], self.generator.size
         copy_stream = torch.cuda.Stream(device=device)
-        n_slots = max(depth, len(lanes)) + lag + 1
+        n_slots = max(depth, len(lanes)) + lag + 3
         slots = [{'z': torch.empty(B, self.config['latent_size']).pin_memory(),
                   'image': torch.empty(B, S, S, 3, dtype=torch.uint8).pin_memory(),
                   'label': torch.empty(B, S, S, 3, dtype=torch.uint8).pin_memory(),
                   'flags': torch.empty(B, dtype=torch.int32).pin_memory()} for _ in range(n_slots)]
         keys = set(cfg.keys_for_class_determination) | set(cfg.keys_for_finegrained_segmentation)
         pending = collections.deque()
-        self.contour_stats = {'images': 0, 'host_fallback': 0}
+        self.contour_stats = {'images': 0, 'host_fallback': 0, 'wait_copy_s': 0.0, 'wait_fallback_s': 0.0}
 
-        def finish(slot):
+        import time
+        resolved = collections.deque()      # batches whose flags are known; their host fall-backs (if any) are running
+
+        def resolve(slot):
+            """Copies done: read the flags, start the host path for the undecided images (asynchronously on `pool`)."""
+            t0 = time.perf_counter()
             slot['done'].synchronize()
+            self.contour_stats['wait_copy_s'] += time.perf_counter() - t0
             flags = slot['flags'].numpy()
             images, labels = slot['image'].numpy().copy(), slot['label'].numpy().copy()
             drop = [int(b) for b in numpy.flatnonzero(flags == contours_device.FLAG_DROP)]
             undecided = [int(b) for b in numpy.flatnonzero(flags == contours_device.FLAG_HOST)]
             self.contour_stats['images'] += len(flags)
             self.contour_stats['host_fallback'] += len(undecided)
+            tasks = []
             if undecided:
                 idx = torch.as_tensor(undecided, device=device)
                 host = {k: (n, m.index_select(1, idx).cpu().numpy()) for k, (n, m) in slot['stacked'].items() if k in keys}
-                tasks = [(pool.submit(contours_device.host_fallback, host, [j], cfg) if pool is not None
-                          else contours_device.host_fallback(host, [j], cfg)) for j in range(len(undecided))]
-                for j, b in enumerate(undecided):
-                    res = tasks[j].result() if hasattr(tasks[j], 'result') else tasks[j]
-                    labels[b] = res[j][0]
-                    if res[j][1]:
-                        drop.append(b)
+                for j in range(len(undecided)):
+                    one = {k: (n, m[:, j:j + 1]) for k, (n, m) in host.items()}
+                    tasks.append(pool.submit(contours_device.host_fallback, one, [0], cfg) if pool is not None
+                                 else contours_device.host_fallback(one, [0], cfg))
             slot['stacked'] = slot['keep'] = None
-            return SegmentedBatch(slot['index'], images, labels, sorted(drop))
+            resolved.append((slot['index'], images, labels, drop, undecided, tasks))
+
+        def collect():
+            index, images, labels, drop, undecided, tasks = resolved.popleft()
+            t0 = time.perf_counter()
+            for b, task in zip(undecided, tasks):
+                res = task.result() if hasattr(task, 'result') else task
+                labels[b] = res[0][0]
+                if res[0][1]:
+                    drop.append(b)
+            self.contour_stats['wait_fallback_s'] += time.perf_counter() - t0
+            return SegmentedBatch(index, images, labels, sorted(drop))
+
+        launched = collections.deque()      # generator + labelling enqueued, contour stage not yet
+
+        def contour_and_copy(slot):
+            st = lanes[slot['lane']][1]
+            with (torch.cuda.stream(st) if st is not None else contextlib.nullcontext()):
+                label_rgb, flags = stages[slot['lane']].run(slot['stacked'])
+                ready = torch.cuda.Event()
+                ready.record(torch.cuda.current_stream(device))
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(ready)
+                slot['image'].copy_(slot['keep'][0], non_blocking=True)
+                slot['label'].copy_(label_rgb, non_blocking=True)
+                slot['flags'].copy_(flags, non_blocking=True)
+                slot['done'] = torch.cuda.Event()
+                slot['done'].record(copy_stream)
+            slot['keep'] = slot['keep'] + (label_rgb, flags)
+            pending.append(slot)
 
         n = 0
         latent_stream = sharded_latent_stream(self.generator, self.config, self.seed, self.rank, self.world_size, self.replay_stream)
@@ -417,23 +450,19 @@ class LabelledPairGenerator:
                 if seg.keys_to_merge:
                     stacked = seg.merge_stacked(stacked)
                 image_u8 = make_image(image)
-                label_rgb, flags = stages[n % len(lanes)].run(stacked)
-                ready = torch.cuda.Event()
-                ready.record(torch.cuda.current_stream(device))
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(ready)
-                slot['image'].copy_(image_u8, non_blocking=True)
-                slot['label'].copy_(label_rgb, non_blocking=True)
-                slot['flags'].copy_(flags, non_blocking=True)
-                slot['done'] = torch.cuda.Event()
-                slot['done'].record(copy_stream)
-            slot['keep'], slot['stacked'], slot['index'] = (image_u8, label_rgb, flags, lat, acts), stacked, idx
-            pending.append(slot)
+            slot['keep'], slot['stacked'], slot['index'], slot['lane'] = (image_u8, lat, acts), stacked, idx, n % len(lanes)
+            launched.append(slot)
             self.stats['pairs'] += B
             self.stats['batches'] += 1
             n += 1
+            # The contour stage of the batch BEFORE the one just enqueued: its host round trips (fixpoint control) now
+            # fall into the time the GPU spends on the newer batch's generator kernels, on the other lane's stream.
+            if len(launched) > (1 if len(lanes) > 1 else 0):
+                contour_and_copy(launched.popleft())
             if len(pending) > max(lag, len(lanes) - 1):
-                yield finish(pending.popleft())
+                resolve(pending.popleft())
+                if len(resolved) > 1:           # a batch's fall-backs get one batch of time before they are waited for
+                    yield collect()
 
     def _iter_segmented_host(self, depth, pool, lag, cfg) -> Iterator[SegmentedBatch]:
         import collections

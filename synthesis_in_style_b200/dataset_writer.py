@@ -191,12 +191,18 @@ def build_dataset(pair_generator, base_dir, num_images: int, contour_pool=None, 
     Returns counters."""
     writer = DatasetWriter(base_dir, num_images, pair_generator.rank, pair_generator.world_size, writer_pool,
                            device=pair_generator.generator.input.input.device if pair_generator.world_size > 1 else None)
-    batches = 0
+    import time
+    batches, t_add, t0 = 0, 0.0, time.perf_counter()
     for sb in pair_generator.iter_segmented(depth=depth, pool=contour_pool, device_contours=device_contours):
+        t1 = time.perf_counter()
         writer.add(sb.images, sb.label_images, sb.image_ids_to_drop)
+        t_add += time.perf_counter() - t1
         batches += 1
         if writer.finished:
             break
+    t_loop = time.perf_counter() - t0
     writer.flush()
+    t_flush = time.perf_counter() - t0 - t_loop
     return {'images_kept_all_ranks': writer.n, 'files_written_this_rank': writer.files_written, 'batches_this_rank': batches,
-            'contour_stage': dict(getattr(pair_generator, 'contour_stats', None) or {'host': True})}
+            'contour_stage': dict(getattr(pair_generator, 'contour_stats', None) or {'host': True}),
+            'seconds': {'loop': round(t_loop, 4), 'writer_add': round(t_add, 4), 'final_flush': round(t_flush, 4)}}
