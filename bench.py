@@ -475,6 +475,8 @@ def run_leg_dataset(args, dev, rank, world, out):
     from synthesis_in_style_b200.model import Generator
     wl = WORKLOADS[2]
     B, S = (args.batch or wl['batch']), wl['size']
+    if args.png:
+        dw.PNG_ENCODER = args.png
     spec, sd = oracle_state(S)
     g = Generator(S, STYLE_DIM, N_MLP, precision=args.precision)
     g.load_state_dict(sd)
@@ -557,7 +559,7 @@ def run_leg_dataset(args, dev, rank, world, out):
                               'seconds': total, 'gpu_only_pairs_per_s': world * args.steps * B / gpu_only,
                               'fraction_of_gpu_rate': (n_gen / total) / (world * args.steps * B / gpu_only),
                               'host_cores': cores, 'contour_workers_per_rank': n_contour, 'png_threads_per_rank': n_png,
-                              'contours': args.contours, 'contour_stage': stats.get('contour_stage'), 'seconds_by_part': stats.get('seconds'),
+                              'png_encoder': dw.PNG_ENCODER, 'contours': args.contours, 'contour_stage': stats.get('contour_stage'), 'seconds_by_part': stats.get('seconds'),
                               'device_contour_stage': contour_info if contour_ms is not None else None,
                               'scratch': 'tmpfs' if base.startswith('/dev/shm') else 'disk',
                               'note': 'wall clock, max over ranks; noise-like masks of a random-init generator (worst case for the contour stage)'}),
@@ -849,6 +851,8 @@ def main():
     ap.add_argument('--profile-steps', type=int, default=10)
     ap.add_argument('--in-flight', type=int, default=2, choices=[1, 2],
                     help='batches in flight on separate CUDA streams / generator workspaces (3 measured slower: do not)')
+    ap.add_argument('--png', default='', choices=['', 'fast', 'stored', 'cv2', 'pil'],
+                    help='--leg dataset: PNG writer (dataset_writer.PNG_ENCODER; default: the module default)')
     ap.add_argument('--contours', default='auto', choices=['auto', 'device', 'host'],
                     help='--leg dataset: contour stage on the device (sis_contour_stage) or as host tasks')
     ap.add_argument('--leg', default='', choices=['', 'contours', 'dataset_gan', 'dataset'],

@@ -245,6 +245,15 @@ SIS_API int sis_contour_stage(const uint8_t* const* d_det_masks, const uint8_t* 
                       void* stream);
 
 /* -----------------------------------------------------------------------------------------------------------
+ * Host-side writer of the dataset's PNG files (no device work; HOST pointers): file i holds, side by side, row rows[i]
+ * of `h_left` [n, height, width_left, channels] and of `h_right` [n, height, width_right, channels] (either side may be
+ * absent: width 0).  Replaces scf/create_dataset_for_segmentation.py:84-99 (save_image / save_generated_images:
+ * numpy.concatenate + PIL.Image.save per file) with native threads: filter 'Up', zlib `level` (0 = stored), one IDAT.
+ * The parent directories must exist.  Blocks until every file is written; call it off the thread that drives the GPU. */
+SIS_API int sis_png_write_pairs(const uint8_t* h_left, const uint8_t* h_right, int height, int width_left, int width_right,
+                        int channels, const int32_t* rows, const char* const* paths, int n_files, int level, int n_threads);
+
+/* -----------------------------------------------------------------------------------------------------------
  * DatasetGAN labeller (the other `segmenter_type`): every capture -> ensemble of per-pixel MLP classifiers -> labels.
  * Replaces DatasetGANSegmenter.create_segmentation_image's device work
  *   scf/segmentation/dataset_gan_segmenter.py:34-60  (predict_labels, label_images_to_color_images)

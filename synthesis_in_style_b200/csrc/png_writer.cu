@@ -1,0 +1,114 @@
+// Host-side PNG writer of the dataset tree: side-by-side "image || label" files, encoded and
+// written by native threads, so the Python process that drives the GPUs never competes with its own writer threads for
+// the interpreter lock.  Replaces the per-file call of the reference,
+//   scf/create_dataset_for_segmentation.py:84-99   save_image / save_generated_images
+//       (numpy.concatenate([generated, label], axis=2), PIL.Image.fromarray(...).save(dest)).
+// Same pixels, different bytes: every row uses PNG filter 'Up' (row minus the row above, mod 256), the stream is zlib at
+// the requested level (1 by default; 0 = stored blocks), one IDAT chunk.  No CUDA in this file.
+#include <zlib.h>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+#include "common.cuh"
+
+namespace sis {
+
+static void put_u32(std::vector<uint8_t>& v, uint32_t x) {
+    v.push_back((uint8_t)(x >> 24)); v.push_back((uint8_t)(x >> 16)); v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x);
+}
+static void put_chunk(std::vector<uint8_t>& out, const char tag[4], const uint8_t* body, size_t n) {
+    put_u32(out, (uint32_t)n);
+    const size_t at = out.size();
+    out.insert(out.end(), tag, tag + 4);
+    if (n) out.insert(out.end(), body, body + n);
+    put_u32(out, (uint32_t)crc32(0L, out.data() + at, (uInt)(n + 4)));
+}
+
+// one file: rows of `left` then `right` (either may be absent: width 0), c channels
+static bool write_png_file(const char* path, const uint8_t* left, int wl, const uint8_t* right, int wr, int h, int c, int level,
+                           std::vector<uint8_t>& raw, std::vector<uint8_t>& comp, std::vector<uint8_t>& file, std::string& err) {
+    static const int color_type[5] = {0, 0, 4, 2, 6};
+    const size_t row = (size_t)(wl + wr) * c, stride = row + 1;
+    raw.resize(stride * h);
+    for (int y = 0; y < h; ++y) {
+        uint8_t* dst = raw.data() + stride * y;
+        const uint8_t* l = left ? left + (size_t)y * wl * c : nullptr;
+        const uint8_t* r = right ? right + (size_t)y * wr * c : nullptr;
+        if (level == 0 || y == 0) {
+            dst[0] = level == 0 ? 0 : 2;              // the first row's predecessor is all zeros: 'Up' leaves it as it is
+            if (l) memcpy(dst + 1, l, (size_t)wl * c);
+            if (r) memcpy(dst + 1 + (size_t)wl * c, r, (size_t)wr * c);
+        } else {
+            dst[0] = 2;
+            if (l) { const uint8_t* p = l - (size_t)wl * c; for (size_t i = 0; i < (size_t)wl * c; ++i) dst[1 + i] = (uint8_t)(l[i] - p[i]); }
+            if (r) { const uint8_t* p = r - (size_t)wr * c; uint8_t* d = dst + 1 + (size_t)wl * c; for (size_t i = 0; i < (size_t)wr * c; ++i) d[i] = (uint8_t)(r[i] - p[i]); }
+        }
+    }
+    uLongf clen = compressBound((uLong)raw.size());
+    comp.resize(clen);
+    if (compress2(comp.data(), &clen, raw.data(), (uLong)raw.size(), level) != Z_OK) { err = std::string("zlib failed for ") + path; return false; }
+    file.clear();
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+    file.insert(file.end(), sig, sig + 8);
+    uint8_t ihdr[13];
+    const uint32_t w = (uint32_t)(wl + wr);
+    ihdr[0] = w >> 24; ihdr[1] = w >> 16; ihdr[2] = w >> 8; ihdr[3] = w;
+    ihdr[4] = (uint32_t)h >> 24; ihdr[5] = (uint32_t)h >> 16; ihdr[6] = (uint32_t)h >> 8; ihdr[7] = (uint32_t)h;
+    ihdr[8] = 8; ihdr[9] = (uint8_t)color_type[c]; ihdr[10] = 0; ihdr[11] = 0; ihdr[12] = 0;
+    put_chunk(file, "IHDR", ihdr, 13);
+    put_chunk(file, "IDAT", comp.data(), clen);
+    put_chunk(file, "IEND", nullptr, 0);
+    FILE* f = fopen(path, "wb");
+    if (!f) { err = std::string("cannot open ") + path; return false; }
+    const bool ok = fwrite(file.data(), 1, file.size(), f) == file.size();
+    if (fclose(f) != 0 || !ok) { err = std::string("short write to ") + path; return false; }
+    return true;
+}
+
+}  // namespace sis
+
+using namespace sis;
+
+extern "C" int sis_png_write_pairs(const uint8_t* h_left, const uint8_t* h_right, int height, int width_left, int width_right,
+                                   int channels, const int32_t* rows, const char* const* paths, int n_files, int level,
+                                   int n_threads) {
+    SIS_REQUIRE(height > 0 && width_left >= 0 && width_right >= 0 && width_left + width_right > 0, "png writer: empty image");
+    SIS_REQUIRE(channels >= 1 && channels <= 4, "png writer: 1..4 channels (got %d)", channels);
+    SIS_REQUIRE(level >= 0 && level <= 9, "png writer: zlib level 0..9 (got %d)", level);
+    SIS_REQUIRE((h_left || width_left == 0) && (h_right || width_right == 0), "png writer: null image pointer");
+    if (n_files <= 0) return SIS_OK;
+    SIS_REQUIRE(rows && paths, "png writer: null row / path list");
+    if (n_threads < 1) n_threads = 1;
+    if (n_threads > n_files) n_threads = n_files;
+    std::atomic<int> next{0}, failed{0};
+    std::string first_error;
+    std::atomic_flag err_lock = ATOMIC_FLAG_INIT;
+    auto work = [&]() {
+        std::vector<uint8_t> raw, comp, file;
+        std::string err;
+        for (int i = next.fetch_add(1); i < n_files; i = next.fetch_add(1)) {
+            const size_t r = (size_t)rows[i];
+            const uint8_t* l = width_left ? h_left + r * (size_t)height * width_left * channels : nullptr;
+            const uint8_t* rr = width_right ? h_right + r * (size_t)height * width_right * channels : nullptr;
+            if (!write_png_file(paths[i], l, width_left, rr, width_right, height, channels, level, raw, comp, file, err)) {
+                if (!failed.exchange(1)) {
+                    while (err_lock.test_and_set()) {}
+                    first_error = err;
+                    err_lock.clear();
+                }
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    if (failed.load()) {
+        set_error("png writer: %s", first_error.c_str());
+        return SIS_ERR_INVALID;
+    }
+    return SIS_OK;
+}

@@ -37,23 +37,60 @@ def name_format_for(num_images: int) -> str:
     return f'{{id:0{max(4, len(str(num_images)))}d}}.png'
 
 
-# PNG encoder of save_image.  'pil' is the reference's call (Image.fromarray(image).save(dest), :88: zlib level 6, 44 ms for
-# a 256 x 512 side-by-side image on one core, and PIL holds the GIL while it deflates, so a thread pool scales 2x at
-# best).  'cv2' writes the same pixels through libpng at its fast setting (5-7 ms, GIL released: a thread pool scales
-# with the cores); the files decode to identical arrays and are ~20 % larger.
-PNG_ENCODER = 'cv2'
+# PNG encoder of save_image.  All of them write files that decode to the same pixels:
+#   'pil'    the reference's call (Image.fromarray(image).save(dest), :88): zlib level 6 behind PIL's adaptive filter, 44 ms
+#            for a 256 x 512 side-by-side image on one core, and PIL holds the GIL while it deflates, so a thread pool
+#            scales 2x at best; 87 KB.  Use it to reproduce the reference's bytes.
+#   'cv2'    libpng at its fast setting: 5-7 ms, GIL released, 105 KB.
+#   'fast'   (default) this module's writer: 'Up' filter on every row (one vectorised subtraction), zlib level 1, the three
+#            chunks assembled by hand: 3.9 ms, 120 KB; zlib and numpy release the GIL, a thread pool scales with the cores.
+#   'stored' the same writer at zlib level 0 (stored deflate blocks): 0.6 ms, 394 KB -- when the writer must keep up with
+#            several GPUs on few host cores.
+PNG_ENCODER = 'fast'
+_PNG_COLOR_TYPE = {1: 0, 2: 4, 3: 2, 4: 6}          # channels -> PNG colour type (grey, grey+alpha, RGB, RGBA)
+
+
+def png_bytes(image: numpy.ndarray, level: int = 1) -> bytes:
+    """A complete PNG file (8-bit, non-interlaced) for an [H, W] or [H, W, C] uint8 array."""
+    import struct
+    import zlib
+    if image.dtype != numpy.uint8 or image.ndim not in (2, 3):
+        raise ValueError('png_bytes expects a uint8 [H, W] or [H, W, C] array')
+    h, w = image.shape[:2]
+    c = 1 if image.ndim == 2 else image.shape[2]
+    if c not in _PNG_COLOR_TYPE or h == 0 or w == 0:
+        raise ValueError(f'cannot write a PNG of shape {image.shape}')
+    flat = numpy.ascontiguousarray(image).reshape(h, w * c)
+    raw = numpy.empty((h, 1 + w * c), dtype=numpy.uint8)
+    if level == 0:
+        raw[:, 0] = 0                                     # filter 'None': nothing to gain without compression
+        raw[:, 1:] = flat
+    else:
+        raw[:, 0] = 2                                     # filter 'Up': row minus the row above (mod 256); the first row's
+        raw[0, 1:] = flat[0]                              # predecessor is all zeros
+        numpy.subtract(flat[1:], flat[:-1], out=raw[1:, 1:])
+    data = zlib.compress(raw, level)
+
+    def chunk(tag: bytes, body: bytes) -> bytes:
+        return struct.pack('>I', len(body)) + tag + body + struct.pack('>I', zlib.crc32(body, zlib.crc32(tag)))
+
+    return b''.join((b'\x89PNG\r\n\x1a\n', chunk(b'IHDR', struct.pack('>IIBBBBB', w, h, 8, _PNG_COLOR_TYPE[c], 0, 0, 0)),
+                     chunk(b'IDAT', data), chunk(b'IEND', b'')))
 
 
 def encode_png(image: numpy.ndarray, dest, encoder: Optional[str] = None):
     encoder = encoder or PNG_ENCODER
     if encoder == 'pil':
         Image.fromarray(image).save(str(dest))
-        return
-    if encoder != 'cv2':
+    elif encoder == 'cv2':
+        data = image if image.ndim == 2 else cv2.cvtColor(image, cv2.COLOR_RGB2BGR if image.shape[2] == 3 else cv2.COLOR_RGBA2BGRA)
+        if not cv2.imwrite(str(dest), data):
+            raise OSError(f'could not write {dest}')
+    elif encoder in ('fast', 'stored'):
+        with open(str(dest), 'wb') as f:
+            f.write(png_bytes(image, 1 if encoder == 'fast' else 0))
+    else:
         raise ValueError(f'unknown PNG encoder {encoder!r}')
-    data = image if image.ndim == 2 else cv2.cvtColor(image, cv2.COLOR_RGB2BGR if image.shape[2] == 3 else cv2.COLOR_RGBA2BGRA)
-    if not cv2.imwrite(str(dest), data):
-        raise OSError(f'could not write {dest}')
 
 
 def save_image(image: numpy.ndarray, image_id: int, base_dir: Path, name_format: str = '{id}.png', encoder: Optional[str] = None) -> Path:
@@ -71,6 +108,31 @@ def save_generated_images(generated_images: numpy.ndarray, semantic_segmentation
     if pool is None:
         return [save_image(image, batch_id + idx, base_dir, fmt) for idx, image in enumerate(images)]
     return [pool.submit(save_image, image, batch_id + idx, base_dir, fmt) for idx, image in enumerate(images)]
+
+
+def save_generated_images_native(generated_images: numpy.ndarray, semantic_segmentation_images: numpy.ndarray, rows: Sequence[int],
+                                 batch_id: int, base_dir: Path, num_images: int, level: int = 1, n_threads: int = 4) -> List[Path]:
+    """save_generated_images (:93-99) for the rows `rows` of a batch, through the library's native writer
+    (`sis_png_write_pairs`, csrc/png_writer.cu): concatenation, filtering, deflate and the file writes run on native
+    threads without the interpreter lock.  File i gets id batch_id + i.  Blocks until the files are on disk."""
+    import ctypes
+
+    from . import _lib
+    gen = numpy.ascontiguousarray(generated_images, dtype=numpy.uint8)
+    lab = numpy.ascontiguousarray(semantic_segmentation_images, dtype=numpy.uint8)
+    if gen.ndim != 4 or lab.ndim != 4 or gen.shape[0] != lab.shape[0] or gen.shape[1] != lab.shape[1] or gen.shape[3] != lab.shape[3]:
+        raise ValueError(f'expected two [B, H, W, C] batches of equal height and channels, got {gen.shape} and {lab.shape}')
+    fmt = name_format_for(num_images)
+    paths = [image_file_name(batch_id + i, base_dir, fmt) for i in range(len(rows))]
+    for parent in {p.parent for p in paths}:
+        parent.mkdir(exist_ok=True, parents=True)
+    if not paths:
+        return paths
+    c_rows = (ctypes.c_int32 * len(rows))(*[int(r) for r in rows])
+    c_paths = (ctypes.c_char_p * len(paths))(*[str(p).encode() for p in paths])
+    _lib.check(_lib.load().sis_png_write_pairs(gen.ctypes.data, lab.ctypes.data, gen.shape[1], gen.shape[2], lab.shape[2], gen.shape[3],
+                                               c_rows, c_paths, len(paths), level, max(1, int(n_threads))))
+    return paths
 
 
 # --------------------------------------------------------------------------- running ids across ranks
@@ -105,17 +167,43 @@ def exchange_kept_counts(kept: int, device=None) -> List[int]:
 class DatasetWriter:
     """The tail of build_dataset's loop for one rank: drop, assign ids, write the PNGs."""
 
-    def __init__(self, base_dir, num_images: int, rank: int = 0, world_size: int = 1, pool=None, device=None):
+    def __init__(self, base_dir, num_images: int, rank: int = 0, world_size: int = 1, pool=None, device=None,
+                 native: Optional[bool] = None, native_threads: Optional[int] = None):
+        """`native` (default: whenever PNG_ENCODER is 'fast' or 'stored'): batches go to the library's native writer
+        (`sis_png_write_pairs`) from ONE background thread, with `native_threads` encoder threads inside the call (default:
+        the size of `pool`, else the host's cores); otherwise one `save_image` task per file on `pool`."""
         self.base_dir, self.num_images = Path(base_dir), num_images
         self.rank, self.world_size, self.pool, self.device = rank, world_size, pool, device
         self.n = 0                       # the reference's pbar.n: images kept so far, over all ranks
         self.finished = False
         self._futures = []
         self.files_written = 0
+        self.native = PNG_ENCODER in ('fast', 'stored') if native is None else bool(native)
+        self._level = 0 if PNG_ENCODER == 'stored' else 1
+        if native_threads is None:
+            import os
+            native_threads = getattr(pool, '_max_workers', None) or os.cpu_count() or 4
+        self.native_threads = native_threads
+        self._native_queue = None
 
     def add(self, generated_images: numpy.ndarray, label_images: numpy.ndarray, image_ids_to_drop: Sequence[int]) -> int:
         """One batch of this rank (one round): returns how many files it queued."""
         drop = list(image_ids_to_drop)
+        if self.native:
+            dropped = set(int(d) for d in drop)
+            rows = [b for b in range(len(label_images)) if b not in dropped]
+            counts = exchange_kept_counts(len(rows), self.device)
+            starts, self.n, self.finished = assign_round_ids(counts, self.n, self.num_images)
+            start = starts[self.rank if len(starts) > 1 else 0]
+            if start is None or not rows:
+                return 0
+            if self._native_queue is None:
+                from concurrent.futures import ThreadPoolExecutor
+                self._native_queue = ThreadPoolExecutor(1)      # one batch at a time; the parallelism is inside the call
+            self._futures.append(self._native_queue.submit(save_generated_images_native, generated_images, label_images, rows, start,
+                                                           self.base_dir, self.num_images, self._level, self.native_threads))
+            self.files_written += len(rows)
+            return len(rows)
         generated_images = numpy.delete(generated_images, drop, axis=0)
         label_images = numpy.delete(label_images, drop, axis=0)
         counts = exchange_kept_counts(len(label_images), self.device)
@@ -133,6 +221,9 @@ class DatasetWriter:
         for f in self._futures:
             f.result()
         self._futures = []
+        if self._native_queue is not None:
+            self._native_queue.shutdown(wait=True)
+            self._native_queue = None
 
 
 # --------------------------------------------------------------------------- train / val JSON

@@ -113,15 +113,54 @@ def test_has_class_flags_and_split(tmp_path):
 
 
 def test_png_encoders_decode_equal(tmp_path):
-    """The fast libpng writer and the reference's PIL call produce files that decode to the same pixels."""
+    """Every PNG writer (the reference's PIL call, libpng's fast setting, this module's own zlib level 1 / stored
+    writers) produces files that decode to the same pixels; RGB, grey and RGBA."""
     from PIL import Image
     rng = numpy.random.RandomState(3)
-    image = rng.randint(0, 256, size=(32, 64, 3)).astype(numpy.uint8)
-    a = dw.save_image(image, 7, tmp_path / 'cv2', '{id}.png', encoder='cv2')
-    b = dw.save_image(image, 7, tmp_path / 'pil', '{id}.png', encoder='pil')
-    assert numpy.array_equal(numpy.array(Image.open(a)), image) and numpy.array_equal(numpy.array(Image.open(b)), image)
-    gray = rng.randint(0, 256, size=(16, 16)).astype(numpy.uint8)
-    c = dw.save_image(gray, 8, tmp_path / 'cv2', '{id}.png', encoder='cv2')
-    assert numpy.array_equal(numpy.array(Image.open(c)), gray)
+    image = rng.randint(0, 256, size=(33, 65, 3)).astype(numpy.uint8)
+    image[5:20] = image[4]                                   # repeated rows: the 'Up' filter path
+    gray = rng.randint(0, 256, size=(16, 17)).astype(numpy.uint8)
+    rgba = rng.randint(0, 256, size=(9, 8, 4)).astype(numpy.uint8)
+    for enc in ('pil', 'cv2', 'fast', 'stored'):
+        for i, arr in enumerate((image, gray, rgba)):
+            f = dw.save_image(arr, i, tmp_path / enc, '{id}.png', encoder=enc)
+            assert numpy.array_equal(numpy.array(Image.open(f)), arr), (enc, arr.shape)
+    assert dw.PNG_ENCODER in ('fast', 'cv2', 'stored', 'pil')
     with pytest.raises(ValueError):
         dw.save_image(image, 9, tmp_path, '{id}.png', encoder='bmp')
+    with pytest.raises(ValueError):
+        dw.png_bytes(image.astype(numpy.float32))
+
+
+def test_native_writer_equals_python_writer(tmp_path):
+    """sis_png_write_pairs (native threads, no GIL) writes the files save_generated_images writes: same names, same
+    pixels; rows select the kept images; stored and deflated variants; an unwritable path is reported."""
+    rng = numpy.random.RandomState(5)
+    gen = rng.randint(0, 256, size=(5, 24, 20, 3), dtype=numpy.uint8)
+    lab = numpy.zeros((5, 24, 28, 3), dtype=numpy.uint8)
+    lab[:, 4:9, 3:17] = (0, 0, 255)
+    rows = [0, 2, 3]
+    for level, sub in ((1, 'fast'), (0, 'stored')):
+        files = dw.save_generated_images_native(gen, lab, rows, 998, tmp_path / sub, 2000, level=level, n_threads=3)
+        assert [f.relative_to(tmp_path / sub).as_posix() for f in files] == ['0/0/0998.png', '0/0/0999.png', '0/1/1000.png']
+        for f, r in zip(files, rows):
+            data = numpy.array(Image.open(f))
+            assert data.shape == (24, 48, 3)
+            assert numpy.array_equal(data[:, :20], gen[r]) and numpy.array_equal(data[:, 20:], lab[r])
+    assert dw.save_generated_images_native(gen, lab, [], 0, tmp_path / 'none', 10) == []
+    blocker = tmp_path / 'blocked'
+    blocker.mkdir()
+    (blocker / '0').write_text('a file where a directory is needed')
+    with pytest.raises((RuntimeError, OSError)):
+        dw.save_generated_images_native(gen, lab, rows, 0, blocker, 10)
+    # the writer object on both paths
+    for native in (True, False):
+        w = dw.DatasetWriter(tmp_path / f'w{int(native)}', 8, native=native)
+        w.add(gen, lab[:, :, :20], [1])
+        w.add(gen, lab[:, :, :20], [])
+        w.flush()
+        assert w.n == 9 and w.finished and w.files_written == 9
+    a, b = _tree(tmp_path / 'w1'), _tree(tmp_path / 'w0')
+    assert a.keys() == b.keys() and len(a) == 9
+    for k in a:
+        assert numpy.array_equal(numpy.array(Image.open(tmp_path / 'w1' / k)), numpy.array(Image.open(tmp_path / 'w0' / k)))
