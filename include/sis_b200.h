@@ -235,13 +235,15 @@ SIS_API int sis_make_image_u8(const float* d_image, int batch, int size, uint8_t
  * d_label_rgb  : uint8 [batch,S,S,3];  d_flags: int32 [batch]: 0 keep, 1 drop, 2 = take this image through the host path
  *                (the reference's drop rule reads the FIRST contour of a class; the device does not order contours and
  *                only decides when the order cannot matter; also set for the whole batch when a capacity is exceeded)
- * info         : HOST, 3 ints or NULL: shapes found, fixpoint rounds, reason the batch was handed to the host (0 none)
- * The call synchronises the stream a few times (fixpoint control) and returns with the last kernels enqueued. */
+ * d_info       : DEVICE, 3 ints or NULL: shapes found, fixpoint rounds that did work, reason the batch was handed to the
+ *                host (0 none, 1 capacity, 2 image size, 3 fixpoint still moving after the enqueued rounds)
+ * Fully asynchronous: the merge fixpoint is controlled on the device (a fixed number of rounds is enqueued, kernels with
+ * nothing left to do return at once); the call never synchronises the stream. */
 SIS_API int sis_contour_stage_workspace_bytes(int batch, int size, int n_classes, int n_det_keys, int n_fine_keys, int64_t* bytes);
 SIS_API int sis_contour_stage(const uint8_t* const* d_det_masks, const uint8_t* const* d_fine_masks, int batch, int size,
                       int n_classes, int n_det_keys, int n_fine_keys, int fine_class, int only_keep_overlapping,
                       double min_class_contour_area, const uint8_t* colors_rgb, const int* render_rank,
-                      void* d_workspace, int64_t workspace_bytes, uint8_t* d_label_rgb, int32_t* d_flags, int32_t* info,
+                      void* d_workspace, int64_t workspace_bytes, uint8_t* d_label_rgb, int32_t* d_flags, int32_t* d_info,
                       void* stream);
 
 /* -----------------------------------------------------------------------------------------------------------

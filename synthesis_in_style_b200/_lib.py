@@ -84,7 +84,7 @@ _SIGNATURES = {
     'sis_make_image_u8': (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p]),
     'sis_contour_stage_workspace_bytes': (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int64)]),
     'sis_contour_stage': (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double,
-                                  c_char_p, POINTER(c_int), c_void_p, c_int64, c_void_p, c_void_p, POINTER(c_int), c_void_p]),
+                                  c_char_p, POINTER(c_int), c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     'sis_png_write_pairs': (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, POINTER(c_char_p), c_int, c_int, c_int]),
     'sis_pixel_ensemble_create': (c_int, [POINTER(c_void_p), c_int, c_int, c_int]),
     'sis_pixel_ensemble_destroy': (None, [c_void_p]),

@@ -9,7 +9,8 @@ i.e. (uint8 [B,S,S,3] colour label images, ids of the images to drop), computed 
 The device does not order contours, and the reference's drop rule reads the FIRST contour of a class.  Whenever that order
 could matter for an image (one contour of a class exceeds 95 % of the image in both directions and another one does
 not), or a capacity of the device stage is exceeded, the kernel flags the image and `segment` sends just that image
-through `contours.segment_masks`, so the results are the reference's in every case.
+through `contours.segment_masks`, so the results are the reference's in every case.  `run` never synchronises: the merge
+fixpoint is controlled on the device.
 """
 import ctypes
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -35,7 +36,7 @@ class DeviceContourStage:
         colors = [cfg.class_to_color_map['background']] + [cfg.class_to_color_map[n] for n in self.classes]
         self._colors = bytes(int(v) for c in colors for v in c)
         self._workspace = None
-        self.last_info = (0, 0, 0)
+        self._info = None
 
     def supports(self, class_names: Dict[str, Sequence[str]]) -> bool:
         """The device stage needs every class under every key it reads (the reference tolerates a key without a class:
@@ -77,17 +78,23 @@ class DeviceContourStage:
             self._workspace = torch.empty(need.value, dtype=torch.uint8, device=device)
         out = torch.empty(B, S, S, 3, dtype=torch.uint8, device=device)
         flags = torch.empty(B, dtype=torch.int32, device=device)
-        info = (ctypes.c_int * 3)()
+        info = torch.zeros(3, dtype=torch.int32, device=device)
         det_p = (ctypes.c_void_p * len(det))(*[_lib.ptr(t) for t in det])
         fine_p = (ctypes.c_void_p * len(fine))(*[_lib.ptr(t) for t in fine])
         with torch.cuda.device(device):
             _lib.check(lib.sis_contour_stage(det_p, fine_p, B, S, n_cls, len(det_keys), len(fine_keys),
                                              self.classes.index(self.fine_class), int(bool(cfg.only_keep_overlapping)),
                                              float(cfg.min_class_contour_area), self._colors, rank, _lib.ptr(self._workspace),
-                                             self._workspace.numel(), _lib.ptr(out), _lib.ptr(flags), info,
+                                             self._workspace.numel(), _lib.ptr(out), _lib.ptr(flags), _lib.ptr(info),
                                              _lib.current_stream_ptr(device)))
-        self.last_info = tuple(info)
+        self._info = info
         return out, flags
+
+    @property
+    def last_info(self):
+        """(shapes found, fixpoint rounds that did work, reason the batch went to the host path or 0) of the last `run`;
+        reading it waits for that call's kernels."""
+        return (0, 0, 0) if self._info is None else tuple(int(v) for v in self._info.cpu())
 
 
 def _stack(predicted_clusters) -> Dict[str, Tuple[List[str], torch.Tensor]]:

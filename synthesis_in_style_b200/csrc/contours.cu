@@ -32,7 +32,13 @@ namespace sis {
 constexpr int CT_MAX_PLANE_TYPES = 32;
 constexpr int CT_MAX_KEYS = 4;
 constexpr int CT_MAX_CLASSES = 7;
-enum { CTR_SHAPES = 0, CTR_OVERFLOW = 1, CTR_CHANGED = 2, CTR_GLIST = 3, CTR_FILL_NEW = 4, CTR_DEFERRED = 5, CTR_GLIST_BIG = 6, CTR_NUM = 8 };
+enum { CTR_SHAPES = 0, CTR_OVERFLOW = 1, CTR_NUM = 8 };
+// The merge fixpoint is controlled ON THE DEVICE: the host enqueues CT_ROUNDS rounds of {pairs, boxes, pairs again, boxes,
+// list, fill small, fill big} without ever reading a result back; every kernel of a round first looks at the control
+// words the earlier kernels left and returns at once when it has nothing to do.  A batch whose fixpoint is still moving
+// after the last round is handed to the host path (flag 2 on every image).
+constexpr int CT_ROUNDS = 6;
+enum { CTL_CHANGED1 = 0, CTL_DEFERRED1 = 1, CTL_CHANGED2 = 2, CTL_GLIST = 3, CTL_GLIST_BIG = 4, CTL_FILL_NEW = 5, CTL_STRIDE = 8 };
 
 struct CtGeom {
     int B, S, n_cls, n_det, n_fine, fine_cls, px;
@@ -54,8 +60,16 @@ struct CtWs {
     int cap;
     int32_t *sh_seg, *sh_cnt, *sh_L, *sh_x0, *sh_y0, *sh_x1, *sh_y1, *parent;
     int32_t *g_x0, *g_y0, *g_x1, *g_y1, *g_members, *g_filled, *g_cnt, *g_L, *g_kept, *g_cls, *score, *glist;
-    int32_t *ctr, *img_kept, *img_huge;
+    int32_t *ctr, *ctl, *img_kept, *img_huge;
 };
+
+// round o does something iff it is the first one or the round before it left new coverage / unfinished merging behind
+__device__ __forceinline__ bool ct_round_active(const CtWs& W, int o) {
+    if (o == 0) return true;
+    const volatile int32_t* c = W.ctl + (o - 1) * CTL_STRIDE;
+    return c[CTL_FILL_NEW] != 0 || c[CTL_CHANGED2] != 0;
+}
+
 
 // ------------------------------------------------------------------------------------------------ union-find
 __device__ __forceinline__ int uf_find(const int32_t* parent, int i) {
@@ -260,7 +274,11 @@ __device__ __forceinline__ int ct_cover(const CtGeom& G, const CtWs& W, int st, 
     }
     return n;
 }
-__global__ void __launch_bounds__(256) ct_pairs_kernel(CtGeom G, CtWs W) {
+__global__ void __launch_bounds__(256) ct_pairs_kernel(CtGeom G, CtWs W, int round, int pass) {
+    int32_t* ctl = W.ctl + round * CTL_STRIDE;
+    // pass 0: whenever the round is active; pass 1: only when pass 0 both joined groups (boxes grew) and held a pair back
+    if (!ct_round_active(W, round)) return;
+    if (pass == 1 && !(((volatile int32_t*)ctl)[CTL_CHANGED1] && ((volatile int32_t*)ctl)[CTL_DEFERRED1])) return;
     const int64_t total = (int64_t)G.n_seg_types() * G.B * G.px;
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
         const int seg = (int)(i / G.px), p = (int)(i - (int64_t)seg * G.px);
@@ -273,18 +291,27 @@ __global__ void __launch_bounds__(256) ct_pairs_kernel(CtGeom G, CtWs W) {
         const int n = ct_cover(G, W, st, b, p, g);
         for (int a = 0; a < n; ++a)
             for (int c = a + 1; c < n; ++c) {
-                if (!ct_strict(W, g[a], g[c])) W.ctr[CTR_DEFERRED] = 1;     // may pass once the boxes have grown
-                else if (uf_unite(W.parent, g[a], g[c])) W.ctr[CTR_CHANGED] = 1;
+                if (!ct_strict(W, g[a], g[c])) { if (pass == 0) ctl[CTL_DEFERRED1] = 1; }    // may pass once the boxes have grown
+                else if (uf_unite(W.parent, g[a], g[c])) ctl[pass == 0 ? CTL_CHANGED1 : CTL_CHANGED2] = 1;
             }
     }
 }
-__global__ void __launch_bounds__(256) ct_group_reset_kernel(CtWs W) {
+// does the box pass after pairs pass `pass` of `round` have anything to do?  (round < 0: unconditional)
+__device__ __forceinline__ bool ct_boxes_needed(const CtWs& W, int round, int pass) {
+    if (round < 0) return true;
+    if (!ct_round_active(W, round)) return false;
+    const volatile int32_t* ctl = W.ctl + round * CTL_STRIDE;
+    return pass == 0 ? ctl[CTL_CHANGED1] != 0 : (ctl[CTL_CHANGED1] != 0 && ctl[CTL_DEFERRED1] != 0);
+}
+__global__ void __launch_bounds__(256) ct_group_reset_kernel(CtWs W, int round, int pass) {
+    if (!ct_boxes_needed(W, round, pass)) return;
     const int n = min(W.ctr[CTR_SHAPES], W.cap);
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
         W.g_x0[i] = INT_MAX; W.g_y0[i] = INT_MAX; W.g_x1[i] = -1; W.g_y1[i] = -1; W.g_members[i] = 0;
     }
 }
-__global__ void __launch_bounds__(256) ct_group_accum_kernel(CtWs W) {
+__global__ void __launch_bounds__(256) ct_group_accum_kernel(CtWs W, int round, int pass) {
+    if (!ct_boxes_needed(W, round, pass)) return;
     const int n = min(W.ctr[CTR_SHAPES], W.cap);
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
         const int r = uf_find(W.parent, i);
@@ -297,13 +324,16 @@ __global__ void __launch_bounds__(256) ct_group_accum_kernel(CtWs W) {
 // merged groups whose hole fill is out of date: small windows from the front of the list, large ones from its end (they
 // get bigger blocks)
 constexpr int CT_BIG_WINDOW = 96 * 96;
-__global__ void __launch_bounds__(256) ct_list_groups_kernel(CtWs W) {
+__global__ void __launch_bounds__(256) ct_list_groups_kernel(CtWs W, int round) {
+    if (!ct_round_active(W, round)) return;
+    int32_t* ctl = W.ctl + round * CTL_STRIDE;
+    if (round > 0 && !((volatile int32_t*)ctl)[CTL_CHANGED1]) return;      // no group changed: every fill is up to date
     const int n = min(W.ctr[CTR_SHAPES], W.cap);
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256)
         if (W.parent[i] == i && W.g_members[i] > 1 && W.g_filled[i] != W.g_members[i]) {
             const bool big = (W.g_x1[i] - W.g_x0[i] + 3) * (W.g_y1[i] - W.g_y0[i] + 3) > CT_BIG_WINDOW;
-            if (big) W.glist[W.cap - 1 - atomicAdd(&W.ctr[CTR_GLIST_BIG], 1)] = i;
-            else W.glist[atomicAdd(&W.ctr[CTR_GLIST], 1)] = i;
+            if (big) W.glist[W.cap - 1 - atomicAdd(&ctl[CTL_GLIST_BIG], 1)] = i;
+            else W.glist[atomicAdd(&ctl[CTL_GLIST], 1)] = i;
         }
 }
 
@@ -328,11 +358,15 @@ __device__ __forceinline__ uint32_t ct_spread(uint32_t s, uint32_t f) {
 // memory; flood of the free pixels from the window's rim; what the flood does not reach and U does not cover is hole.
 // Writes the holes to the fill map and the filled group's pixel count and chain length.
 template <int NT, bool BIG>
-__global__ void __launch_bounds__(NT) ct_group_fill_kernel(CtGeom G, CtWs W) {
+__global__ void __launch_bounds__(NT) ct_group_fill_kernel(CtGeom G, CtWs W, int round) {
     extern __shared__ uint32_t ct_sm[];
     __shared__ int red[3];
     constexpr int NW = NT / 32;
-    const int g = W.glist[BIG ? W.cap - 1 - (int)blockIdx.x : (int)blockIdx.x], tid = threadIdx.x;
+    int32_t* ctl = W.ctl + round * CTL_STRIDE;
+    const int n_list = ((volatile int32_t*)ctl)[BIG ? CTL_GLIST_BIG : CTL_GLIST], tid = threadIdx.x;
+    for (int gi = blockIdx.x; gi < n_list; gi += gridDim.x) {
+    __syncthreads();                                     // the previous group's bitmasks and sums are no longer read
+    const int g = W.glist[BIG ? W.cap - 1 - gi : gi];
     const int seg = W.sh_seg[g], st = seg / G.B, b = seg - st * G.B, nk = G.keys_of(st);
     const int x0 = W.g_x0[g] - 1, y0 = W.g_y0[g] - 1;
     const int ww = W.g_x1[g] - W.g_x0[g] + 3, hh = W.g_y1[g] - W.g_y0[g] + 3, wpr = (ww + 31) >> 5, words = hh * wpr;
@@ -451,7 +485,8 @@ __global__ void __launch_bounds__(NT) ct_group_fill_kernel(CtGeom G, CtWs W) {
     __syncthreads();
     if (tid == 0) {
         W.g_cnt[g] = red[0]; W.g_L[g] = red[1]; W.g_filled[g] = W.g_members[g];
-        if (red[2]) W.ctr[CTR_FILL_NEW] = 1;
+        if (red[2]) ctl[CTL_FILL_NEW] = 1;
+    }
     }
 }
 
@@ -539,9 +574,18 @@ __global__ void __launch_bounds__(256) ct_render_kernel(CtGeom G, CtWs W, uint8_
                 certain |= huge > 0 && huge == kept;
                 undecided |= huge > 0 && huge != kept;
             }
-            flags[b] = certain ? 1 : undecided ? 2 : 0;       // a certain drop in one class decides the image
+            const bool settled = !ct_round_active(W, CT_ROUNDS) && !W.ctr[CTR_OVERFLOW];
+            flags[b] = !settled ? 2 : certain ? 1 : undecided ? 2 : 0;       // a certain drop in one class decides the image
         }
     }
+}
+// [shapes, rounds that did something, why the batch was handed to the host (0: it was not, 1: capacity, 3: fixpoint still moving)]
+__global__ void ct_info_kernel(CtWs W, int32_t* info) {
+    int rounds = 0;
+    for (int o = 0; o < CT_ROUNDS; ++o) rounds += ct_round_active(W, o) && (o == 0 || W.ctl[o * CTL_STRIDE + CTL_CHANGED1] || W.ctl[(o - 1) * CTL_STRIDE + CTL_FILL_NEW]);
+    info[0] = W.ctr[CTR_SHAPES];
+    info[1] = rounds;
+    info[2] = W.ctr[CTR_OVERFLOW] ? 1 : ct_round_active(W, CT_ROUNDS) ? 3 : 0;
 }
 __global__ void ct_fill_flags_kernel(int32_t* flags, int n, int v) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -568,7 +612,7 @@ static CtLayout ct_layout(int B, int S, int n_cls, int n_det, int n_fine) {
     const int64_t per_plane = px / 4 < 16384 ? px / 4 : 16384;
     L.cap = (int)(np * per_plane);
     L.shapes = off; off += up((int64_t)L.cap * 4) * (20 + n_cls);
-    L.ctr = off; off += up(CTR_NUM * 4);
+    L.ctr = off; off += up((CTR_NUM + (CT_ROUNDS + 1) * CTL_STRIDE) * 4);
     L.img = off; off += up((int64_t)B * n_cls * 4) * 2;
     L.total = off;
     return L;
@@ -589,7 +633,7 @@ extern "C" int sis_contour_stage(const uint8_t* const* d_det_masks, const uint8_
                                  int n_classes, int n_det_keys, int n_fine_keys, int fine_class, int only_keep_overlapping,
                                  double min_class_contour_area, const uint8_t* colors_rgb, const int* render_rank,
                                  void* d_workspace, int64_t workspace_bytes, uint8_t* d_label_rgb, int32_t* d_flags,
-                                 int32_t* info, void* stream_) {
+                                 int32_t* d_info, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     SIS_REQUIRE(batch > 0 && size > 0, "contour stage: batch and image size must be positive");
     SIS_REQUIRE(n_classes >= 1 && n_classes <= CT_MAX_CLASSES, "contour stage: 1..%d classes besides the background (got %d)", CT_MAX_CLASSES, n_classes);
@@ -626,20 +670,18 @@ extern "C" int sis_contour_stage(const uint8_t* const* d_det_masks, const uint8_
                           &W.g_x1, &W.g_y1, &W.g_members, &W.g_filled, &W.g_cnt, &W.g_L, &W.g_kept, &W.g_cls, &W.glist, &W.score};
     for (int i = 0; i < 20; ++i) *fields[i] = (int32_t*)(base + L.shapes + stride * i);      // score takes slots 19 .. 19+n_cls
     W.ctr = (int32_t*)(base + L.ctr);
+    W.ctl = W.ctr + CTR_NUM;
     W.img_kept = (int32_t*)(base + L.img);
     W.img_huge = W.img_kept + ((int64_t)batch * n_classes * 4 + 255) / 256 * 64;
 
     const int64_t np = (int64_t)G.n_plane_types() * batch, ns = (int64_t)G.n_seg_types() * batch;
     const int wmax = size + 2, fill_smem = 2 * wmax * ((wmax + 31) / 32) * 4;
     const int fill_smem_small = min(fill_smem, 2 * 4 * (CT_BIG_WINDOW / 32 + wmax + 8));    // words <= area/32 + rows
-    int host_ctr[CTR_NUM] = {0};
-    auto give_up = [&](int why) -> int {      // the whole batch goes to the host path
-        ct_fill_flags_kernel<<<ceil_div(batch, 128), 128, 0, stream>>>(d_flags, batch, 2);
-        SIS_CHECK_LAUNCH();
-        if (info) { info[0] = host_ctr[CTR_SHAPES]; info[1] = 0; info[2] = why; }
+    if (fill_smem > 200 * 1024) {                          // window bitmasks do not fit in shared memory (S > ~880)
+        ct_fill_flags_kernel<<<ceil_div(batch, 128), 128, 0, stream>>>(d_flags, batch, 2); SIS_CHECK_LAUNCH();
+        if (d_info) { const int32_t why[3] = {0, 0, 2}; SIS_CHECK_CUDA(cudaMemcpyAsync(d_info, why, sizeof(why), cudaMemcpyHostToDevice, stream)); }
         return SIS_OK;
-    };
-    if (fill_smem > 200 * 1024) return give_up(2);        // window bitmasks do not fit in shared memory (S > ~880)
+    }
     static int fill_smem_set = 0;
     if (fill_smem > fill_smem_set) {
         SIS_CHECK_CUDA(cudaFuncSetAttribute(ct_group_fill_kernel<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fill_smem));
@@ -647,11 +689,11 @@ extern "C" int sis_contour_stage(const uint8_t* const* d_det_masks, const uint8_
     }
     SIS_CHECK_CUDA(cudaMemsetAsync(W.fillmap, 0xff, ns * G.px * 4, stream));
     SIS_CHECK_CUDA(cudaMemsetAsync(W.key_count, 0, np * 4, stream));
-    SIS_CHECK_CUDA(cudaMemsetAsync(W.ctr, 0, CTR_NUM * 4, stream));
-    SIS_CHECK_CUDA(cudaMemsetAsync(W.img_kept, 0, (char*)(base + L.total) - (char*)W.img_kept, stream));
+    SIS_CHECK_CUDA(cudaMemsetAsync(W.ctr, 0, (char*)(base + L.total) - (char*)W.ctr, stream));      // counters, control words, per-image sums
     const int grid_px = (int)min((int64_t)kNumSMs * 16, ceil_div64(np * G.px, 256));
     const int grid_seg = (int)min((int64_t)kNumSMs * 16, ceil_div64(ns * G.px, 256));
     const int grid_img = (int)min((int64_t)kNumSMs * 16, ceil_div64((int64_t)batch * G.px, 256));
+    const int grid_sh = kNumSMs * 4;       // the shape-table kernels size their loops from the device counter
     ct_bg_init_kernel<<<grid_px, 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
     ct_bg_merge_kernel<<<grid_px, 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
     ct_bg_touch_kernel<<<(int)min((int64_t)kNumSMs * 8, ceil_div64(np * 4 * size, 256)), 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
@@ -659,50 +701,26 @@ extern "C" int sis_contour_stage(const uint8_t* const* d_det_masks, const uint8_
     ct_fg_merge_kernel<<<grid_px, 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
     ct_fg_ids_kernel<<<grid_px, 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
     ct_shape_stats_kernel<<<grid_px, 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
-    auto read_ctr = [&]() -> cudaError_t {
-        cudaError_t e = cudaMemcpyAsync(host_ctr, W.ctr, sizeof(host_ctr), cudaMemcpyDeviceToHost, stream);
-        return e != cudaSuccess ? e : cudaStreamSynchronize(stream);
-    };
-    // the shape-table kernels size their loops from the device counter: a fixed grid, no host round trip for the count
-    const int grid_sh = kNumSMs * 4;
-    int rounds = 0;
-    const bool merging = n_det_keys > 1 || n_fine_keys > 1;
-    ct_group_reset_kernel<<<grid_sh, 256, 0, stream>>>(W); SIS_CHECK_LAUNCH();
-    ct_group_accum_kernel<<<grid_sh, 256, 0, stream>>>(W); SIS_CHECK_LAUNCH();
-    while (merging) {
-        // one pairs pass joins every chain of overlapping shapes; it is repeated only when a pair was held back by the
-        // bounding-box test AND boxes grew in the same pass.  The list of groups to fill rides in the same round trip.
-        while (true) {
-            ++rounds;
-            SIS_CHECK_CUDA(cudaMemsetAsync(W.ctr + CTR_CHANGED, 0, 4 * (CTR_NUM - CTR_CHANGED), stream));
-            ct_pairs_kernel<<<grid_seg, 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
-            ct_group_reset_kernel<<<grid_sh, 256, 0, stream>>>(W); SIS_CHECK_LAUNCH();
-            ct_group_accum_kernel<<<grid_sh, 256, 0, stream>>>(W); SIS_CHECK_LAUNCH();
-            ct_list_groups_kernel<<<grid_sh, 256, 0, stream>>>(W); SIS_CHECK_LAUNCH();
-            SIS_CHECK_CUDA(read_ctr());
-            if (host_ctr[CTR_OVERFLOW]) return give_up(1);
-            if (!(host_ctr[CTR_CHANGED] && host_ctr[CTR_DEFERRED])) break;
-            SIS_REQUIRE(rounds < 10000, "contour stage: merge fixpoint did not converge");
+    ct_group_reset_kernel<<<grid_sh, 256, 0, stream>>>(W, -1, 0); SIS_CHECK_LAUNCH();
+    ct_group_accum_kernel<<<grid_sh, 256, 0, stream>>>(W, -1, 0); SIS_CHECK_LAUNCH();
+    if (n_det_keys > 1 || n_fine_keys > 1) {
+        // No host round trip: CT_ROUNDS rounds are enqueued, each kernel decides on the device whether it still has work
+        // (a round whose predecessor changed nothing returns in a few microseconds).
+        for (int o = 0; o < CT_ROUNDS; ++o) {
+            for (int pass = 0; pass < 2; ++pass) {
+                ct_pairs_kernel<<<grid_seg, 256, 0, stream>>>(G, W, o, pass); SIS_CHECK_LAUNCH();
+                ct_group_reset_kernel<<<grid_sh, 256, 0, stream>>>(W, o, pass); SIS_CHECK_LAUNCH();
+                ct_group_accum_kernel<<<grid_sh, 256, 0, stream>>>(W, o, pass); SIS_CHECK_LAUNCH();
+            }
+            ct_list_groups_kernel<<<grid_sh, 256, 0, stream>>>(W, o); SIS_CHECK_LAUNCH();
+            ct_group_fill_kernel<128, false><<<kNumSMs * 8, 128, fill_smem_small, stream>>>(G, W, o); SIS_CHECK_LAUNCH();
+            ct_group_fill_kernel<1024, true><<<kNumSMs, 1024, fill_smem, stream>>>(G, W, o); SIS_CHECK_LAUNCH();
         }
-        if (host_ctr[CTR_GLIST] == 0 && host_ctr[CTR_GLIST_BIG] == 0) break;
-        if (host_ctr[CTR_GLIST]) {
-            ct_group_fill_kernel<128, false><<<host_ctr[CTR_GLIST], 128, fill_smem_small, stream>>>(G, W); SIS_CHECK_LAUNCH();
-        }
-        if (host_ctr[CTR_GLIST_BIG]) {       // the few windows that span much of the image: 32 warps each
-            ct_group_fill_kernel<1024, true><<<host_ctr[CTR_GLIST_BIG], 1024, fill_smem, stream>>>(G, W); SIS_CHECK_LAUNCH();
-        }
-        SIS_CHECK_CUDA(read_ctr());
-        if (!host_ctr[CTR_FILL_NEW]) break;              // no pixel became covered: no new pair can appear
     }
-    if (!merging) {
-        SIS_CHECK_CUDA(read_ctr());
-        if (host_ctr[CTR_OVERFLOW]) return give_up(1);
-    }
-    const int n_shapes = host_ctr[CTR_SHAPES];
     ct_finalize_kernel<<<grid_sh, 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
     ct_classify_kernel<<<grid_img, 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
     ct_assign_kernel<<<grid_sh, 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();
     ct_render_kernel<<<grid_img, 256, 0, stream>>>(G, W, d_label_rgb, d_flags); SIS_CHECK_LAUNCH();
-    if (info) { info[0] = n_shapes; info[1] = rounds; info[2] = 0; }
+    if (d_info) { ct_info_kernel<<<1, 1, 0, stream>>>(W, d_info); SIS_CHECK_LAUNCH(); }
     return SIS_OK;
 }

@@ -411,14 +411,18 @@ class LabelledPairGenerator:
             self.contour_stats['wait_fallback_s'] += time.perf_counter() - t0
             return SegmentedBatch(index, images, labels, sorted(drop))
 
-        launched = collections.deque()      # generator + labelling enqueued, contour stage not yet
+        # The stage never synchronises (its fixpoint is controlled on the device), so it is enqueued right behind the
+        # batch's generator pass, on a HIGH-priority stream of its own: its ~70 short kernels slot in at the next kernel
+        # boundary of the other lane's generator instead of queueing behind it, and the finished batch leaves early.
+        contour_streams = [torch.cuda.Stream(device=device, priority=-1) for _ in lanes]
 
         def contour_and_copy(slot):
-            st = lanes[slot['lane']][1]
-            with (torch.cuda.stream(st) if st is not None else contextlib.nullcontext()):
+            cs = contour_streams[slot['lane']]
+            with torch.cuda.stream(cs):
+                cs.wait_event(slot['generated'])
                 label_rgb, flags = stages[slot['lane']].run(slot['stacked'])
                 ready = torch.cuda.Event()
-                ready.record(torch.cuda.current_stream(device))
+                ready.record(cs)
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(ready)
                 slot['image'].copy_(slot['keep'][0], non_blocking=True)
@@ -426,7 +430,7 @@ class LabelledPairGenerator:
                 slot['flags'].copy_(flags, non_blocking=True)
                 slot['done'] = torch.cuda.Event()
                 slot['done'].record(copy_stream)
-            slot['keep'] = slot['keep'] + (label_rgb, flags)
+            slot['keep'] = slot['keep'] + (label_rgb, flags)      # device tensors outlive the asynchronous work on them
             pending.append(slot)
 
         n = 0
@@ -450,16 +454,14 @@ class LabelledPairGenerator:
                 if seg.keys_to_merge:
                     stacked = seg.merge_stacked(stacked)
                 image_u8 = make_image(image)
+                slot['generated'] = torch.cuda.Event()
+                slot['generated'].record(torch.cuda.current_stream(device))
             slot['keep'], slot['stacked'], slot['index'], slot['lane'] = (image_u8, lat, acts), stacked, idx, n % len(lanes)
-            launched.append(slot)
+            contour_and_copy(slot)
             self.stats['pairs'] += B
             self.stats['batches'] += 1
             n += 1
-            # The contour stage of the batch BEFORE the one just enqueued: its host round trips (fixpoint control) now
-            # fall into the time the GPU spends on the newer batch's generator kernels, on the other lane's stream.
-            if len(launched) > (1 if len(lanes) > 1 else 0):
-                contour_and_copy(launched.popleft())
-            if len(pending) > max(lag, len(lanes) - 1):
+            if len(pending) > max(lag, len(lanes)):
                 resolve(pending.popleft())
                 if len(resolved) > 1:           # a batch's fall-backs get one batch of time before they are waited for
                     yield collect()

@@ -30,18 +30,22 @@ def to_stacked(pred, device):
             for key, per_class in pred.items()}
 
 
-def check_against(pred, batch, cfg, device, want_images, want_drop, max_undecided=None):
+def check_against(pred, batch, cfg, device, want_images, want_drop, max_undecided=None, allow_unsettled=False):
     stage = pd.DeviceContourStage(cfg)
     images_d, flags_d = stage.run(to_stacked(pred, device))
     torch.cuda.synchronize()
     images, flags = images_d.cpu().numpy(), flags_d.cpu().numpy()
-    assert stage.last_info[2] == 0, f'device stage gave the batch up (reason {stage.last_info[2]})'
+    reason = stage.last_info[2]
+    assert reason in ((0, 3) if allow_unsettled else (0,)), f'device stage gave the batch up (reason {reason})'
     assert images.shape == want_images.shape and images.dtype == numpy.uint8
-    bad = [b for b in range(batch) if not numpy.array_equal(images[b], want_images[b])]
-    assert not bad, f'label images differ for images {bad}'
-    for b in range(batch):
-        if flags[b] != pd.FLAG_HOST:
-            assert (flags[b] == pd.FLAG_DROP) == (b in want_drop), f'image {b}: flag {flags[b]}, reference drop {b in want_drop}'
+    if reason == 3:        # the merge fixpoint was still moving after the enqueued rounds: every image goes to the host path
+        assert (flags == pd.FLAG_HOST).all()
+    else:
+        bad = [b for b in range(batch) if not numpy.array_equal(images[b], want_images[b])]
+        assert not bad, f'label images differ for images {bad}'
+        for b in range(batch):
+            if flags[b] != pd.FLAG_HOST:
+                assert (flags[b] == pd.FLAG_DROP) == (b in want_drop), f'image {b}: flag {flags[b]}, reference drop {b in want_drop}'
     undecided = int((flags == pd.FLAG_HOST).sum())
     if max_undecided is not None:
         assert undecided <= max_undecided, f'{undecided} of {batch} images undecided'
@@ -94,7 +98,7 @@ def test_device_equals_polygon_path_noise(cuda_device, case):
     pred = noise_masks(seed, batch, size, smooth)
     cfg = pc.ContourConfig(size, COLORS, ['8', '9'], ['12', '13'], keep, min_area)
     want_images, want_drop = pc.segment_masks(pred, batch, cfg)
-    check_against(pred, batch, cfg, cuda_device, want_images, want_drop)
+    check_against(pred, batch, cfg, cuda_device, want_images, want_drop, allow_unsettled=True)
 
 
 def test_device_edge_cases(cuda_device):
