@@ -170,13 +170,17 @@ def build_dataset(args: argparse.Namespace, creation_config: Dict, original_conf
             creation_config = get_dataset_gan_params(generator, mean_latent, creation_config, config['image_size'], config['latent_size'])
         segmenter = get_dataset_segmenter(args, creation_config, config['image_size'], semantic_segmentation_base_dir)
         cores = max(2, (os.cpu_count() or 2) // world)
-        with ThreadPoolExecutor(max(1, cores // 4)) as png_pool:
+        with ThreadPoolExecutor(max(1, cores * 3 // 4)) as png_pool:       # its size = the native writer's encoder threads
             if isinstance(segmenter, ClusterSegmenter) and not debug:
                 spawn = multiprocessing.get_context('spawn')      # the workers only run OpenCV / numpy: never fork a CUDA process
                 pipe = dc.LabelledPairGenerator(generator, segmenter, config, seed=creation_config['seed'], mean_latent=mean_latent,
                                                 rank=rank, world_size=world, capture_only_labelled=True, in_flight=2)
+                if pipe.device_contours_supported():
+                    # contour stage on the device: the pool only serves the few images that fall back to the host path
+                    with ThreadPoolExecutor(max(1, cores // 4)) as contour_pool:
+                        return dw.build_dataset(pipe, image_save_base_dir, args.num_images, contour_pool, png_pool, device_contours=True)
                 with ProcessPoolExecutor(max(1, cores * 3 // 4), mp_context=spawn) as contour_pool:
-                    return dw.build_dataset(pipe, image_save_base_dir, args.num_images, contour_pool, png_pool)
+                    return dw.build_dataset(pipe, image_save_base_dir, args.num_images, contour_pool, png_pool, device_contours=False)
             # generic loop (:127-148): any segmenter with create_segmentation_image; `debug` keeps dropped images
             writer = dw.DatasetWriter(image_save_base_dir, args.num_images, rank, world, png_pool, device=device if world > 1 else None)
             batches = 0

@@ -341,17 +341,26 @@ class LabelledPairGenerator:
         False: the masks are copied out and the per-image host tasks (`contours.segment_masks`) run on `pool` (a
         concurrent.futures executor; None = inline) while the GPU produces the next `lag` batches.
         None (default): the device when the configuration is one it handles."""
-        from . import contours_device
         cfg = self.segmenter.contour_config()
         if device_contours is None:
-            names = {layer: list(self.segmenter.class_label_map[layer].keys()) for layer in self.segmenter.catalog}
-            for dst in self.segmenter.keys_to_merge:
-                names[dst] = list(self.segmenter.class_to_color_map)
-            device_contours = contours_device.DeviceContourStage(cfg).supports(names) and self.generator.size <= 832
+            device_contours = self.device_contours_supported()
         if device_contours:
             yield from self._iter_segmented_device(depth, pool, lag, cfg)
         else:
             yield from self._iter_segmented_host(depth, pool, lag, cfg)
+
+    def device_contours_supported(self) -> bool:
+        """Whether `iter_segmented` takes the device contour stage by default: every class is present under every key the
+        stage reads, and the image size is one whose window bitmasks fit in shared memory (<= 832)."""
+        from . import contours_device
+        names = {layer: list(self.segmenter.class_label_map[layer].keys()) for layer in self.segmenter.catalog}
+        for dst in self.segmenter.keys_to_merge:
+            names[dst] = list(self.segmenter.class_to_color_map)
+        try:
+            stage = contours_device.DeviceContourStage(self.segmenter.contour_config())
+        except KeyError:
+            return False
+        return stage.supports(names) and self.generator.size <= 832
 
     def _iter_segmented_device(self, depth, pool, lag, cfg) -> Iterator[SegmentedBatch]:
         import collections
