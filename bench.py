@@ -502,9 +502,8 @@ def run_leg_dataset(args, dev, rank, world, out):
 
     try:
         spawn = multiprocessing.get_context('spawn')
-        # host contours: one process per worker (Python-heavy tasks); device contours: the rare fall-backs run on threads
-        with (ProcessPoolExecutor(n_contour, mp_context=spawn) if args.contours == 'host' else ThreadPoolExecutor(n_contour)) as cpool, \
-                ThreadPoolExecutor(n_png) as wpool:
+        # one process per contour worker (Python-heavy tasks); with device contours they only serve the rare fall-backs
+        with ProcessPoolExecutor(n_contour, mp_context=spawn) as cpool, ThreadPoolExecutor(n_png) as wpool:
             # GPU-only rate of the same pipeline (host buffers out, nothing downstream)
             pipe = dc.LabelledPairGenerator(g, seg, cfg, seed=1, rank=rank, world_size=world, in_flight=args.in_flight)
             it = pipe.iter_host(depth=2, image_u8=True)

@@ -107,6 +107,16 @@ def _stack(predicted_clusters) -> Dict[str, Tuple[List[str], torch.Tensor]]:
     return out
 
 
+def warm_worker() -> int:
+    """Nothing but the imports a fall-back task needs (run once per pool worker before the pipeline starts)."""
+    import os
+    import time
+
+    from . import contours  # noqa: F401
+    time.sleep(0.05)          # keep this worker busy so the next warm-up task lands on another one
+    return os.getpid()
+
+
 def host_fallback(stacked_host: Dict[str, Tuple[Sequence[str], numpy.ndarray]], image_ids: Sequence[int], cfg: ContourConfig):
     """`contours.segment_masks` for single images; stacked_host holds uint8 [n_class, B, S, S] numpy arrays.
     Returns {image id: (uint8 [S,S,3], dropped)}."""

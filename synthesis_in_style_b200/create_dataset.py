@@ -177,7 +177,7 @@ def build_dataset(args: argparse.Namespace, creation_config: Dict, original_conf
                                                 rank=rank, world_size=world, capture_only_labelled=True, in_flight=2)
                 if pipe.device_contours_supported():
                     # contour stage on the device: the pool only serves the few images that fall back to the host path
-                    with ThreadPoolExecutor(max(1, cores // 4)) as contour_pool:
+                    with ProcessPoolExecutor(max(1, cores // 4), mp_context=spawn) as contour_pool:
                         return dw.build_dataset(pipe, image_save_base_dir, args.num_images, contour_pool, png_pool, device_contours=True)
                 with ProcessPoolExecutor(max(1, cores * 3 // 4), mp_context=spawn) as contour_pool:
                     return dw.build_dataset(pipe, image_save_base_dir, args.num_images, contour_pool, png_pool, device_contours=False)

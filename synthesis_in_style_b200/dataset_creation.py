@@ -383,6 +383,13 @@ class LabelledPairGenerator:
         keys = set(cfg.keys_for_class_determination) | set(cfg.keys_for_finegrained_segmentation)
         pending = collections.deque()
         self.contour_stats = {'images': 0, 'host_fallback': 0, 'wait_copy_s': 0.0, 'wait_fallback_s': 0.0}
+        fallback_lag = 8                    # batches a fall-back task may take before the loop waits for it (host copies of 8 batches)
+        if pool is not None and hasattr(pool, '_max_workers'):
+            # start the workers now (a spawned process imports numpy / OpenCV / this package: seconds, once), not at the
+            # first fall-back in the middle of the run
+            warm = [pool.submit(contours_device.warm_worker) for _ in range(pool._max_workers)]
+            for w in warm:
+                w.result()
 
         import time
         resolved = collections.deque()      # batches whose flags are known; their host fall-backs (if any) are running
@@ -472,7 +479,7 @@ class LabelledPairGenerator:
             n += 1
             if len(pending) > max(lag, len(lanes)):
                 resolve(pending.popleft())
-                if len(resolved) > 1:           # a batch's fall-backs get one batch of time before they are waited for
+                if len(resolved) > fallback_lag:    # a batch's fall-backs get a few batches of time before they are waited for
                     yield collect()
 
     def _iter_segmented_host(self, depth, pool, lag, cfg) -> Iterator[SegmentedBatch]:

@@ -199,7 +199,9 @@ class DatasetWriter:
                 return 0
             if self._native_queue is None:
                 from concurrent.futures import ThreadPoolExecutor
-                self._native_queue = ThreadPoolExecutor(1)      # one batch at a time; the parallelism is inside the call
+                # two batches in flight: a batch's files rarely divide evenly over the encoder threads, the second call
+                # fills the idle tail of the first (the parallelism proper is inside the call)
+                self._native_queue = ThreadPoolExecutor(2)
             self._futures.append(self._native_queue.submit(save_generated_images_native, generated_images, label_images, rows, start,
                                                            self.base_dir, self.num_images, self._level, self.native_threads))
             self.files_written += len(rows)
