@@ -706,6 +706,9 @@ def measure(wl, args, dev, rank, world, steps, warmup, profile_steps, with_e2e=T
     sampler = ClockSampler(dev)
     if rank == 0:
         sampler.start()
+    import gc
+    gc.collect()
+    gc.disable()                              # no collector pause on the thread that enqueues the timed steps
     barrier()
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -716,6 +719,7 @@ def measure(wl, args, dev, rank, world, steps, warmup, profile_steps, with_e2e=T
     e1.record()
     barrier()
     t_end = time.perf_counter()
+    gc.enable()
     launches = _lib.launch_count() - launches0
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop(t_begin, t_end) if rank == 0 else None

@@ -232,11 +232,12 @@ SIS_API int sis_make_image_u8(const float* d_image, int batch, int size, uint8_t
  * colors_rgb   : HOST, (1 + n_classes) * 3 bytes: background colour, then the classes
  * render_rank  : HOST, n_classes ints: position of each class in the mask dict the reference's renderer iterates
  *                (a later class overwrites an earlier one)
+ * S <= 1024.
  * d_label_rgb  : uint8 [batch,S,S,3];  d_flags: int32 [batch]: 0 keep, 1 drop, 2 = take this image through the host path
  *                (the reference's drop rule reads the FIRST contour of a class; the device does not order contours and
  *                only decides when the order cannot matter; also set for the whole batch when a capacity is exceeded)
  * d_info       : DEVICE, 3 ints or NULL: shapes found, fixpoint rounds that did work, reason the batch was handed to the
- *                host (0 none, 1 capacity, 2 image size, 3 fixpoint still moving after the enqueued rounds)
+ *                host (0 none, 1 capacity, 3 fixpoint still moving after the enqueued rounds)
  * Fully asynchronous: the merge fixpoint is controlled on the device (a fixed number of rounds is enqueued, kernels with
  * nothing left to do return at once); the call never synchronises the stream. */
 SIS_API int sis_contour_stage_workspace_bytes(int batch, int size, int n_classes, int n_det_keys, int n_fine_keys, int64_t* bytes);

@@ -62,6 +62,8 @@ struct CtWs {
     int32_t *sh_seg, *sh_cnt, *sh_L, *sh_x0, *sh_y0, *sh_x1, *sh_y1, *parent;
     int32_t *g_x0, *g_y0, *g_x1, *g_y1, *g_members, *g_filled, *g_cnt, *g_L, *g_kept, *g_cls, *score, *glist;
     int32_t *ctr, *ctl, *img_kept, *img_huge;
+    uint32_t* scratch;          // per-block bitmask slices of the big-window fill kernel (image sizes above ~830), or null
+    int scratch_words;
 };
 
 // round o does something iff it is the first one or the round before it left new coverage / unfinished merging behind
@@ -374,8 +376,12 @@ __device__ __forceinline__ uint32_t ct_spread(uint32_t s, uint32_t f) {
 // One block per merged group: the union U of its members over the bounding box grown by one pixel, as a bitmask in shared
 // memory; flood of the free pixels from the window's rim; what the flood does not reach and U does not cover is hole.
 // Writes the holes to the fill map and the filled group's pixel count and chain length.
+// Windows whose two bitmasks exceed the shared memory of the launch (image sizes above ~830: only the few groups that span
+// most of such an image) keep them in a per-block slice of the workspace instead (W.scratch; the sweeps then run out of
+// L2).  A window wider than 1024 pixels (32 word columns, one per lane) drops its left / right rim columns and seeds the
+// free pixels of its first / last column instead: a reached rim column next to them is all the rim ever contributes.
 template <int NT, bool BIG>
-__global__ void __launch_bounds__(NT) ct_group_fill_kernel(CtGeom G, CtWs W, int round) {
+__global__ void __launch_bounds__(NT) ct_group_fill_kernel(CtGeom G, CtWs W, int round, int smem_words) {
     extern __shared__ uint32_t ct_sm[];
     __shared__ int red[3];
     constexpr int NW = NT / 32;
@@ -385,10 +391,11 @@ __global__ void __launch_bounds__(NT) ct_group_fill_kernel(CtGeom G, CtWs W, int
     __syncthreads();                                     // the previous group's bitmasks and sums are no longer read
     const int g = W.glist[BIG ? W.cap - 1 - gi : gi];
     const int seg = W.sh_seg[g], st = seg / G.B, b = seg - st * G.B, nk = G.keys_of(st);
-    const int x0 = W.g_x0[g] - 1, y0 = W.g_y0[g] - 1;
-    const int ww = W.g_x1[g] - W.g_x0[g] + 3, hh = W.g_y1[g] - W.g_y0[g] + 3, wpr = (ww + 31) >> 5, words = hh * wpr;
-    uint32_t* U = ct_sm;
-    uint32_t* R = ct_sm + words;
+    const int rimx = (W.g_x1[g] - W.g_x0[g] + 3 > 1024) ? 0 : 1;
+    const int x0 = W.g_x0[g] - rimx, y0 = W.g_y0[g] - 1;
+    const int ww = W.g_x1[g] - W.g_x0[g] + 1 + 2 * rimx, hh = W.g_y1[g] - W.g_y0[g] + 3, wpr = (ww + 31) >> 5, words = hh * wpr;
+    uint32_t* U = (BIG && 2 * words > smem_words) ? W.scratch + (size_t)blockIdx.x * W.scratch_words : ct_sm;
+    uint32_t* R = U + words;
     if (tid < 3) red[tid] = 0;
     // U: one word per warp step, lane = pixel (coalesced label reads of every key, one ballot per word)
     for (int w0 = tid >> 5; w0 < words; w0 += 2 * NW) {
@@ -399,7 +406,7 @@ __global__ void __launch_bounds__(NT) ct_group_fill_kernel(CtGeom G, CtWs W, int
             bool in = false;
             if (w < words) {
                 const int row = w / wpr, wc = w - row * wpr, xw = wc * 32 + (tid & 31);
-                if (row > 0 && row < hh - 1 && xw > 0 && xw < ww - 1) {
+                if (row > 0 && row < hh - 1 && xw >= rimx && xw < ww - rimx) {
                     const int p = (y0 + row) * G.S + x0 + xw;
                     int ids[CT_MAX_KEYS];
 #pragma unroll
@@ -424,6 +431,7 @@ __global__ void __launch_bounds__(NT) ct_group_fill_kernel(CtGeom G, CtWs W, int
                 else {
                     if (wc == 0) r |= 1u;
                     if (wc == wpr - 1) r |= 1u << ((ww - 1) & 31);
+                    if (!rimx) r &= ~ub[j];                    // no rim columns: the free pixels of the edge columns are the seeds
                 }
                 U[w] = ub[j];
                 R[w] = r;
@@ -609,8 +617,10 @@ __global__ void ct_fill_flags_kernel(int32_t* flags, int n, int v) {
     if (i < n) flags[i] = v;
 }
 
+constexpr int CT_FILL_SMEM_MAX = 200 * 1024;
 struct CtLayout {
-    int64_t lab, aux, fillmap, key_count, fmask, touch, shapes, ctr, img, total;
+    int64_t lab, aux, fillmap, key_count, fmask, touch, shapes, ctr, img, scratch, total;
+    int scratch_words;
     int cap;
 };
 static CtLayout ct_layout(int B, int S, int n_cls, int n_det, int n_fine) {
@@ -631,6 +641,10 @@ static CtLayout ct_layout(int B, int S, int n_cls, int n_det, int n_fine) {
     L.shapes = off; off += up((int64_t)L.cap * 4) * (20 + n_cls);
     L.ctr = off; off += up((CTR_NUM + (CT_ROUNDS + 1) * CTL_STRIDE) * 4);
     L.img = off; off += up((int64_t)B * n_cls * 4) * 2;
+    // big-window bitmasks that do not fit in shared memory: one slice per block of the (one block per SM) big-window launch
+    const int64_t wmax = S + 2, mask_words = 2 * wmax * ((wmax + 31) / 32);
+    L.scratch_words = mask_words * 4 > CT_FILL_SMEM_MAX ? (int)mask_words : 0;
+    L.scratch = off; off += up((int64_t)L.scratch_words * 4) * kNumSMs;
     L.total = off;
     return L;
 }
@@ -688,17 +702,16 @@ extern "C" int sis_contour_stage(const uint8_t* const* d_det_masks, const uint8_
     for (int i = 0; i < 20; ++i) *fields[i] = (int32_t*)(base + L.shapes + stride * i);      // score takes slots 19 .. 19+n_cls
     W.ctr = (int32_t*)(base + L.ctr);
     W.ctl = W.ctr + CTR_NUM;
+    W.scratch = L.scratch_words ? (uint32_t*)(base + L.scratch) : nullptr;
+    W.scratch_words = (int)(((int64_t)L.scratch_words * 4 + 255) / 256 * 64);
     W.img_kept = (int32_t*)(base + L.img);
     W.img_huge = W.img_kept + ((int64_t)batch * n_classes * 4 + 255) / 256 * 64;
 
     const int64_t np = (int64_t)G.n_plane_types() * batch, ns = (int64_t)G.n_seg_types() * batch;
-    const int wmax = size + 2, fill_smem = 2 * wmax * ((wmax + 31) / 32) * 4;
+    const int wmax = size + 2, fill_full = 2 * wmax * ((wmax + 31) / 32) * 4;
+    const int fill_smem = fill_full <= CT_FILL_SMEM_MAX ? fill_full : 96 * 1024;          // larger windows go to W.scratch
     const int fill_smem_small = min(fill_smem, 2 * 4 * (CT_BIG_WINDOW / 32 + wmax + 8));    // words <= area/32 + rows
-    if (fill_smem > 200 * 1024) {                          // window bitmasks do not fit in shared memory (S > ~880)
-        ct_fill_flags_kernel<<<ceil_div(batch, 128), 128, 0, stream>>>(d_flags, batch, 2); SIS_CHECK_LAUNCH();
-        if (d_info) { const int32_t why[3] = {0, 0, 2}; SIS_CHECK_CUDA(cudaMemcpyAsync(d_info, why, sizeof(why), cudaMemcpyHostToDevice, stream)); }
-        return SIS_OK;
-    }
+    SIS_REQUIRE(size <= 1024, "contour stage: image size %d not supported (a window row must fit 32 word columns: <= 1024)", size);
     static int halve_set = -1;
     if (halve_set < 0) {
         const char* e = getenv("SIS_CT_HALVE");
@@ -712,7 +725,7 @@ extern "C" int sis_contour_stage(const uint8_t* const* d_det_masks, const uint8_
     }
     SIS_CHECK_CUDA(cudaMemsetAsync(W.fillmap, 0xff, ns * G.px * 4, stream));
     SIS_CHECK_CUDA(cudaMemsetAsync(W.key_count, 0, np * 4, stream));
-    SIS_CHECK_CUDA(cudaMemsetAsync(W.ctr, 0, (char*)(base + L.total) - (char*)W.ctr, stream));      // counters, control words, per-image sums
+    SIS_CHECK_CUDA(cudaMemsetAsync(W.ctr, 0, (char*)(base + L.scratch) - (char*)W.ctr, stream));    // counters, control words, per-image sums
     const int grid_px = (int)min((int64_t)kNumSMs * 16, ceil_div64(np * G.px, 256));
     const int grid_seg = (int)min((int64_t)kNumSMs * 16, ceil_div64(ns * G.px, 256));
     const int grid_img = (int)min((int64_t)kNumSMs * 16, ceil_div64((int64_t)batch * G.px, 256));
@@ -736,8 +749,8 @@ extern "C" int sis_contour_stage(const uint8_t* const* d_det_masks, const uint8_
                 ct_group_accum_kernel<<<grid_sh, 256, 0, stream>>>(W, o, pass); SIS_CHECK_LAUNCH();
             }
             ct_list_groups_kernel<<<grid_sh, 256, 0, stream>>>(W, o); SIS_CHECK_LAUNCH();
-            ct_group_fill_kernel<128, false><<<kNumSMs * 8, 128, fill_smem_small, stream>>>(G, W, o); SIS_CHECK_LAUNCH();
-            ct_group_fill_kernel<1024, true><<<kNumSMs, 1024, fill_smem, stream>>>(G, W, o); SIS_CHECK_LAUNCH();
+            ct_group_fill_kernel<128, false><<<kNumSMs * 8, 128, fill_smem_small, stream>>>(G, W, o, fill_smem_small / 4); SIS_CHECK_LAUNCH();
+            ct_group_fill_kernel<1024, true><<<kNumSMs, 1024, fill_smem, stream>>>(G, W, o, fill_smem / 4); SIS_CHECK_LAUNCH();
         }
     }
     ct_finalize_kernel<<<grid_sh, 256, 0, stream>>>(G, W); SIS_CHECK_LAUNCH();

@@ -351,7 +351,7 @@ class LabelledPairGenerator:
 
     def device_contours_supported(self) -> bool:
         """Whether `iter_segmented` takes the device contour stage by default: every class is present under every key the
-        stage reads, and the image size is one whose window bitmasks fit in shared memory (<= 832)."""
+        stage reads, and the image size is at most 1024 (a window row of the hole fill is 32 word columns)."""
         from . import contours_device
         names = {layer: list(self.segmenter.class_label_map[layer].keys()) for layer in self.segmenter.catalog}
         for dst in self.segmenter.keys_to_merge:
@@ -360,7 +360,7 @@ class LabelledPairGenerator:
             stage = contours_device.DeviceContourStage(self.segmenter.contour_config())
         except KeyError:
             return False
-        return stage.supports(names) and self.generator.size <= 832
+        return stage.supports(names) and self.generator.size <= 1024
 
     def _iter_segmented_device(self, depth, pool, lag, cfg) -> Iterator[SegmentedBatch]:
         import collections

@@ -152,15 +152,27 @@ def assign_round_ids(kept_counts: Sequence[int], n_before: int, num_images: int)
     return starts, n, n >= num_images
 
 
+_HOST_GROUP = None
+
+
 def exchange_kept_counts(kept: int, device=None) -> List[int]:
-    """All-gather of this rank's kept count (one int64 per rank and round); [kept] without a process group."""
+    """All-gather of this rank's kept count (one int64 per rank and round); [kept] without a process group.
+    The exchange runs over a host-side (gloo) group created on first use: a NCCL collective would be enqueued behind the
+    generator passes already queued on the device and stall the loop for a whole batch every round."""
     import torch
     import torch.distributed as dist
+    global _HOST_GROUP
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return [int(kept)]
-    mine = torch.tensor([int(kept)], dtype=torch.int64, device=device)
+    if dist.get_backend() == 'gloo':
+        group = None
+    else:
+        if _HOST_GROUP is None:
+            _HOST_GROUP = dist.new_group(backend='gloo')        # collective: every rank reaches its first `add` together
+        group = _HOST_GROUP
+    mine = torch.tensor([int(kept)], dtype=torch.int64)
     gathered = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
-    dist.all_gather(gathered, mine)
+    dist.all_gather(gathered, mine, group=group)
     return [int(g.item()) for g in gathered]
 
 

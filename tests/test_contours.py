@@ -154,3 +154,31 @@ def test_empty_and_single_inputs():
     blank = {k: {n: numpy.zeros((2, 64, 64), dtype=bool) for n in COLORS} for k in ('8', '12')}
     images, drop = pc.segment_masks(blank, 2, cfg)
     assert images.shape == (2, 64, 64, 3) and not images.any() and drop == []
+
+
+def test_device_stage_host_logic():
+    """contours_device without a GPU: `supports` (every class under every key), the host fall-back entry point, and
+    `segment` taking the host path as a whole when a key lacks a class (the device stage needs all of them)."""
+    import torch
+    from synthesis_in_style_b200 import contours_device as pd
+    cfg = pc.ContourConfig(64, COLORS, ['8', '9'], ['12', '13'], False, 10)
+    stage = pd.DeviceContourStage(cfg)
+    names = {k: list(COLORS) for k in ('8', '9', '12', '13')}
+    assert stage.classes == ['printed_text', 'handwritten_text'] and stage.supports(names)
+    assert not stage.supports({**names, '9': ['background', 'printed_text']}) and not stage.supports({k: names[k] for k in ('8', '9', '12')})
+    with pytest.raises(KeyError):
+        pd.DeviceContourStage(cfg, fine_class='nope')
+    pred = co.synthetic_document_masks(9, 3, 64)
+    want_images, want_drop = pc.segment_masks(pred, 3, cfg)
+    host = {k: (list(v), numpy.stack([m.astype(numpy.uint8) for m in v.values()])) for k, v in pred.items()}
+    res = pd.host_fallback(host, [2, 0], cfg)
+    assert set(res) == {0, 2}
+    for b in (0, 2):
+        assert numpy.array_equal(res[b][0], want_images[b]) and res[b][1] == (b in want_drop)
+    # a key without 'handwritten_text': the reference's contour lists are then shorter; the whole batch goes to the host path
+    partial = {k: {n: torch.from_numpy(m.astype(numpy.uint8)) for n, m in v.items() if not (k == '9' and n == 'handwritten_text')}
+               for k, v in pred.items()}
+    ref_images, ref_drop = pc.segment_masks({k: {n: m.numpy() for n, m in v.items()} for k, v in partial.items()}, 3, cfg)
+    got_images, got_drop = pd.segment(partial, 3, cfg)
+    assert numpy.array_equal(got_images, ref_images) and got_drop == sorted(ref_drop)
+    assert pd.warm_worker() > 0

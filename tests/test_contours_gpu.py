@@ -133,6 +133,24 @@ def test_device_other_key_counts(cuda_device, keys):
     check_against(pred, batch, cfg, cuda_device, want_images, want_drop)
 
 
+@pytest.mark.parametrize('size', [512, 1024])
+def test_device_large_images(cuda_device, size):
+    """512^2 (bitmasks of the widest windows still in shared memory) and 1024^2 (workspace slices, windows without rim
+    columns): a frame around the whole image makes one group span it; a blob inside the frame's hole gets swallowed."""
+    batch = 2
+    pred = co.synthetic_document_masks(5, batch, size)
+    pred = {k: {n: numpy.ascontiguousarray(m).astype(numpy.uint8) for n, m in v.items()} for k, v in pred.items()}
+    frame = numpy.zeros((size, size), numpy.uint8)
+    frame[0:6, :] = frame[-6:, :] = 1
+    frame[:, 0:6] = frame[:, -6:] = 1
+    for k in ('12', '13', '8', '9'):
+        pred[k]['printed_text'][1] |= frame
+        pred[k]['background'][1] &= 1 - frame
+    cfg = pc.ContourConfig(size, COLORS, ['8', '9'], ['12', '13'], False, 50)
+    want_images, want_drop = pc.segment_masks(pred, batch, cfg)
+    check_against(pred, batch, cfg, cuda_device, want_images, want_drop)
+
+
 def test_device_stage_errors(cuda_device):
     cfg = pc.ContourConfig(64, COLORS, ['8', '9'], ['12', '13'], True, 0)
     pred = co.synthetic_document_masks(3, 2, 64)
