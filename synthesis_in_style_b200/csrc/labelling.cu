@@ -167,9 +167,15 @@ __global__ void __launch_bounds__(32 * LBL_SLICES) label_native_kernel(LabelArgs
 // margins are unchanged): k packed FMAs per pixel pair per channel instead of 2k.  At k ~ 20 the direct form needs more
 // fp32 FMA throughput than the SM has per HBM byte; SURVEY.md §7 measured <= 1 flip per 131 k pixels (never at margin
 // > 1e-3) between the two forms.  k <= 8 keeps the reference's (A - B)^2 form, which is memory-bound anyway.
-template <int KMAX, bool RGB>
+// SPLIT = 4 (maps with fewer than two blocks per SM, e.g. 64^2 at batch 32: 128 blocks on 148 SMs at 34-48 % of the DRAM
+// peak): a block is 64 quads x 4 channel slices, each slice accumulates a quarter of the channels for the same pixels and
+// slices 1..3 hand their partial sums to slice 0 through shared memory (added in slice order: deterministic), which
+// finalises as before: four times the blocks and loads in flight for the same bytes.
+template <int KMAX, bool RGB, int SPLIT = 1>
 __global__ void __launch_bounds__(256, (KMAX > 8 ? 2 : 3)) label_wide_kernel(LabelArgs a, ToRgbArgs g) {
     constexpr bool EXPANDED = KMAX > 8;
+    static_assert(SPLIT == 1 || !EXPANDED, "the channel split is only built for the direct form (k <= 8)");
+    constexpr int QPB = 256 / SPLIT;                                            // quads per block
     extern __shared__ float smem[];
     float2* sc2 = reinterpret_cast<float2*>(smem);                              // [C][KMAX] splatted centroids
     float2* sw2 = sc2 + (size_t)a.C * KMAX;                                     // [C][3] splatted scale*W*s of this sample (RGB)
@@ -179,8 +185,9 @@ __global__ void __launch_bounds__(256, (KMAX > 8 ? 2 : 3)) label_wide_kernel(Lab
     const int64_t hw = (int64_t)a.H * a.W;
     const int64_t quads_per_sample = hw >> 2;                                   // a multiple of 256 (checked on the host):
     const int64_t total = quads_per_sample * a.batch;                           // a block never straddles two samples
-    const int64_t q = (int64_t)blockIdx.x * 256 + tid;
-    const int b_blk = (int)(((int64_t)blockIdx.x * 256) / quads_per_sample);
+    const int slice = tid / QPB;
+    const int64_t q = (int64_t)blockIdx.x * QPB + (tid - slice * QPB);
+    const int b_blk = (int)(((int64_t)blockIdx.x * QPB) / quads_per_sample);
     for (int i = tid; i < a.C * KMAX; i += 256) {
         int c = i / KMAX, kk = i - c * KMAX;
         const float m = kk < a.k ? a.centroids[(int64_t)kk * a.C + c] : 0.0f;
@@ -221,8 +228,9 @@ __global__ void __launch_bounds__(256, (KMAX > 8 ? 2 : 3)) label_wide_kernel(Lab
             for (int p = 0; p < 4; ++p) accK[kk][p] = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < 3; ++j) { rgb2[j][0] = make_float2(0.f, 0.f); rgb2[j][1] = make_float2(0.f, 0.f); }
+        const int c_per = a.C / SPLIT, c_begin = slice * c_per, c_end = c_begin + c_per;     // C % SPLIT == 0 (host-side check)
 #pragma unroll 8
-        for (int c = 0; c < a.C; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
             const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(xb + (int64_t)c * hw));
             const float2 x01 = make_float2(v.x, v.y), x23 = make_float2(v.z, v.w);
             if (RGB) {
@@ -253,6 +261,47 @@ __global__ void __launch_bounds__(256, (KMAX > 8 ? 2 : 3)) label_wide_kernel(Lab
                 }
             }
         }
+        if (SPLIT > 1) {
+            // every thread of the block is in range (quads per sample is a multiple of 256): the barrier is uniform
+            constexpr int NACC = KMAX * 4 + (RGB ? 12 : 0);
+            float* red = scn + KMAX;                                             // [SPLIT - 1][QPB][NACC], conflict-free by quad
+            const int ql = tid - slice * QPB;
+            if (slice > 0) {
+                float* r = red + ((size_t)(slice - 1) * NACC) * QPB + ql;
+#pragma unroll
+                for (int kk = 0; kk < KMAX; ++kk) {
+                    r[(kk * 4 + 0) * QPB] = acc2[kk][0].x; r[(kk * 4 + 1) * QPB] = acc2[kk][0].y;
+                    r[(kk * 4 + 2) * QPB] = acc2[kk][1].x; r[(kk * 4 + 3) * QPB] = acc2[kk][1].y;
+                }
+                if (RGB) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        r[(KMAX * 4 + j * 4 + 0) * QPB] = rgb2[j][0].x; r[(KMAX * 4 + j * 4 + 1) * QPB] = rgb2[j][0].y;
+                        r[(KMAX * 4 + j * 4 + 2) * QPB] = rgb2[j][1].x; r[(KMAX * 4 + j * 4 + 3) * QPB] = rgb2[j][1].y;
+                    }
+                }
+            }
+            __syncthreads();
+            if (slice == 0) {
+#pragma unroll
+                for (int sl = 0; sl < SPLIT - 1; ++sl) {
+                    const float* r = red + ((size_t)sl * NACC) * QPB + ql;
+#pragma unroll
+                    for (int kk = 0; kk < KMAX; ++kk) {
+                        acc2[kk][0].x += r[(kk * 4 + 0) * QPB]; acc2[kk][0].y += r[(kk * 4 + 1) * QPB];
+                        acc2[kk][1].x += r[(kk * 4 + 2) * QPB]; acc2[kk][1].y += r[(kk * 4 + 3) * QPB];
+                    }
+                    if (RGB) {
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+                            rgb2[j][0].x += r[(KMAX * 4 + j * 4 + 0) * QPB]; rgb2[j][0].y += r[(KMAX * 4 + j * 4 + 1) * QPB];
+                            rgb2[j][1].x += r[(KMAX * 4 + j * 4 + 2) * QPB]; rgb2[j][1].y += r[(KMAX * 4 + j * 4 + 3) * QPB];
+                        }
+                    }
+                }
+            }
+        }
+        if (slice == 0) {
         float acc[KMAX][4];
         if (EXPANDED) {
 #pragma unroll
@@ -330,6 +379,7 @@ __global__ void __launch_bounds__(256, (KMAX > 8 ? 2 : 3)) label_wide_kernel(Lab
                 }
             }
         }
+        }      // slice 0
     }
     if (a.hist) {
         for (int kk = 0; kk < a.k; ++kk) {
@@ -464,15 +514,32 @@ static int launch_native(const LabelArgs& a, cudaStream_t stream) {
     return SIS_OK;
 }
 
-template <int KMAX, bool RGB>
-static int launch_wide_impl(const LabelArgs& a, const ToRgbArgs& g, cudaStream_t stream) {
-    size_t smem = ((size_t)a.C * KMAX * 2 + (RGB ? 6 * a.C : 0) + 2 * KMAX) * sizeof(float);   // (expanded form uses half the table)
-    auto kern = label_wide_kernel<KMAX, RGB>;
+static int label_split_enabled() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SIS_LABEL_SPLIT"); v = (e && e[0] == '0') ? 0 : 1; }
+    return v;
+}
+
+template <int KMAX, bool RGB, int SPLIT>
+static int launch_wide_split(const LabelArgs& a, const ToRgbArgs& g, cudaStream_t stream) {
+    constexpr int QPB = 256 / SPLIT, NACC = KMAX * 4 + (RGB ? 12 : 0);
+    size_t smem = ((size_t)a.C * KMAX * 2 + (RGB ? 6 * a.C : 0) + 2 * KMAX + (size_t)(SPLIT - 1) * QPB * NACC) * sizeof(float);   // (expanded form uses half the table)
+    auto kern = label_wide_kernel<KMAX, RGB, SPLIT>;
     if (smem > 48 * 1024) SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t quads = (int64_t)a.H * a.W / 4 * a.batch;
-    kern<<<(unsigned)ceil_div64(quads, 256), 256, smem, stream>>>(a, g);
+    kern<<<(unsigned)ceil_div64(quads, QPB), 256, smem, stream>>>(a, g);
     SIS_CHECK_LAUNCH();
     return SIS_OK;
+}
+
+template <int KMAX, bool RGB>
+static int launch_wide_impl(const LabelArgs& a, const ToRgbArgs& g, cudaStream_t stream) {
+    // fewer than two blocks per SM: split the channels over four thread groups (direct form only)
+    const int64_t quads = (int64_t)a.H * a.W / 4 * a.batch;
+    if constexpr (KMAX <= 8) {
+        if (quads / 256 < 2 * kNumSMs && a.C % 4 == 0 && label_split_enabled()) return launch_wide_split<KMAX, RGB, 4>(a, g, stream);
+    }
+    return launch_wide_split<KMAX, RGB, 1>(a, g, stream);
 }
 template <int KMAX>
 static int launch_wide(const LabelArgs& a, const ToRgbArgs* g, cudaStream_t stream) {
