@@ -612,11 +612,6 @@ __global__ void ct_info_kernel(CtWs W, int32_t* info) {
     info[1] = rounds;
     info[2] = W.ctr[CTR_OVERFLOW] ? 1 : ct_round_active(W, CT_ROUNDS) ? 3 : 0;
 }
-__global__ void ct_fill_flags_kernel(int32_t* flags, int n, int v) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) flags[i] = v;
-}
-
 constexpr int CT_FILL_SMEM_MAX = 200 * 1024;
 struct CtLayout {
     int64_t lab, aux, fillmap, key_count, fmask, touch, shapes, ctr, img, scratch, total;
