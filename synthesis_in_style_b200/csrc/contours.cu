@@ -124,12 +124,12 @@ __device__ __forceinline__ int ct_run_start(bool in, bool row_start, int lane) {
 }
 
 // pass 1: dilated mask; background pixels point at their run start, foreground = -1
-__global__ void __launch_bounds__(256) ct_bg_init_kernel(CtGeom G, CtWs W) {
-    const int64_t total = (int64_t)G.n_plane_types() * G.B * G.px, rounded = (total + 31) / 32 * 32;
+__global__ void __launch_bounds__(256) ct_bg_init_kernel(const __grid_constant__ CtGeom G, const __grid_constant__ CtWs W) {
+    const int total = G.n_plane_types() * G.B * G.px, rounded = (total + 31) / 32 * 32;     // < 2^31 (checked on the host)
     const int lane = threadIdx.x & 31;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < rounded; i += (int64_t)gridDim.x * 256) {
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < rounded; i += gridDim.x * 256) {
         const bool valid = i < total;
-        const int plane = valid ? (int)(i / G.px) : 0, p = valid ? (int)(i - (int64_t)plane * G.px) : 0;
+        const int plane = valid ? i / G.px : 0, p = valid ? i - plane * G.px : 0;
         const int y = p / G.S, x = p - y * G.S;
         bool d = true;
         if (valid) {
@@ -149,11 +149,11 @@ __global__ void __launch_bounds__(256) ct_bg_init_kernel(CtGeom G, CtWs W) {
     }
 }
 // background, 4-connectivity
-__global__ void __launch_bounds__(256) ct_bg_merge_kernel(CtGeom G, CtWs W) {
-    const int64_t total = (int64_t)G.n_plane_types() * G.B * G.px;
+__global__ void __launch_bounds__(256) ct_bg_merge_kernel(const __grid_constant__ CtGeom G, const __grid_constant__ CtWs W) {
+    const int total = G.n_plane_types() * G.B * G.px;
     const int lane = threadIdx.x & 31;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-        const int plane = (int)(i / G.px), p = (int)(i - (int64_t)plane * G.px);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+        const int plane = i / G.px, p = i - plane * G.px;
         int32_t* par = W.aux + (int64_t)plane * G.px;
         if (par[p] < 0) continue;
         const int y = p / G.S, x = p - y * G.S;
@@ -163,22 +163,22 @@ __global__ void __launch_bounds__(256) ct_bg_merge_kernel(CtGeom G, CtWs W) {
     }
 }
 // background sets that reach the image border are the outside (marked at their roots, once the sets are final)
-__global__ void __launch_bounds__(256) ct_bg_touch_kernel(CtGeom G, CtWs W) {
-    const int64_t total = (int64_t)G.n_plane_types() * G.B * 4 * G.S;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-        const int plane = (int)(i / (4 * G.S)), j = (int)(i - (int64_t)plane * 4 * G.S), side = j / G.S, t = j - side * G.S;
+__global__ void __launch_bounds__(256) ct_bg_touch_kernel(const __grid_constant__ CtGeom G, const __grid_constant__ CtWs W) {
+    const int total = G.n_plane_types() * G.B * 4 * G.S;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+        const int plane = i / (4 * G.S), j = i - plane * 4 * G.S, side = j / G.S, t = j - side * G.S;
         const int p = side == 0 ? t : side == 1 ? (G.S - 1) * G.S + t : side == 2 ? t * G.S : t * G.S + G.S - 1;
         int32_t* par = W.aux + (int64_t)plane * G.px;
         if (par[p] >= 0) W.touch[(int64_t)plane * G.px + uf_find_halve(par, p)] = 1;
     }
 }
 // pass 2: filled foreground = dilated mask + background that does not reach the border; pixels point at their run start
-__global__ void __launch_bounds__(256) ct_fg_init_kernel(CtGeom G, CtWs W) {
-    const int64_t total = (int64_t)G.n_plane_types() * G.B * G.px, rounded = (total + 31) / 32 * 32;
+__global__ void __launch_bounds__(256) ct_fg_init_kernel(const __grid_constant__ CtGeom G, const __grid_constant__ CtWs W) {
+    const int total = G.n_plane_types() * G.B * G.px, rounded = (total + 31) / 32 * 32;     // < 2^31 (checked on the host)
     const int lane = threadIdx.x & 31;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < rounded; i += (int64_t)gridDim.x * 256) {
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < rounded; i += gridDim.x * 256) {
         const bool valid = i < total;
-        const int plane = valid ? (int)(i / G.px) : 0, p = valid ? (int)(i - (int64_t)plane * G.px) : 0;
+        const int plane = valid ? i / G.px : 0, p = valid ? i - plane * G.px : 0;
         const int x = p % G.S;
         bool f = false;
         if (valid) {
@@ -194,12 +194,12 @@ __global__ void __launch_bounds__(256) ct_fg_init_kernel(CtGeom G, CtWs W) {
 }
 // filled foreground, 8-connectivity: W at the segment seam; N at the first pixel of a contact; NW / NE only when neither N
 // nor the run neighbour on that side already carries the link
-__global__ void __launch_bounds__(256) ct_fg_merge_kernel(CtGeom G, CtWs W) {
-    const int64_t total = (int64_t)G.n_plane_types() * G.B * G.px;
+__global__ void __launch_bounds__(256) ct_fg_merge_kernel(const __grid_constant__ CtGeom G, const __grid_constant__ CtWs W) {
+    const int total = G.n_plane_types() * G.B * G.px;
     const int lane = threadIdx.x & 31;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
         if (!W.fmask[i]) continue;
-        const int plane = (int)(i / G.px), p = (int)(i - (int64_t)plane * G.px);
+        const int plane = i / G.px, p = i - plane * G.px;
         int32_t* lab = W.lab + (int64_t)plane * G.px;
         const uint8_t* f = W.fmask + (int64_t)plane * G.px;
         const int S = G.S, y = p / S, x = p - y * S;
@@ -216,11 +216,11 @@ __global__ void __launch_bounds__(256) ct_fg_merge_kernel(CtGeom G, CtWs W) {
     }
 }
 // roots get a compact shape id (aux[root]); every pixel's label becomes its root
-__global__ void __launch_bounds__(256) ct_fg_ids_kernel(CtGeom G, CtWs W) {
-    const int64_t total = (int64_t)G.n_plane_types() * G.B * G.px;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+__global__ void __launch_bounds__(256) ct_fg_ids_kernel(const __grid_constant__ CtGeom G, const __grid_constant__ CtWs W) {
+    const int total = G.n_plane_types() * G.B * G.px;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
         if (!W.fmask[i]) continue;
-        const int plane = (int)(i / G.px), p = (int)(i - (int64_t)plane * G.px);
+        const int plane = i / G.px, p = i - plane * G.px;
         int32_t* lab = W.lab + (int64_t)plane * G.px;
         // plain find: every store of this kernel is a final root.  (A halving find here could land its grandparent store
         // AFTER another thread's root store and leave a pixel pointing at an inner node, which the next kernel would read.)
@@ -241,12 +241,12 @@ __global__ void __launch_bounds__(256) ct_fg_ids_kernel(CtGeom G, CtWs W) {
     }
 }
 // per-shape pixel count, chain length (cracks - convex corners) and bounding box; labels become shape ids
-__global__ void __launch_bounds__(256) ct_shape_stats_kernel(CtGeom G, CtWs W) {
-    const int64_t total = (int64_t)G.n_plane_types() * G.B * G.px;
+__global__ void __launch_bounds__(256) ct_shape_stats_kernel(const __grid_constant__ CtGeom G, const __grid_constant__ CtWs W) {
+    const int total = G.n_plane_types() * G.B * G.px;
     const int lane = threadIdx.x & 31;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
         if (!W.fmask[i]) continue;
-        const int plane = (int)(i / G.px), p = (int)(i - (int64_t)plane * G.px);
+        const int plane = i / G.px, p = i - plane * G.px;
         const int64_t base = (int64_t)plane * G.px;
         const int id = W.aux[base + W.lab[i]];
         W.lab[i] = id;
@@ -293,14 +293,14 @@ __device__ __forceinline__ int ct_cover(const CtGeom& G, const CtWs& W, int st, 
     }
     return n;
 }
-__global__ void __launch_bounds__(256) ct_pairs_kernel(CtGeom G, CtWs W, int round, int pass) {
+__global__ void __launch_bounds__(256) ct_pairs_kernel(const __grid_constant__ CtGeom G, const __grid_constant__ CtWs W, int round, int pass) {
     int32_t* ctl = W.ctl + round * CTL_STRIDE;
     // pass 0: whenever the round is active; pass 1: only when pass 0 both joined groups (boxes grew) and held a pair back
     if (!ct_round_active(W, round)) return;
     if (pass == 1 && !(((volatile int32_t*)ctl)[CTL_CHANGED1] && ((volatile int32_t*)ctl)[CTL_DEFERRED1])) return;
-    const int64_t total = (int64_t)G.n_seg_types() * G.B * G.px;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-        const int seg = (int)(i / G.px), p = (int)(i - (int64_t)seg * G.px);
+    const int total = G.n_seg_types() * G.B * G.px;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+        const int seg = i / G.px, p = i - seg * G.px;
         const int st = seg / G.B, b = seg - st * G.B, nk = G.keys_of(st);
         if (nk < 2) continue;                            // a single key is never merged (base_cluster_based...:209)
         int covered = W.fillmap[i] >= 0;
@@ -322,14 +322,14 @@ __device__ __forceinline__ bool ct_boxes_needed(const CtWs& W, int round, int pa
     const volatile int32_t* ctl = W.ctl + round * CTL_STRIDE;
     return pass == 0 ? ctl[CTL_CHANGED1] != 0 : (ctl[CTL_CHANGED1] != 0 && ctl[CTL_DEFERRED1] != 0);
 }
-__global__ void __launch_bounds__(256) ct_group_reset_kernel(CtWs W, int round, int pass) {
+__global__ void __launch_bounds__(256) ct_group_reset_kernel(const __grid_constant__ CtWs W, int round, int pass) {
     if (!ct_boxes_needed(W, round, pass)) return;
     const int n = min(W.ctr[CTR_SHAPES], W.cap);
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
         W.g_x0[i] = INT_MAX; W.g_y0[i] = INT_MAX; W.g_x1[i] = -1; W.g_y1[i] = -1; W.g_members[i] = 0;
     }
 }
-__global__ void __launch_bounds__(256) ct_group_accum_kernel(CtWs W, int round, int pass) {
+__global__ void __launch_bounds__(256) ct_group_accum_kernel(const __grid_constant__ CtWs W, int round, int pass) {
     if (!ct_boxes_needed(W, round, pass)) return;
     const int n = min(W.ctr[CTR_SHAPES], W.cap);
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(256) ct_group_accum_kernel(CtWs W, int round, 
 // merged groups whose hole fill is out of date: small windows from the front of the list, large ones from its end (they
 // get bigger blocks)
 constexpr int CT_BIG_WINDOW = 96 * 96;
-__global__ void __launch_bounds__(256) ct_list_groups_kernel(CtWs W, int round) {
+__global__ void __launch_bounds__(256) ct_list_groups_kernel(const __grid_constant__ CtWs W, int round) {
     if (!ct_round_active(W, round)) return;
     int32_t* ctl = W.ctl + round * CTL_STRIDE;
     if (round > 0 && !((volatile int32_t*)ctl)[CTL_CHANGED1]) return;      // no group changed: every fill is up to date
@@ -381,7 +381,7 @@ __device__ __forceinline__ uint32_t ct_spread(uint32_t s, uint32_t f) {
 // L2).  A window wider than 1024 pixels (32 word columns, one per lane) drops its left / right rim columns and seeds the
 // free pixels of its first / last column instead: a reached rim column next to them is all the rim ever contributes.
 template <int NT, bool BIG>
-__global__ void __launch_bounds__(NT) ct_group_fill_kernel(CtGeom G, CtWs W, int round, int smem_words) {
+__global__ void __launch_bounds__(NT) ct_group_fill_kernel(const __grid_constant__ CtGeom G, const __grid_constant__ CtWs W, int round, int smem_words) {
     extern __shared__ uint32_t ct_sm[];
     __shared__ int red[3];
     constexpr int NW = NT / 32;
@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(NT) ct_group_fill_kernel(CtGeom G, CtWs W, int
 
 // ------------------------------------------------------------------------------------------------ decisions
 // which groups survive merge_contours_of_same_class_from_different_images + drop_too_small_contours
-__global__ void __launch_bounds__(256) ct_finalize_kernel(CtGeom G, CtWs W) {
+__global__ void __launch_bounds__(256) ct_finalize_kernel(const __grid_constant__ CtGeom G, const __grid_constant__ CtWs W) {
     const int n = min(W.ctr[CTR_SHAPES], W.cap);
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
         if (W.parent[i] != i) continue;
@@ -534,10 +534,10 @@ __global__ void __launch_bounds__(256) ct_finalize_kernel(CtGeom G, CtWs W) {
 }
 // classify_fine_grained_contours' overlap sums: score[fine group][class] += 1 per common pixel with a kept region of the
 // class whose bounding box strictly overlaps the fine group's
-__global__ void __launch_bounds__(256) ct_classify_kernel(CtGeom G, CtWs W) {
-    const int64_t total = (int64_t)G.B * G.px;
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-        const int b = (int)(i / G.px), p = (int)(i - (int64_t)b * G.px);
+__global__ void __launch_bounds__(256) ct_classify_kernel(const __grid_constant__ CtGeom G, const __grid_constant__ CtWs W) {
+    const int total = G.B * G.px;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+        const int b = i / G.px, p = i - b * G.px;
         int fg[CT_MAX_KEYS + 1], rg[CT_MAX_KEYS + 1];
         const int nf = ct_cover(G, W, G.n_cls, b, p, fg);
         if (!nf) continue;
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(256) ct_classify_kernel(CtGeom G, CtWs W) {
         }
     }
 }
-__global__ void __launch_bounds__(256) ct_assign_kernel(CtGeom G, CtWs W) {
+__global__ void __launch_bounds__(256) ct_assign_kernel(const __grid_constant__ CtGeom G, const __grid_constant__ CtWs W) {
     const int n = min(W.ctr[CTR_SHAPES], W.cap);
     for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
         if (W.parent[i] != i || !W.g_kept[i]) continue;
@@ -575,11 +575,11 @@ __global__ void __launch_bounds__(256) ct_assign_kernel(CtGeom G, CtWs W) {
     }
 }
 // render_segmentation_image + determine_images_to_drop
-__global__ void __launch_bounds__(256) ct_render_kernel(CtGeom G, CtWs W, uint8_t* __restrict__ out, int32_t* __restrict__ flags) {
-    const int64_t total = (int64_t)G.B * G.px;
+__global__ void __launch_bounds__(256) ct_render_kernel(const __grid_constant__ CtGeom G, const __grid_constant__ CtWs W, uint8_t* __restrict__ out, int32_t* __restrict__ flags) {
+    const int total = G.B * G.px;
     const uint8_t* ink_plane = G.planes[G.n_cls * G.n_det + G.n_fine - 1];
-    for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
-        const int b = (int)(i / G.px), p = (int)(i - (int64_t)b * G.px);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+        const int b = i / G.px, p = i - b * G.px;
         int cls = -1;
         if (ink_plane[i]) {
             int fg[CT_MAX_KEYS + 1];
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(256) ct_render_kernel(CtGeom G, CtWs W, uint8_
     }
 }
 // [shapes, rounds that did something, why the batch was handed to the host (0: it was not, 1: capacity, 3: fixpoint still moving)]
-__global__ void ct_info_kernel(CtWs W, int32_t* info) {
+__global__ void ct_info_kernel(const __grid_constant__ CtWs W, int32_t* info) {
     int rounds = 0;
     for (int o = 0; o < CT_ROUNDS; ++o) rounds += ct_round_active(W, o) && (o == 0 || W.ctl[o * CTL_STRIDE + CTL_CHANGED1] || W.ctl[(o - 1) * CTL_STRIDE + CTL_FILL_NEW]);
     info[0] = W.ctr[CTR_SHAPES];
@@ -707,6 +707,8 @@ extern "C" int sis_contour_stage(const uint8_t* const* d_det_masks, const uint8_
     const int fill_smem = fill_full <= CT_FILL_SMEM_MAX ? fill_full : 96 * 1024;          // larger windows go to W.scratch
     const int fill_smem_small = min(fill_smem, 2 * 4 * (CT_BIG_WINDOW / 32 + wmax + 8));    // words <= area/32 + rows
     SIS_REQUIRE(size <= 1024, "contour stage: image size %d not supported (a window row must fit 32 word columns: <= 1024)", size);
+    SIS_REQUIRE((int64_t)(n_classes * n_det_keys + n_fine_keys) * batch * size * size < (int64_t)1 << 31,
+                "contour stage: %d planes of %d^2 pixels exceed the 32-bit pixel index; split the batch", (n_classes * n_det_keys + n_fine_keys) * batch, size);
     static int halve_set = -1;
     if (halve_set < 0) {
         const char* e = getenv("SIS_CT_HALVE");
