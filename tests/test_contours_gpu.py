@@ -159,3 +159,16 @@ def test_device_stage_errors(cuda_device):
         stage.run({k: (list(v), torch.stack([torch.from_numpy(m.astype(numpy.uint8)) for m in v.values()])) for k, v in pred.items()})   # host tensors
     with pytest.raises(KeyError):
         pd.DeviceContourStage(cfg, fine_class='no_such_class')
+
+
+def test_device_randomised_cross_check(cuda_device):
+    """A short run of scripts/stress_contours.py (random mask statistics, sizes that are not multiples of 32, 1-3 keys per
+    stage, all configurations): every case must agree with the host polygon path.  (530 cases on a B200:
+    profiles/r03t_contour_stress.txt.)"""
+    import subprocess
+    import sys
+    root = os.path.dirname(HERE)
+    res = subprocess.run([sys.executable, os.path.join(root, 'scripts', 'stress_contours.py'), '--cases', '30', '--seed', '11'],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
+    assert ' 0 mismatching cases' in res.stdout
