@@ -174,12 +174,14 @@ __global__ void __launch_bounds__(32 * LBL_SLICES) label_native_kernel(LabelArgs
 template <int KMAX, bool RGB, int SPLIT = 1>
 __global__ void __launch_bounds__(256, (KMAX > 8 ? 2 : 3)) label_wide_kernel(LabelArgs a, ToRgbArgs g) {
     constexpr bool EXPANDED = KMAX > 8;
-    static_assert(SPLIT == 1 || !EXPANDED, "the channel split is only built for the direct form (k <= 8)");
     constexpr int QPB = 256 / SPLIT;                                            // quads per block
     extern __shared__ float smem[];
     float2* sc2 = reinterpret_cast<float2*>(smem);                              // [C][KMAX] splatted centroids
     float2* sw2 = sc2 + (size_t)a.C * KMAX;                                     // [C][3] splatted scale*W*s of this sample (RGB)
-    unsigned* shist = reinterpret_cast<unsigned*>(sw2 + (RGB ? 3 * a.C : 0));  // [KMAX]
+    // the tables and (SPLIT > 1) the partial sums of slices 1.. share one region: the sums are written after the channel loop
+    constexpr int RED_FLOATS = (SPLIT - 1) * (256 / SPLIT) * (KMAX * 4 + (RGB ? 12 : 0));
+    const int tab_floats = a.C * KMAX * 2 + (RGB ? 6 * a.C : 0);
+    unsigned* shist = reinterpret_cast<unsigned*>(smem + (tab_floats > RED_FLOATS ? tab_floats : RED_FLOATS));  // [KMAX]
     float* scn = reinterpret_cast<float*>(shist + KMAX);                        // [KMAX] |c_k|^2 (expanded form)
     const int tid = threadIdx.x;
     const int64_t hw = (int64_t)a.H * a.W;
@@ -264,14 +266,22 @@ __global__ void __launch_bounds__(256, (KMAX > 8 ? 2 : 3)) label_wide_kernel(Lab
         if (SPLIT > 1) {
             // every thread of the block is in range (quads per sample is a multiple of 256): the barrier is uniform
             constexpr int NACC = KMAX * 4 + (RGB ? 12 : 0);
-            float* red = scn + KMAX;                                             // [SPLIT - 1][QPB][NACC], conflict-free by quad
+            float* red = smem;                                                   // [SPLIT - 1][QPB][NACC], conflict-free by quad
             const int ql = tid - slice * QPB;
+            __syncthreads();                                                     // every slice is done with the tables
             if (slice > 0) {
                 float* r = red + ((size_t)(slice - 1) * NACC) * QPB + ql;
+                if (EXPANDED) {
 #pragma unroll
-                for (int kk = 0; kk < KMAX; ++kk) {
-                    r[(kk * 4 + 0) * QPB] = acc2[kk][0].x; r[(kk * 4 + 1) * QPB] = acc2[kk][0].y;
-                    r[(kk * 4 + 2) * QPB] = acc2[kk][1].x; r[(kk * 4 + 3) * QPB] = acc2[kk][1].y;
+                    for (int kk = 0; kk < KMAX / 2; ++kk)
+#pragma unroll
+                        for (int p = 0; p < 4; ++p) { r[(kk * 8 + p * 2) * QPB] = accK[kk][p].x; r[(kk * 8 + p * 2 + 1) * QPB] = accK[kk][p].y; }
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < KMAX; ++kk) {
+                        r[(kk * 4 + 0) * QPB] = acc2[kk][0].x; r[(kk * 4 + 1) * QPB] = acc2[kk][0].y;
+                        r[(kk * 4 + 2) * QPB] = acc2[kk][1].x; r[(kk * 4 + 3) * QPB] = acc2[kk][1].y;
+                    }
                 }
                 if (RGB) {
 #pragma unroll
@@ -286,10 +296,17 @@ __global__ void __launch_bounds__(256, (KMAX > 8 ? 2 : 3)) label_wide_kernel(Lab
 #pragma unroll
                 for (int sl = 0; sl < SPLIT - 1; ++sl) {
                     const float* r = red + ((size_t)sl * NACC) * QPB + ql;
+                    if (EXPANDED) {
 #pragma unroll
-                    for (int kk = 0; kk < KMAX; ++kk) {
-                        acc2[kk][0].x += r[(kk * 4 + 0) * QPB]; acc2[kk][0].y += r[(kk * 4 + 1) * QPB];
-                        acc2[kk][1].x += r[(kk * 4 + 2) * QPB]; acc2[kk][1].y += r[(kk * 4 + 3) * QPB];
+                        for (int kk = 0; kk < KMAX / 2; ++kk)
+#pragma unroll
+                            for (int p = 0; p < 4; ++p) { accK[kk][p].x += r[(kk * 8 + p * 2) * QPB]; accK[kk][p].y += r[(kk * 8 + p * 2 + 1) * QPB]; }
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < KMAX; ++kk) {
+                            acc2[kk][0].x += r[(kk * 4 + 0) * QPB]; acc2[kk][0].y += r[(kk * 4 + 1) * QPB];
+                            acc2[kk][1].x += r[(kk * 4 + 2) * QPB]; acc2[kk][1].y += r[(kk * 4 + 3) * QPB];
+                        }
                     }
                     if (RGB) {
 #pragma unroll
@@ -523,7 +540,8 @@ static int label_split_enabled() {
 template <int KMAX, bool RGB, int SPLIT>
 static int launch_wide_split(const LabelArgs& a, const ToRgbArgs& g, cudaStream_t stream) {
     constexpr int QPB = 256 / SPLIT, NACC = KMAX * 4 + (RGB ? 12 : 0);
-    size_t smem = ((size_t)a.C * KMAX * 2 + (RGB ? 6 * a.C : 0) + 2 * KMAX + (size_t)(SPLIT - 1) * QPB * NACC) * sizeof(float);   // (expanded form uses half the table)
+    const size_t tab = (size_t)a.C * KMAX * 2 + (RGB ? 6 * a.C : 0), red = (size_t)(SPLIT - 1) * QPB * NACC;   // share one region
+    size_t smem = ((tab > red ? tab : red) + 2 * KMAX) * sizeof(float);
     auto kern = label_wide_kernel<KMAX, RGB, SPLIT>;
     if (smem > 48 * 1024) SIS_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int64_t quads = (int64_t)a.H * a.W / 4 * a.batch;
@@ -534,11 +552,9 @@ static int launch_wide_split(const LabelArgs& a, const ToRgbArgs& g, cudaStream_
 
 template <int KMAX, bool RGB>
 static int launch_wide_impl(const LabelArgs& a, const ToRgbArgs& g, cudaStream_t stream) {
-    // fewer than two blocks per SM: split the channels over four thread groups (direct form only)
+    // fewer than two blocks per SM: split the channels over four thread groups
     const int64_t quads = (int64_t)a.H * a.W / 4 * a.batch;
-    if constexpr (KMAX <= 8) {
-        if (quads / 256 < 2 * kNumSMs && a.C % 4 == 0 && label_split_enabled()) return launch_wide_split<KMAX, RGB, 4>(a, g, stream);
-    }
+    if (quads / 256 < 2 * kNumSMs && a.C % 4 == 0 && label_split_enabled()) return launch_wide_split<KMAX, RGB, 4>(a, g, stream);
     return launch_wide_split<KMAX, RGB, 1>(a, g, stream);
 }
 template <int KMAX>
