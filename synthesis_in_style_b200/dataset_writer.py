@@ -176,6 +176,31 @@ def exchange_kept_counts(kept: int, device=None) -> List[int]:
     return [int(g.item()) for g in gathered]
 
 
+def exchange_kept_counts_async(kept: int):
+    """The same all-gather, started now and finished later: returns `wait() -> [kept count of every rank]`.  The writer
+    starts the exchange of a round when its batch arrives and only needs the answer when it names that batch's files,
+    one batch later: the ranks no longer walk in lock step."""
+    import torch
+    import torch.distributed as dist
+    global _HOST_GROUP
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return lambda: [int(kept)]
+    if dist.get_backend() == 'gloo':
+        group = None
+    else:
+        if _HOST_GROUP is None:
+            _HOST_GROUP = dist.new_group(backend='gloo')
+        group = _HOST_GROUP
+    mine = torch.tensor([int(kept)], dtype=torch.int64)
+    gathered = [torch.zeros_like(mine) for _ in range(dist.get_world_size())]
+    work = dist.all_gather(gathered, mine, group=group, async_op=True)
+
+    def wait():
+        work.wait()
+        return [int(g.item()) for g in gathered]
+    return wait
+
+
 class DatasetWriter:
     """The tail of build_dataset's loop for one rank: drop, assign ids, write the PNGs."""
 
@@ -197,6 +222,8 @@ class DatasetWriter:
             native_threads = getattr(pool, '_max_workers', None) or os.cpu_count() or 4
         self.native_threads = native_threads
         self._native_queue = None
+        self._awaiting = []              # native path: batches whose kept-count exchange is still in flight
+        self.seconds_waiting_for_ranks = 0.0
 
     def add(self, generated_images: numpy.ndarray, label_images: numpy.ndarray, image_ids_to_drop: Sequence[int]) -> int:
         """One batch of this rank (one round): returns how many files it queued."""
@@ -204,20 +231,14 @@ class DatasetWriter:
         if self.native:
             dropped = set(int(d) for d in drop)
             rows = [b for b in range(len(label_images)) if b not in dropped]
-            counts = exchange_kept_counts(len(rows), self.device)
-            starts, self.n, self.finished = assign_round_ids(counts, self.n, self.num_images)
-            start = starts[self.rank if len(starts) > 1 else 0]
-            if start is None or not rows:
-                return 0
-            if self._native_queue is None:
-                from concurrent.futures import ThreadPoolExecutor
-                # two batches in flight: a batch's files rarely divide evenly over the encoder threads, the second call
-                # fills the idle tail of the first (the parallelism proper is inside the call)
-                self._native_queue = ThreadPoolExecutor(2)
-            self._futures.append(self._native_queue.submit(save_generated_images_native, generated_images, label_images, rows, start,
-                                                           self.base_dir, self.num_images, self._level, self.native_threads))
-            self.files_written += len(rows)
-            return len(rows)
+            # The ids of this round need every rank's kept count: the exchange starts now and is waited for when the NEXT
+            # batch arrives (single process: at once).  `finished` therefore turns true one round late in multi-rank runs;
+            # the extra batch gets no ids (assign_round_ids) and is not written.
+            self._awaiting.append((generated_images, label_images, rows, exchange_kept_counts_async(len(rows))))
+            queued = 0
+            while len(self._awaiting) > (1 if self.world_size > 1 else 0):
+                queued += self._name_and_write(self._awaiting.pop(0))
+            return queued
         generated_images = numpy.delete(generated_images, drop, axis=0)
         label_images = numpy.delete(label_images, drop, axis=0)
         counts = exchange_kept_counts(len(label_images), self.device)
@@ -231,7 +252,29 @@ class DatasetWriter:
         self.files_written += len(out)
         return len(out)
 
+    def _name_and_write(self, item) -> int:
+        import time
+        generated_images, label_images, rows, wait = item
+        t0 = time.perf_counter()
+        counts = wait()
+        self.seconds_waiting_for_ranks += time.perf_counter() - t0
+        starts, self.n, self.finished = assign_round_ids(counts, self.n, self.num_images)
+        start = starts[self.rank if len(starts) > 1 else 0]
+        if start is None or not rows:
+            return 0
+        if self._native_queue is None:
+            from concurrent.futures import ThreadPoolExecutor
+            # two batches in flight: a batch's files rarely divide evenly over the encoder threads, the second call
+            # fills the idle tail of the first (the parallelism proper is inside the call)
+            self._native_queue = ThreadPoolExecutor(2)
+        self._futures.append(self._native_queue.submit(save_generated_images_native, generated_images, label_images, rows, start,
+                                                       self.base_dir, self.num_images, self._level, self.native_threads))
+        self.files_written += len(rows)
+        return len(rows)
+
     def flush(self):
+        while self._awaiting:
+            self._name_and_write(self._awaiting.pop(0))
         for f in self._futures:
             f.result()
         self._futures = []
@@ -310,4 +353,5 @@ def build_dataset(pair_generator, base_dir, num_images: int, contour_pool=None, 
     t_flush = time.perf_counter() - t0 - t_loop
     return {'images_kept_all_ranks': writer.n, 'files_written_this_rank': writer.files_written, 'batches_this_rank': batches,
             'contour_stage': dict(getattr(pair_generator, 'contour_stats', None) or {'host': True}),
-            'seconds': {'loop': round(t_loop, 4), 'writer_add': round(t_add, 4), 'final_flush': round(t_flush, 4)}}
+            'seconds': {'loop': round(t_loop, 4), 'writer_add': round(t_add, 4), 'final_flush': round(t_flush, 4),
+                        'waiting_for_ranks': round(writer.seconds_waiting_for_ranks, 4)}}
