@@ -1,5 +1,6 @@
 #!/bin/bash
-TAG=${1:-r03d}
+# dataset leg on one GPU: native PNG writer (deflate, stored) and, for comparison, host contours.  Usage: scripts/gpu_leg_dataset.sh <tag>
+TAG=${1:-r03}
 for PNG in fast stored; do
   timeout 600 python bench.py --leg dataset --steps 150 --png $PNG > gpurun_out/${TAG}_leg_dataset_n1_$PNG.json 2> gpurun_out/${TAG}_leg_dataset_n1_$PNG.err; echo leg1_${PNG}_rc=$?
   python -c "
