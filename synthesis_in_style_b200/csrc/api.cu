@@ -82,5 +82,5 @@ extern "C" void sis_watchdog_clear(void) {
 }
 
 extern "C" const char* sis_last_error(void) { return sis::g_error; }
-extern "C" int sis_version(void) { return 100; }
+extern "C" int sis_version(void) { return 120; }   // 1.2: contour stage, native PNG writer (round 2)
 extern "C" uint64_t sis_launch_count(void) { return (uint64_t)sis::g_launches.load(); }
