@@ -182,3 +182,52 @@ def test_device_stage_host_logic():
     got_images, got_drop = pd.segment(partial, 3, cfg)
     assert numpy.array_equal(got_images, ref_images) and got_drop == sorted(ref_drop)
     assert pd.warm_worker() > 0
+
+
+@pytest.mark.parametrize('tag', ['a', 'b', 'c', 'd', 'e'])
+def test_shape_algebra_equals_reference_goldens(gold, tag):
+    """The algorithm the CUDA contour stage implements (oracle/contour_shape_oracle.py: filled shapes from labelled
+    complements, area from crack / corner counts, merge as a fixpoint, per-pixel classification) reproduces the label
+    images the reference's own classes produced, and its drop decision wherever it does not depend on contour order."""
+    from oracle import contour_shape_oracle as so
+    pred, batch, cfg = load_full(gold, tag)
+    want_images, want_drop = gold[f'full/{tag}/images'], set(int(d) for d in gold[f'full/{tag}/drop'])
+    undecided = 0
+    for b in range(batch):
+        masks = {k: {n: numpy.ascontiguousarray(m[b]).astype(numpy.uint8) for n, m in v.items()} for k, v in pred.items()}
+        image, drop = so.segment_one(masks, cfg.keys_for_class_determination, cfg.keys_for_finegrained_segmentation, list(COLORS), COLORS,
+                                     cfg.image_size, cfg.only_keep_overlapping, cfg.min_class_contour_area)
+        assert numpy.array_equal(image, want_images[b]), (tag, b)
+        if drop is None:
+            undecided += 1
+        else:
+            assert drop == (b in want_drop), (tag, b)
+    assert undecided <= batch // 2
+
+
+def test_shape_algebra_identities_against_cv2():
+    """The three identities on random masks: filled contour = complement component, contourArea = pixels - L/2 - 1,
+    findContours order = descending first pixel."""
+    from scipy import ndimage
+    from oracle import contour_shape_oracle as so
+    rng = numpy.random.RandomState(4)
+    for trial in range(40):
+        size = int(rng.choice([17, 32, 64]))
+        if trial % 2:
+            mask = (rng.rand(size, size) < rng.choice([0.05, 0.3, 0.6])).astype(numpy.uint8)
+        else:
+            mask = (ndimage.gaussian_filter(rng.randn(size, size), 2) > 0.02).astype(numpy.uint8)
+        found, _ = cv2.findContours(mask, cv2.RETR_EXTERNAL, cv2.CHAIN_APPROX_SIMPLE)
+        filled_map = so.fill_outside(mask > 0)
+        labels, n = ndimage.label(filled_map, structure=numpy.ones((3, 3), int))
+        assert n == len(found)
+        firsts = []
+        for contour in found:
+            canvas = numpy.zeros_like(mask)
+            cv2.drawContours(canvas, [contour], 0, 1, cv2.FILLED)
+            ids = numpy.unique(labels[canvas > 0])
+            assert len(ids) == 1 and numpy.array_equal(canvas > 0, labels == ids[0])
+            count, chain = so.crack_stats(labels == ids[0])
+            assert abs(cv2.contourArea(contour) - (count - chain / 2 - 1)) < 1e-9
+            firsts.append(int(numpy.flatnonzero((labels == ids[0]).ravel())[0]))
+        assert firsts == sorted(firsts, reverse=True)
