@@ -382,7 +382,8 @@ class LabelledPairGenerator:
                   'flags': torch.empty(B, dtype=torch.int32).pin_memory()} for _ in range(n_slots)]
         keys = set(cfg.keys_for_class_determination) | set(cfg.keys_for_finegrained_segmentation)
         pending = collections.deque()
-        self.contour_stats = {'images': 0, 'host_fallback': 0, 'wait_copy_s': 0.0, 'wait_fallback_s': 0.0}
+        self.contour_stats = {'images': 0, 'host_fallback': 0, 'wait_copy_s': 0.0, 'wait_fallback_s': 0.0,
+                              'enqueue_generator_s': 0.0, 'enqueue_stage_s': 0.0, 'host_copies_s': 0.0}
         fallback_lag = 8                    # batches a fall-back task may take before the loop waits for it (host copies of 8 batches)
         if pool is not None and hasattr(pool, '_max_workers'):
             # start the workers now (a spawned process imports numpy / OpenCV / this package: seconds, once), not at the
@@ -400,7 +401,9 @@ class LabelledPairGenerator:
             slot['done'].synchronize()
             self.contour_stats['wait_copy_s'] += time.perf_counter() - t0
             flags = slot['flags'].numpy()
+            t1 = time.perf_counter()
             images, labels = slot['image'].numpy().copy(), slot['label'].numpy().copy()
+            self.contour_stats['host_copies_s'] += time.perf_counter() - t1
             drop = [int(b) for b in numpy.flatnonzero(flags == contours_device.FLAG_DROP)]
             undecided = [int(b) for b in numpy.flatnonzero(flags == contours_device.FLAG_HOST)]
             self.contour_stats['images'] += len(flags)
@@ -454,6 +457,7 @@ class LabelledPairGenerator:
         while True:
             slot = slots[n % n_slots]
             g, st = lanes[n % len(lanes)]
+            t_enq = time.perf_counter()
             with (torch.cuda.stream(st) if st is not None else contextlib.nullcontext()):
                 idx, latents = next(latent_stream)
                 slot['z'].copy_(latents.latent)
@@ -473,7 +477,10 @@ class LabelledPairGenerator:
                 slot['generated'] = torch.cuda.Event()
                 slot['generated'].record(torch.cuda.current_stream(device))
             slot['keep'], slot['stacked'], slot['index'], slot['lane'] = (image_u8, lat, acts), stacked, idx, n % len(lanes)
+            t_stage = time.perf_counter()
             contour_and_copy(slot)
+            self.contour_stats['enqueue_generator_s'] += t_stage - t_enq
+            self.contour_stats['enqueue_stage_s'] += time.perf_counter() - t_stage
             self.stats['pairs'] += B
             self.stats['batches'] += 1
             n += 1
